@@ -1,0 +1,560 @@
+"""ecoracle — CPU restatement (Python big integers) of the reference's batched hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is imported, linked or executed by the
+product (``rustcrypto-elliptic-curves_b200/``); only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may use it, and only as the checker.
+
+Parity status: PINNED.  ``tests/test_oracle_golden.py`` replays every golden vector the
+reference holds for this path (ADD/MUL group vectors, field KATs incl. the risc0 8x32 KATs,
+FIPS 186-4 ECDSA vectors with the flipped-s negative, all 1172 Wycheproof rows, the sm2 d->Q pair
+and SM2DSA vector) from ``tests/golden/*.json`` (scraped from /root/reference by
+``tests/golden/make_golden.py``).
+
+Because every observable output of the path is canonical (SEC1 bytes of a normalised affine
+point, or a boolean), the oracle works in plain affine big-integer arithmetic; functions cite
+the reference file:line whose *behaviour* they restate (paths relative to /root/reference).
+Third-party crates that are not vendored in the reference tree are restated from their published
+behaviour: ecdsa 0.16.9 (hazmat::verify_prehashed, bits2field, Signature range checks),
+elliptic-curve 0.13.8 (BatchInvert/BatchNormalize, sec1 EncodedPoint), crypto-bigint
+0.5.5-risczero.0 — see SURVEY.md App. B.
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+Point = Optional[Tuple[int, int]]  # None = identity
+
+
+@dataclass(frozen=True)
+class Curve:
+    name: str
+    cid: int          # C-ABI curve id (include/ecb200.h)
+    p: int
+    a: int
+    b: int
+    n: int
+    gx: int
+    gy: int
+    fb: int           # field bytes
+    compress: bool    # reference default for To EncodedPoint (k256/src/lib.rs:108-111 etc.)
+    low_s: bool       # k256 rejects high-s (k256/src/ecdsa.rs:201-208)
+
+    @property
+    def G(self) -> Point:
+        return (self.gx, self.gy)
+
+    @property
+    def bits(self) -> int:
+        return self.fb * 8
+
+
+# Constants: SURVEY.md App. A (k256/src/arithmetic/field.rs:312-313, k256/src/lib.rs:76,
+# k256/src/arithmetic/affine.rs:63-75; p256/src/arithmetic.rs:37-59, p256/src/lib.rs:74;
+# p384/src/arithmetic.rs:36-61, p384/src/lib.rs:50; sm2/src/arithmetic.rs:37-58, sm2/src/lib.rs:60)
+K256 = Curve(
+    "k256", 0,
+    p=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEFFFFFC2F,
+    a=0, b=7,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141,
+    gx=0x79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798,
+    gy=0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8,
+    fb=32, compress=True, low_s=True)
+P256 = Curve(
+    "p256", 1,
+    p=0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF,
+    a=-3 % 0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF,
+    b=0x5AC635D8AA3A93E7B3EBBD55769886BC651D06B0CC53B0F63BCE3C3E27D2604B,
+    n=0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551,
+    gx=0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
+    gy=0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5,
+    fb=32, compress=False, low_s=False)
+_P384_P = 2**384 - 2**128 - 2**96 + 2**32 - 1
+P384 = Curve(
+    "p384", 2,
+    p=_P384_P, a=-3 % _P384_P,
+    b=0xB3312FA7E23EE7E4988E056BE3F82D19181D9C6EFE8141120314088F5013875AC656398D8A2ED19D2A85C8EDD3EC2AEF,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFC7634D81F4372DDF581A0DB248B0A77AECEC196ACCC52973,
+    gx=0xAA87CA22BE8B05378EB1C71EF320AD746E1D3B628BA79B9859F741E082542A385502F25DBF55296C3A545E3872760AB7,
+    gy=0x3617DE4A96262C6F5D9E98BF9292DC29F8F41DBD289A147CE9DA3113B5F0B8C00A60B1CE1D7E819D7A431D7C90EA0E5F,
+    fb=48, compress=False, low_s=False)
+_SM2_P = 0xFFFFFFFEFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFF00000000FFFFFFFFFFFFFFFF
+SM2 = Curve(
+    "sm2", 3,
+    p=_SM2_P, a=-3 % _SM2_P,
+    b=0x28E9FA9E9D9F5E344D5A9E4BCF6509A7F39789F515AB8F92DDBCBD414D940E93,
+    n=0xFFFFFFFEFFFFFFFFFFFFFFFFFFFFFFFF7203DF6B21C6052B53BBF40939D54123,
+    gx=0x32C4AE2C1F1981195F9904466A39C9948FE30BBFF2660BE1715A4589334C74C7,
+    gy=0xBC3736A2F4F6779C59BDCEE36B692153D0A9877CC62A474002DF32E52139F0A0,
+    fb=32, compress=False, low_s=False)
+
+CURVES = {c.name: c for c in (K256, P256, P384, SM2)}
+BY_ID = {c.cid: c for c in CURVES.values()}
+
+
+def curve(name_or_id) -> Curve:
+    return CURVES[name_or_id] if isinstance(name_or_id, str) else BY_ID[name_or_id]
+
+
+# ----------------------------------------------------------------------------------------------
+# field helpers
+
+def inv_mod(x: int, m: int) -> int:
+    return pow(x, -1, m)
+
+
+def sqrt_mod(c: Curve, v: int) -> Optional[int]:
+    """sqrt for p = 3 (mod 4) (all four curves): k256 field.rs:220-255, p256 field.rs:385-411,
+    p384 field.rs:95-117, sm2 field.rs `sqrt`."""
+    r = pow(v, (c.p + 1) // 4, c.p)
+    return r if r * r % c.p == v % c.p else None
+
+
+def on_curve(c: Curve, x: int, y: int) -> bool:
+    return (y * y - (x * x * x + c.a * x + c.b)) % c.p == 0
+
+
+# ----------------------------------------------------------------------------------------------
+# group law (affine; identity = None).  Behavioural restatement of the complete formulas
+# k256/src/arithmetic/projective.rs:96-274 and primeorder/src/point_arithmetic.rs:209-317:
+# P+P == double(P), P+(-P) == identity, identity is neutral.
+
+def pt_neg(c: Curve, P: Point) -> Point:
+    return None if P is None else (P[0], (-P[1]) % c.p)
+
+
+def pt_dbl(c: Curve, P: Point) -> Point:
+    if P is None:
+        return None
+    x, y = P
+    if y == 0:
+        return None
+    lam = (3 * x * x + c.a) * inv_mod(2 * y, c.p) % c.p
+    x3 = (lam * lam - 2 * x) % c.p
+    return (x3, (lam * (x - x3) - y) % c.p)
+
+
+def pt_add(c: Curve, P: Point, Q: Point) -> Point:
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    x1, y1 = P
+    x2, y2 = Q
+    if x1 == x2:
+        if (y1 + y2) % c.p == 0:
+            return None
+        return pt_dbl(c, P)
+    lam = (y2 - y1) * inv_mod(x2 - x1, c.p) % c.p
+    x3 = (lam * lam - x1 - x2) % c.p
+    return (x3, (lam * (x1 - x3) - y1) % c.p)
+
+
+def _jac_dbl(c, X, Y, Z):
+    p = c.p
+    if Z == 0 or Y == 0:
+        return (1, 1, 0)
+    YY = Y * Y % p
+    S = 4 * X * YY % p
+    M = (3 * X * X + c.a * pow(Z, 4, p)) % p
+    X3 = (M * M - 2 * S) % p
+    Y3 = (M * (S - X3) - 8 * YY * YY) % p
+    Z3 = 2 * Y * Z % p
+    return (X3, Y3, Z3)
+
+
+def _jac_add_affine(c, X1, Y1, Z1, x2, y2):
+    p = c.p
+    if Z1 == 0:
+        return (x2, y2, 1)
+    Z1Z1 = Z1 * Z1 % p
+    U2 = x2 * Z1Z1 % p
+    S2 = y2 * Z1 * Z1Z1 % p
+    H = (U2 - X1) % p
+    R = (S2 - Y1) % p
+    if H == 0:
+        if R == 0:
+            return _jac_dbl(c, X1, Y1, Z1)
+        return (1, 1, 0)
+    HH = H * H % p
+    HHH = H * HH % p
+    V = X1 * HH % p
+    X3 = (R * R - HHH - 2 * V) % p
+    Y3 = (R * (V - X3) - Y1 * HHH) % p
+    Z3 = Z1 * H % p
+    return (X3, Y3, Z3)
+
+
+def pt_mul(c: Curve, k: int, P: Point) -> Point:
+    """k·P (k reduced mod n first, as a `Scalar` always is).  Result-equivalent to
+    k256 mul.rs:342-393,443-445 and primeorder projective.rs:106-150 (outputs are canonical).
+    Uses Jacobian double-and-add with a single inversion so that 2^16-element checks stay cheap."""
+    k %= c.n
+    if P is None or k == 0:
+        return None
+    x2, y2 = P
+    X, Y, Z = 1, 1, 0
+    for bit in bin(k)[2:]:
+        X, Y, Z = _jac_dbl(c, X, Y, Z)
+        if bit == "1":
+            X, Y, Z = _jac_add_affine(c, X, Y, Z, x2, y2)
+    if Z == 0:
+        return None
+    zi = inv_mod(Z, c.p)
+    zi2 = zi * zi % c.p
+    return (X * zi2 % c.p, Y * zi2 * zi % c.p)
+
+
+def pt_lincomb(c: Curve, terms: Sequence[Tuple[Point, int]]) -> Point:
+    """sum k_i·P_i — k256 mul.rs:313-393 (LinearCombinationExt), primeorder projective.rs:415-420."""
+    acc = None
+    for P, k in terms:
+        acc = pt_add(c, acc, pt_mul(c, k, P))
+    return acc
+
+
+def mul_gen(c: Curve, k: int) -> Point:
+    """MulByGenerator — k256 mul.rs:424-439; primeorder projective.rs:422-431."""
+    return pt_mul(c, k, c.G)
+
+
+def proj_to_affine(c: Curve, X: int, Y: int, Z: int) -> Point:
+    """Homogeneous projective (x = X/Z, y = Y/Z) to affine; Z = 0 -> identity.
+    k256 projective.rs:73-84; primeorder projective.rs:62-74."""
+    if Z % c.p == 0:
+        return None
+    zi = inv_mod(Z, c.p)
+    return (X * zi % c.p, Y * zi % c.p)
+
+
+def batch_normalize(c: Curve, pts: Sequence[Tuple[int, int, int]]) -> List[Point]:
+    """k256 projective.rs:350-379 / primeorder projective.rs:382-413 + BatchInvert (Montgomery trick,
+    SURVEY App. B.6): zero Z replaced by ONE for the product chain, such slots become IDENTITY."""
+    zs = [(z % c.p) or 1 for (_, _, z) in pts]
+    pref = []
+    acc = 1
+    for z in zs:
+        acc = acc * z % c.p
+        pref.append(acc)
+    out: List[Point] = [None] * len(pts)
+    if not pts:
+        return out
+    inv = inv_mod(acc, c.p)
+    for i in range(len(pts) - 1, -1, -1):
+        zi = inv * (pref[i - 1] if i else 1) % c.p
+        inv = inv * zs[i] % c.p
+        X, Y, Z = pts[i]
+        out[i] = None if Z % c.p == 0 else (X * zi % c.p, Y * zi % c.p)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# SEC1 encoding (k256 affine.rs:233-238,272-284; primeorder affine.rs:233-243,340-358)
+
+def sec1_encode(c: Curve, P: Point, compress: Optional[bool] = None) -> bytes:
+    """EncodedPoint bytes: identity = single 00; compressed 02/03||x; uncompressed 04||x||y."""
+    if compress is None:
+        compress = c.compress
+    if P is None:
+        return b"\x00"
+    x, y = P
+    if compress:
+        return bytes([2 + (y & 1)]) + x.to_bytes(c.fb, "big")
+    return b"\x04" + x.to_bytes(c.fb, "big") + y.to_bytes(c.fb, "big")
+
+
+def slot_encode(c: Curve, P: Point, compress: Optional[bool] = None) -> bytes:
+    """Fixed-stride output slot used by the C ABI (include/ecb200.h): SEC1 bytes zero-padded to
+    1+FB (compressed) or 1+2FB (uncompressed); identity = all zeros (== GroupEncoding::to_bytes
+    identity, k256 affine.rs:233-238)."""
+    if compress is None:
+        compress = c.compress
+    size = 1 + (c.fb if compress else 2 * c.fb)
+    e = sec1_encode(c, P, compress)
+    return e + b"\x00" * (size - len(e))
+
+
+def sec1_decode(c: Curve, data: bytes) -> Tuple[bool, Point]:
+    """from_encoded_point (k256 affine.rs:241-270; primeorder affine.rs:164-195) incl. decompress
+    (k256 affine.rs:184-202; primeorder affine.rs:129-150).  Returns (ok, point)."""
+    if len(data) == 1 and data[0] == 0:
+        return True, None
+    if len(data) == 1 + c.fb and data[0] in (2, 3):
+        x = int.from_bytes(data[1:], "big")
+        if x >= c.p:
+            return False, None
+        y = sqrt_mod(c, (x * x * x + c.a * x + c.b) % c.p)
+        if y is None:
+            return False, None
+        if (y & 1) != (data[0] & 1):
+            y = c.p - y
+        return True, (x, y)
+    if len(data) == 1 + 2 * c.fb and data[0] == 4:
+        x = int.from_bytes(data[1:1 + c.fb], "big")
+        y = int.from_bytes(data[1 + c.fb:], "big")
+        if x >= c.p or y >= c.p or not on_curve(c, x, y):
+            return False, None
+        return True, (x, y)
+    return False, None
+
+
+# ----------------------------------------------------------------------------------------------
+# k256 GLV + signed radix-16 (restated so the device decomposition can be checked digit-for-digit)
+
+K256_LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72  # mul.rs:4-5
+K256_BETA = 0x7AE96A2B657C07106E64479EAC3434E99CF0497512F58995C1396C28719501EE    # projective.rs:29-34
+K256_MINUS_B1 = 0xE4437ED6010E88286F547FA90ABFE4C3                                  # mul.rs:135-138
+K256_MINUS_B2 = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFE8A280AC50774346DD765CDA83DB1562C  # mul.rs:140-143
+K256_G1 = 0x3086D221A7D46BCDE86C90E49284EB153DAA8A1471E8CA7FE893209A45DBB031        # mul.rs:145-148
+K256_G2 = 0xE4437ED6010E88286F547FA90ABFE4C4221208AC9DF506C61571B4AE8AC47F71        # mul.rs:150-152
+
+
+def k256_mul_shift_384(a: int, b: int) -> int:
+    """WideScalar::mul_shift_vartime(384) — wide64.rs:64-119: (a*b) >> 384, plus the bit below."""
+    prod = a * b
+    return (prod >> 384) + ((prod >> 383) & 1)
+
+
+def k256_decompose(k: int) -> Tuple[int, int]:
+    """decompose_scalar — mul.rs:260-268.  Returns (r1, r2) as scalars mod n with
+    r1 + r2*lambda == k (mod n)."""
+    n = K256.n
+    c1 = k256_mul_shift_384(k, K256_G1) * K256_MINUS_B1 % n
+    c2 = k256_mul_shift_384(k, K256_G2) * K256_MINUS_B2 % n
+    r2 = (c1 + c2) % n
+    r1 = (k + r2 * (n - K256_LAMBDA)) % n
+    return r1, r2
+
+
+def k256_decompose_signed(k: int) -> Tuple[int, bool, int, bool]:
+    """mul.rs:350-362: (|r1|, r1 negated?, |r2|, r2 negated?) with |ri| < 2^128."""
+    n = K256.n
+    r1, r2 = k256_decompose(k)
+    s1 = r1 > n >> 1
+    s2 = r2 > n >> 1
+    return (n - r1 if s1 else r1, s1, n - r2 if s2 else r2, s2)
+
+
+def radix16_signed(v: int, digits: int) -> List[int]:
+    """Radix16Decomposition::new — mul.rs:281-304 (digits in -8..7, last possibly 8)."""
+    d = [(v >> (4 * i)) & 15 for i in range(digits - 1)] + [0]
+    # reference fills D-1 nibbles (2 per byte) and leaves the last digit for the carry
+    for i in range(digits - 1):
+        carry = (d[i] + 8) >> 4
+        d[i] -= carry << 4
+        d[i + 1] += carry
+    return d
+
+
+def k256_lincomb_reference_algorithm(terms: Sequence[Tuple[Point, int]]) -> Point:
+    """Step-for-step restatement of lincomb() — mul.rs:342-393 (tables, digits, 33 rounds), used to
+    prove that the restated GLV constants / recoding reproduce plain k·P."""
+    c = K256
+    tables = []
+    digs = []
+    for P, k in terms:
+        a1, s1, a2, s2 = k256_decompose_signed(k % c.n)
+        assert a1 < 1 << 128 and a2 < 1 << 128
+        P1 = pt_neg(c, P) if s1 else P
+        Pb = None if P is None else (P[0] * K256_BETA % c.p, P[1])
+        P2 = pt_neg(c, Pb) if s2 else Pb
+        for Pt, a in ((P1, a1), (P2, a2)):
+            t = [None]
+            for j in range(8):
+                t.append(pt_add(c, t[-1], Pt))
+            tables.append(t)
+            digs.append(radix16_signed(a, 33))
+    acc = None
+    for i in range(32, -1, -1):
+        for _ in range(4):
+            acc = pt_dbl(c, acc)
+        for t, d in zip(tables, digs):
+            e = t[abs(d[i])]
+            acc = pt_add(c, acc, pt_neg(c, e) if d[i] < 0 else e)
+    return acc
+
+
+# ----------------------------------------------------------------------------------------------
+# ECDSA verify (ecdsa 0.16.9 hazmat::verify_prehashed + bits2field,
+# call sites k256/src/ecdsa.rs:200-209, p256/src/ecdsa.rs:71-75)
+
+def bits2field(c: Curve, prehash: bytes) -> Optional[bytes]:
+    """len < FB/2 -> Err; shorter -> left-pad with zeros; longer -> keep leftmost FB bytes."""
+    if len(prehash) < c.fb // 2:
+        return None
+    if len(prehash) < c.fb:
+        return b"\x00" * (c.fb - len(prehash)) + prehash
+    return prehash[:c.fb]
+
+
+def reduce_once(c: Curve, v: int) -> int:
+    """Reduce<Uint>::reduce — k256 scalar.rs:700-713, p256 scalar.rs:661-673: one conditional
+    subtraction of n (valid because 2^(8FB) < 2n)."""
+    return v - c.n if v >= c.n else v
+
+
+def verify_prehashed(c: Curve, Q: Point, z_bytes: bytes, r: int, s: int) -> bool:
+    """verify_prehashed(&Q, z, sig): z_bytes is the FB-byte output of bits2field.  Range failures of
+    r/s (rejected at Signature construction in the reference) and invalid public keys (rejected at
+    VerifyingKey construction) return False — in the batch ABI those are per-element data."""
+    if not (1 <= r < c.n and 1 <= s < c.n):
+        return False
+    if Q is None or not (0 <= Q[0] < c.p and 0 <= Q[1] < c.p) or not on_curve(c, Q[0], Q[1]):
+        return False
+    if c.low_s and s > c.n >> 1:           # k256/src/ecdsa.rs:203-205, scalar.rs:519-523
+        return False
+    z = reduce_once(c, int.from_bytes(z_bytes, "big"))
+    w = inv_mod(s, c.n)
+    u1 = z * w % c.n
+    u2 = r * w % c.n
+    R = pt_lincomb(c, [(c.G, u1), (Q, u2)])
+    x = 0 if R is None else R[0]           # AffinePoint::IDENTITY.x == 0 (k256 affine.rs:51-55)
+    return reduce_once(c, x) == r
+
+
+def verify_prehash(c: Curve, Q: Point, prehash: bytes, r: int, s: int) -> bool:
+    """VerifyingKey::verify_prehash (PrehashVerifier) = bits2field + verify_prehashed."""
+    z = bits2field(c, prehash)
+    return False if z is None else verify_prehashed(c, Q, z, r, s)
+
+
+def sm2dsa_verify_prehashed(Q: Point, e_bytes: bytes, r: int, s: int) -> bool:
+    """SM2DSA verify — sm2/src/dsa/verifying.rs:130-168 (prehash must be exactly 32 bytes)."""
+    c = SM2
+    if len(e_bytes) != 32:
+        return False
+    if not (1 <= r < c.n and 1 <= s < c.n):
+        return False
+    e = reduce_once(c, int.from_bytes(e_bytes, "big"))
+    t = (r + s) % c.n
+    if t == 0:
+        return False
+    R = pt_lincomb(c, [(c.G, s), (Q, t)])
+    x1 = 0 if R is None else R[0]
+    return r == (e + reduce_once(c, x1)) % c.n
+
+
+def sm2_z_hash(distid: bytes, Q: Point) -> bytes:
+    """Z = SM3(ENTL || ID || a || b || xG || yG || xA || yA) — sm2/src/lib.rs / distid hashing."""
+    c = SM2
+    h = hashlib.new("sm3")
+    h.update((len(distid) * 8).to_bytes(2, "big") + distid)
+    for v in (c.a, c.b, c.gx, c.gy, Q[0], Q[1]):
+        h.update(v.to_bytes(32, "big"))
+    return h.digest()
+
+
+# ----------------------------------------------------------------------------------------------
+# strict DER (ecdsa::der::Signature::from_der as exercised by the Wycheproof runners)
+
+def der_parse_strict(sig: bytes, c: Curve) -> Optional[Tuple[int, int]]:
+    """SEQUENCE{INTEGER r, INTEGER s}, minimal definite lengths, minimal non-negative INTEGERs, no
+    trailing bytes; values longer than FB bytes are rejected.  Returns (r, s) or None."""
+    def read_len(buf, i):
+        if i >= len(buf):
+            return None
+        b0 = buf[i]
+        i += 1
+        if b0 < 0x80:
+            return b0, i
+        nb = b0 & 0x7F
+        if nb == 0 or nb > 4 or i + nb > len(buf):
+            return None
+        v = int.from_bytes(buf[i:i + nb], "big")
+        if buf[i] == 0 or v < 0x80:
+            return None                      # non-minimal length
+        return v, i + nb
+
+    def read_int(buf, i):
+        if i >= len(buf) or buf[i] != 0x02:
+            return None
+        r = read_len(buf, i + 1)
+        if r is None:
+            return None
+        ln, i = r
+        if ln == 0 or i + ln > len(buf):
+            return None
+        body = buf[i:i + ln]
+        if body[0] & 0x80:
+            return None                      # negative
+        if ln > 1 and body[0] == 0 and not (body[1] & 0x80):
+            return None                      # non-minimal
+        v = int.from_bytes(body, "big")
+        if len(body.lstrip(b"\x00")) > c.fb:
+            return None
+        return v, i + ln
+
+    if len(sig) < 2 or sig[0] != 0x30:
+        return None
+    r = read_len(sig, 1)
+    if r is None:
+        return None
+    ln, i = r
+    if i + ln != len(sig):
+        return None
+    a = read_int(sig, i)
+    if a is None:
+        return None
+    rv, i = a
+    b = read_int(sig, i)
+    if b is None:
+        return None
+    sv, i = b
+    if i != len(sig):
+        return None
+    return rv, sv
+
+
+# ----------------------------------------------------------------------------------------------
+# batch helpers on ABI byte layouts (what tests compare the CUDA path with)
+
+def be(v: int, n: int) -> bytes:
+    return v.to_bytes(n, "big")
+
+
+def batch_mul_gen(c: Curve, k_bytes: bytes, compress=None) -> bytes:
+    fb = c.fb
+    out = bytearray()
+    for i in range(len(k_bytes) // fb):
+        k = int.from_bytes(k_bytes[i * fb:(i + 1) * fb], "big")
+        out += slot_encode(c, mul_gen(c, k), compress)
+    return bytes(out)
+
+
+def batch_mul_var_affine(c: Curve, pts: bytes, inf: Optional[bytes], k_bytes: bytes, compress=None) -> bytes:
+    fb = c.fb
+    n = len(k_bytes) // fb
+    out = bytearray()
+    for i in range(n):
+        x = int.from_bytes(pts[2 * fb * i:2 * fb * i + fb], "big")
+        y = int.from_bytes(pts[2 * fb * i + fb:2 * fb * (i + 1)], "big")
+        P = None if (inf is not None and inf[i]) else (x, y)
+        k = int.from_bytes(k_bytes[i * fb:(i + 1) * fb], "big")
+        out += slot_encode(c, pt_mul(c, k, P), compress)
+    return bytes(out)
+
+
+def batch_mul_var_proj(c: Curve, xyz: bytes, k_bytes: bytes, compress=None) -> bytes:
+    fb = c.fb
+    n = len(k_bytes) // fb
+    out = bytearray()
+    for i in range(n):
+        X, Y, Z = (int.from_bytes(xyz[(3 * i + j) * fb:(3 * i + j + 1) * fb], "big") for j in range(3))
+        P = proj_to_affine(c, X, Y, Z)
+        k = int.from_bytes(k_bytes[i * fb:(i + 1) * fb], "big")
+        out += slot_encode(c, pt_mul(c, k, P), compress)
+    return bytes(out)
+
+
+def batch_verify(c: Curve, q: bytes, z: bytes, rs: bytes) -> bytes:
+    fb = c.fb
+    n = len(z) // fb
+    out = bytearray()
+    for i in range(n):
+        qx = int.from_bytes(q[2 * fb * i:2 * fb * i + fb], "big")
+        qy = int.from_bytes(q[2 * fb * i + fb:2 * fb * (i + 1)], "big")
+        r = int.from_bytes(rs[2 * fb * i:2 * fb * i + fb], "big")
+        s = int.from_bytes(rs[2 * fb * i + fb:2 * fb * (i + 1)], "big")
+        out.append(1 if verify_prehashed(c, (qx, qy), z[i * fb:(i + 1) * fb], r, s) else 0)
+    return bytes(out)
