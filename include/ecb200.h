@@ -1,0 +1,138 @@
+/* ecb200.h — C ABI of the B200-native batched elliptic-curve engine.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of the RustCrypto `elliptic-curves`
+ * workspace (risc0 fork): independent scalar multiplications, batch normalisation, small linear
+ * combinations and ECDSA verify_prehash over secp256k1 (k256) and the primeorder curves P-256,
+ * P-384 and SM2.  The reference has no FFI of its own; its only accelerator precedent is the risc0
+ * zkVM syscall `modmul_u256_denormalized(&U256,&U256,&U256)` (k256/src/arithmetic/field/
+ * field_8x32_risc0.rs:177-193, k256/src/arithmetic/scalar.rs:114-134), which swaps ONE modular
+ * multiplication.  Across PCIe that granularity is useless, so the boundary moves up to whole batches
+ * of the trait-level operations; each entry point cites the reference item it replaces.
+ *
+ * Conventions
+ *   - All integers cross the boundary as big-endian byte strings of FB bytes (FB = 32 for
+ *     K256/P256/SM2, 48 for P384), arrays of structures, one element after another — the layout of
+ *     `FieldBytes` / `Scalar::to_bytes()` / `EncodedPoint` coordinates in the reference.
+ *   - Caller owns every buffer; the library copies and never retains.  Host entry points take host
+ *     pointers (pageable or pinned) and return when the results are in the output buffers.
+ *     `_dev` entry points take device pointers on the context's device and enqueue on `stream`
+ *     (a cudaStream_t cast to void*; NULL = the context's own stream) without synchronising.
+ *   - Return value: 0 on success, negative ecb200_status otherwise (ecb200_last_error gives text).
+ *     Per-element failures are data, not status (ok[i] / invalid[i]), mirroring
+ *     `Result<(), signature::Error>` and `CtOption`.
+ *   - A context is bound to one CUDA device and is thread-compatible (one call at a time).
+ *     One process per GPU creates one context; batches shard by index range across ranks.
+ *   - There is no CPU fallback: every entry point fails with ECB200_ERR_CUDA if no sm_100 device
+ *     is usable.
+ */
+#ifndef ECB200_H
+#define ECB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ecb200_ctx ecb200_ctx;
+
+typedef enum {
+    ECB200_K256 = 0, /* secp256k1  — k256/src/lib.rs:76-111 */
+    ECB200_P256 = 1, /* NIST P-256 — p256/src/lib.rs:74-120 */
+    ECB200_P384 = 2, /* NIST P-384 — p384/src/lib.rs:50-76 */
+    ECB200_SM2 = 3   /* SM2        — sm2/src/lib.rs:60-85 */
+} ecb200_curve;
+
+typedef enum {
+    ECB200_OK = 0,
+    ECB200_ERR_ARG = -1,   /* null pointer, bad curve id, negative count */
+    ECB200_ERR_CUDA = -2,  /* CUDA runtime failure (no device, launch or copy error) */
+    ECB200_ERR_ALLOC = -3  /* out of device or pinned memory */
+} ecb200_status;
+
+/* flags */
+#define ECB200_FLAG_CT 1u           /* secret-scalar path: fixed windows, full table scans, no secret-dependent
+                                       branch or address (mirrors k256 mul.rs:92-127, primeorder projective.rs:127-147) */
+#define ECB200_FLAG_COMPRESSED 2u   /* force 02/03||x output */
+#define ECB200_FLAG_UNCOMPRESSED 4u /* force 04||x||y output; neither flag = the reference default for the curve
+                                       (k256 compressed, k256/src/lib.rs:108-111; others uncompressed) */
+#define ECB200_FLAG_PROJ 8u         /* input points are X||Y||Z homogeneous projective (x = X/Z), 3*FB bytes each */
+
+/* Field bytes of a curve (32 or 48); 0 for an unknown curve. */
+size_t ecb200_field_bytes(int curve);
+/* Output slot size for one encoded point under `flags`: 1+FB (compressed) or 1+2*FB.
+ * A slot holds the SEC1 encoding; the identity is an all-zero slot (tag 00), which is also
+ * GroupEncoding::to_bytes of the identity (k256/src/arithmetic/affine.rs:233-238). */
+size_t ecb200_point_slot_bytes(int curve, uint32_t flags);
+
+/* Create / destroy a context on CUDA device `device`.  Builds the fixed-base tables on the device. */
+int ecb200_init(int device, ecb200_ctx** out);
+void ecb200_destroy(ecb200_ctx* ctx);
+const char* ecb200_last_error(const ecb200_ctx* ctx);
+const char* ecb200_version(void);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches evidence). */
+uint64_t ecb200_launch_count(const ecb200_ctx* ctx);
+/* Block until everything enqueued on the context's stream has finished. */
+int ecb200_sync(ecb200_ctx* ctx);
+
+/* out[i] = SEC1(k[i] * G).  Replaces `ProjectivePoint::mul_by_generator(&k)` + `to_encoded_point`
+ * (k256/src/arithmetic/mul.rs:415-440, primeorder/src/projective.rs:422-431; k256 affine.rs:272-284).
+ * k: n x FB scalars, reduced mod n once like Reduce<Uint>::reduce_bytes (k256 scalar.rs:700-713). */
+int ecb200_mul_gen(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* k, uint8_t* out, uint32_t flags);
+
+/* out[i] = SEC1(k[i] * P[i]).  Replaces `&P * &k` (k256 mul.rs:443-481 -> lincomb N=1;
+ * primeorder/src/projective.rs:106-150) followed by batch normalisation.
+ * pts: n x 2FB (x||y) affine, or n x 3FB with ECB200_FLAG_PROJ; inf: optional n bytes, non-zero marks
+ * the affine identity (ignored with FLAG_PROJ, where Z = 0 is the identity); invalid: optional n bytes,
+ * set to 1 where a point failed validation (coordinate >= p or off-curve; its output is the identity
+ * slot) — the analogue of a failed `AffinePoint::from_encoded_point` (k256 affine.rs:241-270). */
+int ecb200_mul_var(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* pts, const uint8_t* inf, const uint8_t* k,
+                   uint8_t* out, uint8_t* invalid, uint32_t flags);
+
+/* (X:Y:Z) -> (x, y).  Replaces `BatchNormalize<[ProjectivePoint]>::batch_normalize` /
+ * `group::Curve::batch_normalize` (k256/src/arithmetic/projective.rs:325-379,519-525;
+ * primeorder/src/projective.rs:346-413).  xyz: n x 3FB; xy: n x 2FB; inf: n bytes (1 where Z == 0,
+ * xy zeroed = AffinePoint::IDENTITY). */
+int ecb200_batch_normalize(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* xyz, uint8_t* xy, uint8_t* inf);
+
+/* out_point = sum_i k[i] * P[i] (ONE point).  Replaces `LinearCombinationExt::lincomb_ext(&[(P, k)])`
+ * and `LinearCombination::lincomb` (k256 mul.rs:313-393; primeorder/src/projective.rs:415-420).
+ * pts as in ecb200_mul_var; with ECB200_FLAG_PROJ in `out_flags_proj` the result is written as
+ * X||Y||Z (3FB bytes, a partial sum another rank can keep adding to), else as one SEC1 slot. */
+int ecb200_lincomb(ecb200_ctx* ctx, int curve, size_t n_terms, const uint8_t* pts, const uint8_t* k, uint8_t* out_point,
+                   uint32_t flags, uint32_t out_flags_proj);
+
+/* ok[i] = 1 iff the signature verifies.  Replaces `VerifyingKey::verify_prehash` after bits2field, i.e.
+ * `<AffinePoint as VerifyPrimitive>::verify_prehashed(&Q, &z, &sig)` (k256/src/ecdsa.rs:200-209 with the
+ * low-s rule; p256/src/ecdsa.rs:71-75, p384/src/ecdsa.rs default impl; body in ecdsa 0.16.9
+ * hazmat::verify_prehashed).  q: n x 2FB public keys x||y; z: n x FB prehash after bits2field;
+ * rs: n x 2FB r||s.  Keys off the curve / coordinates >= p and r, s outside [1, n-1] give ok = 0
+ * (the reference rejects them when the key / signature is constructed). */
+int ecb200_ecdsa_verify(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* q, const uint8_t* z, const uint8_t* rs,
+                        uint8_t* ok);
+
+/* Test hook: out[i] = a[i] (op) b[i] in the base field (which = 0) or scalar field (which = 1).
+ * op: 0 add, 1 sub, 2 mul, 3 square, 4 negate, 5 invert (0 -> 0), 6 sqrt (base field).
+ * ok[i] = 0 when an input is >= the modulus (from_repr failure) or the root does not exist.
+ * Mirrors the per-op surface the risc0 backend replaces (field_8x32_risc0.rs:139-193) so the
+ * reference's field KATs can be replayed on the device. */
+int ecb200_field_op(ecb200_ctx* ctx, int curve, int which, int op, size_t n, const uint8_t* a, const uint8_t* b,
+                    uint8_t* out, uint8_t* ok);
+
+/* Device-pointer variants: same semantics, buffers already resident in HBM on the context's device,
+ * work enqueued on `stream` (NULL = context stream), no synchronisation.  Scratch memory is owned by
+ * the context and reused, so calls on one context must be stream-ordered. */
+int ecb200_mul_gen_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_k, uint8_t* d_out, uint32_t flags,
+                       void* stream);
+int ecb200_mul_var_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_pts, const uint8_t* d_inf,
+                       const uint8_t* d_k, uint8_t* d_out, uint8_t* d_invalid, uint32_t flags, void* stream);
+int ecb200_batch_normalize_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_xyz, uint8_t* d_xy,
+                               uint8_t* d_inf, void* stream);
+int ecb200_ecdsa_verify_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_q, const uint8_t* d_z,
+                            const uint8_t* d_rs, uint8_t* d_ok, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECB200_H */

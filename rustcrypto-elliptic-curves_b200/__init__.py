@@ -1,0 +1,282 @@
+"""ecb200 — host-side mirror of the reference's batch-able trait surface over the C ABI.
+
+The reference is Rust (no toolchain in this image), so this module plays the role of the wrapper
+crate: same names, argument meaning and error behaviour as the reference operators on the hot
+path, each a thin ctypes call into ``libecb200.so`` (include/ecb200.h).  There is NO CPU fallback:
+if the CUDA library is missing or no B200 is visible, construction raises.
+
+    reference item                                              here
+    ----------------------------------------------------------  ---------------------------------------
+    ProjectivePoint::mul_by_generator(&k)  (k256 mul.rs:415-440) Engine.mul_by_generator_batch(curve, ks)
+    &P * &k  + batch_normalize              (mul.rs:443-481)     Engine.mul_batch(curve, points, ks)
+    BatchNormalize::batch_normalize         (projective.rs:325)  Engine.batch_normalize(curve, xyz)
+    LinearCombinationExt::lincomb_ext       (mul.rs:313-340)     Engine.lincomb(curve, points, ks)
+    VerifyingKey::verify_prehash            (ecdsa.rs:200-209)   Engine.verify_prehash_batch(curve, keys, prehashes, sigs)
+    FieldElement / Scalar ops (test hook)   (field_8x32_risc0.rs) Engine.field_op(curve, which, op, a, b)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libecb200.so")
+
+K256, P256, P384, SM2 = 0, 1, 2, 3
+CURVE_IDS = {"k256": K256, "secp256k1": K256, "p256": P256, "p384": P384, "sm2": SM2}
+
+FLAG_CT = 1
+FLAG_COMPRESSED = 2
+FLAG_UNCOMPRESSED = 4
+FLAG_PROJ = 8
+
+# every symbol include/ecb200.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "ecb200_field_bytes", "ecb200_point_slot_bytes", "ecb200_init", "ecb200_destroy", "ecb200_last_error",
+    "ecb200_version", "ecb200_launch_count", "ecb200_sync", "ecb200_mul_gen", "ecb200_mul_var",
+    "ecb200_batch_normalize", "ecb200_lincomb", "ecb200_ecdsa_verify", "ecb200_field_op", "ecb200_mul_gen_dev",
+    "ecb200_mul_var_dev", "ecb200_batch_normalize_dev", "ecb200_ecdsa_verify_dev",
+]
+
+
+class Ecb200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libecb200.so and declare prototypes.  Raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Ecb200Error("libecb200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                          "there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    u8p, vp, sz, u32, ci = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
+    lib.ecb200_field_bytes.restype = sz
+    lib.ecb200_field_bytes.argtypes = [ci]
+    lib.ecb200_point_slot_bytes.restype = sz
+    lib.ecb200_point_slot_bytes.argtypes = [ci, u32]
+    lib.ecb200_init.argtypes = [ci, ctypes.POINTER(vp)]
+    lib.ecb200_destroy.argtypes = [vp]
+    lib.ecb200_destroy.restype = None
+    lib.ecb200_last_error.argtypes = [vp]
+    lib.ecb200_last_error.restype = ctypes.c_char_p
+    lib.ecb200_version.restype = ctypes.c_char_p
+    lib.ecb200_launch_count.argtypes = [vp]
+    lib.ecb200_launch_count.restype = ctypes.c_uint64
+    lib.ecb200_sync.argtypes = [vp]
+    lib.ecb200_mul_gen.argtypes = [vp, ci, sz, u8p, u8p, u32]
+    lib.ecb200_mul_var.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, u8p, u32]
+    lib.ecb200_batch_normalize.argtypes = [vp, ci, sz, u8p, u8p, u8p]
+    lib.ecb200_lincomb.argtypes = [vp, ci, sz, u8p, u8p, u8p, u32, u32]
+    lib.ecb200_ecdsa_verify.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p]
+    lib.ecb200_field_op.argtypes = [vp, ci, ci, ci, sz, u8p, u8p, u8p, u8p]
+    lib.ecb200_mul_gen_dev.argtypes = [vp, ci, sz, u8p, u8p, u32, vp]
+    lib.ecb200_mul_var_dev.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, u8p, u32, vp]
+    lib.ecb200_batch_normalize_dev.argtypes = [vp, ci, sz, u8p, u8p, u8p, vp]
+    lib.ecb200_ecdsa_verify_dev.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, vp]
+    _lib = lib
+    return lib
+
+
+def curve_id(curve) -> int:
+    return CURVE_IDS[curve] if isinstance(curve, str) else int(curve)
+
+
+def field_bytes(curve) -> int:
+    return 48 if curve_id(curve) == P384 else 32
+
+
+def slot_bytes(curve, flags: int = 0) -> int:
+    cid = curve_id(curve)
+    comp = True if flags & FLAG_COMPRESSED else False if flags & FLAG_UNCOMPRESSED else cid == K256
+    return 1 + (field_bytes(cid) if comp else 2 * field_bytes(cid))
+
+
+def bits2field(curve, prehash: bytes) -> bytes:
+    """ecdsa::hazmat::bits2field: < FB/2 bytes -> error; shorter -> left-pad;
+    longer -> leftmost FB bytes.  Host-side, as in the reference (it is byte shuffling, not arithmetic)."""
+    fb = field_bytes(curve)
+    if len(prehash) < fb // 2:
+        raise ValueError("prehash too short")            # signature::Error in the reference
+    if len(prehash) < fb:
+        return b"\x00" * (fb - len(prehash)) + prehash
+    return prehash[:fb]
+
+
+def _as_buf(b) -> Tuple[ctypes.c_void_p, object]:
+    """bytes / bytearray / numpy uint8 array -> (void*, keep-alive)"""
+    if b is None:
+        return None, None
+    if isinstance(b, bytes):       # zero-copy view of the immutable buffer (inputs only)
+        return ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p), b
+    if isinstance(b, bytearray):
+        arr = (ctypes.c_uint8 * len(b)).from_buffer(b)
+        return ctypes.cast(arr, ctypes.c_void_p), arr
+    if hasattr(b, "ctypes"):      # numpy
+        return ctypes.c_void_p(b.ctypes.data), b
+    raise TypeError("unsupported buffer type %r" % type(b))
+
+
+class Engine:
+    """One context = one GPU (one process per GPU).  Thread-compatible, not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.ecb200_init(int(device), ctypes.byref(h))
+        if rc != 0 or not h:
+            raise Ecb200Error("ecb200_init(device=%d) failed with %d: no usable CUDA device or kernel build mismatch "
+                              "(there is no CPU fallback)" % (device, rc))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ecb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise Ecb200Error("%s failed (%d): %s" % (what, rc, self.lib.ecb200_last_error(self.h).decode()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ecb200_launch_count(self.h))
+
+    def sync(self):
+        self._check(self.lib.ecb200_sync(self.h), "sync")
+
+    # ------------------------------------------------------------------ host-buffer API (bytes in, bytes out)
+    def mul_by_generator_batch(self, curve, ks: bytes, flags: int = 0) -> bytes:
+        """[k_i * G] as SEC1 slots.  ks = n x FB big-endian scalars."""
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = len(ks) // fb
+        out = bytearray(n * slot_bytes(cid, flags))
+        pk, k1 = _as_buf(ks)
+        po, k2 = _as_buf(out)
+        self._check(self.lib.ecb200_mul_gen(self.h, cid, n, pk, po, flags), "mul_gen")
+        return bytes(out)
+
+    def mul_batch(self, curve, points: bytes, ks: bytes, inf: Optional[bytes] = None, flags: int = 0) -> Tuple[bytes, bytes]:
+        """[k_i * P_i] as SEC1 slots, plus the per-element invalid-point flags."""
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = len(ks) // fb
+        out = bytearray(n * slot_bytes(cid, flags))
+        invalid = bytearray(n)
+        pp, a = _as_buf(points)
+        pi, b = _as_buf(inf)
+        pk, c = _as_buf(ks)
+        po, d = _as_buf(out)
+        pv, e = _as_buf(invalid)
+        self._check(self.lib.ecb200_mul_var(self.h, cid, n, pp, pi, pk, po, pv, flags), "mul_var")
+        return bytes(out), bytes(invalid)
+
+    def batch_normalize(self, curve, xyz: bytes) -> Tuple[bytes, bytes]:
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = len(xyz) // (3 * fb)
+        xy = bytearray(n * 2 * fb)
+        inf = bytearray(n)
+        pi, a = _as_buf(xyz)
+        po, b = _as_buf(xy)
+        pf, c = _as_buf(inf)
+        self._check(self.lib.ecb200_batch_normalize(self.h, cid, n, pi, po, pf), "batch_normalize")
+        return bytes(xy), bytes(inf)
+
+    def lincomb(self, curve, points: bytes, ks: bytes, flags: int = 0, out_proj: bool = False) -> bytes:
+        """sum_i k_i * P_i as one SEC1 slot (or X||Y||Z when out_proj)."""
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = len(ks) // fb
+        out = bytearray(3 * fb if out_proj else slot_bytes(cid, flags))
+        pp, a = _as_buf(points)
+        pk, b = _as_buf(ks)
+        po, c = _as_buf(out)
+        self._check(self.lib.ecb200_lincomb(self.h, cid, n, pp, pk, po, flags, FLAG_PROJ if out_proj else 0), "lincomb")
+        return bytes(out)
+
+    def ecdsa_verify(self, curve, q: bytes, z: bytes, rs: bytes) -> bytes:
+        """ok bytes for n x (Q = x||y, z = bits2field(prehash), r||s)."""
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = len(z) // fb
+        ok = bytearray(n)
+        pq, a = _as_buf(q)
+        pz, b = _as_buf(z)
+        pr, c = _as_buf(rs)
+        po, d = _as_buf(ok)
+        self._check(self.lib.ecb200_ecdsa_verify(self.h, cid, n, pq, pz, pr, po), "ecdsa_verify")
+        return bytes(ok)
+
+    def verify_prehash_batch(self, curve, keys: Sequence[Tuple[int, int]], prehashes: Sequence[bytes],
+                             sigs: Sequence[Tuple[int, int]]) -> List[bool]:
+        """Vec<Result<(), Error>> of VerifyingKey::verify_prehash over slices (True = Ok(()))."""
+        cid, fb = curve_id(curve), field_bytes(curve)
+        lim = 1 << (8 * fb)
+        idx, q, z, rs = [], bytearray(), bytearray(), bytearray()
+        res = [False] * len(keys)
+        for i, ((x, y), h, (r, s)) in enumerate(zip(keys, prehashes, sigs)):
+            try:
+                zb = bits2field(cid, h)
+            except ValueError:
+                continue
+            if not (0 <= x < lim and 0 <= y < lim and 0 <= r < lim and 0 <= s < lim):
+                continue
+            idx.append(i)
+            q += x.to_bytes(fb, "big") + y.to_bytes(fb, "big")
+            z += zb
+            rs += r.to_bytes(fb, "big") + s.to_bytes(fb, "big")
+        ok = self.ecdsa_verify(cid, bytes(q), bytes(z), bytes(rs))
+        for j, i in enumerate(idx):
+            res[i] = bool(ok[j])
+        return res
+
+    def field_op(self, curve, which: int, op: int, a: bytes, b: Optional[bytes] = None) -> Tuple[bytes, bytes]:
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = len(a) // fb
+        out = bytearray(n * fb)
+        ok = bytearray(n)
+        pa, k1 = _as_buf(a)
+        pb, k2 = _as_buf(b)
+        po, k3 = _as_buf(out)
+        pk, k4 = _as_buf(ok)
+        self._check(self.lib.ecb200_field_op(self.h, cid, which, op, n, pa, pb, po, pk), "field_op")
+        return bytes(out), bytes(ok)
+
+    # ------------------------------------------------------------------ device-pointer API (torch uint8 CUDA tensors)
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def mul_gen_dev(self, curve, n, d_k, d_out, flags=0, stream=None):
+        self._check(self.lib.ecb200_mul_gen_dev(self.h, curve_id(curve), n, self._ptr(d_k), self._ptr(d_out), flags,
+                                                ctypes.c_void_p(stream) if stream else None), "mul_gen_dev")
+
+    def mul_var_dev(self, curve, n, d_pts, d_inf, d_k, d_out, d_invalid=None, flags=0, stream=None):
+        self._check(self.lib.ecb200_mul_var_dev(self.h, curve_id(curve), n, self._ptr(d_pts), self._ptr(d_inf), self._ptr(d_k),
+                                                self._ptr(d_out), self._ptr(d_invalid), flags,
+                                                ctypes.c_void_p(stream) if stream else None), "mul_var_dev")
+
+    def batch_normalize_dev(self, curve, n, d_xyz, d_xy, d_inf=None, stream=None):
+        self._check(self.lib.ecb200_batch_normalize_dev(self.h, curve_id(curve), n, self._ptr(d_xyz), self._ptr(d_xy),
+                                                        self._ptr(d_inf), ctypes.c_void_p(stream) if stream else None),
+                    "batch_normalize_dev")
+
+    def ecdsa_verify_dev(self, curve, n, d_q, d_z, d_rs, d_ok, stream=None):
+        self._check(self.lib.ecb200_ecdsa_verify_dev(self.h, curve_id(curve), n, self._ptr(d_q), self._ptr(d_z), self._ptr(d_rs),
+                                                     self._ptr(d_ok), ctypes.c_void_p(stream) if stream else None),
+                    "ecdsa_verify_dev")
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous index shard [lo, hi) of rank `rank`: floor(i*n/g) boundaries."""
+    return (rank * n) // world, ((rank + 1) * n) // world

@@ -1,0 +1,505 @@
+// abi.cu — host runtime behind include/ecb200.h: context, device scratch, fixed-base table
+// construction, host<->device staging and the extern "C" entry points.  No arithmetic happens on
+// the host; every entry point fails loudly when CUDA is unavailable.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/ecb200.h"
+#include "launch.h"
+
+namespace ecb {
+uint64_t g_launch_count = 0;
+}
+using namespace ecb;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr size_t CHUNK = (size_t)1 << 20;   // elements per pipelined chunk of the host entry points
+constexpr int NSLOT = 2;                    // double buffering: H2D / kernel / D2H of adjacent chunks overlap
+
+}  // namespace
+
+struct ecb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;           // compute stream of the host entry points
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[NSLOT] = {}, ev_done[NSLOT] = {}, ev_out[NSLOT] = {};
+    const CurveLaunch* cl[4] = {};
+    uint32_t* gtab[4] = {};                  // affine multiples 1..ngtab of G (internal limbs)
+    uint32_t* gentab[4] = {};                // fixed-base window tables (k256)
+    DevBuf proj;                             // projective scratch (n x 3L limbs) — shared by all entry points
+    DevBuf partial, one_point;
+    DevBuf d_in[NSLOT][4], d_out[NSLOT][2];  // staging for host-pointer entry points
+    PinBuf h_in[NSLOT][4], h_out[NSLOT][2];
+    std::string err;
+    uint64_t launches_base = 0;
+};
+
+namespace {
+
+int fail(ecb200_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+#define CU(ctx, call)                                                         \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return fail(ctx, ECB200_ERR_CUDA, #call, e_);  \
+    } while (0)
+
+const CurveLaunch* curve_of(ecb200_ctx* c, int curve) {
+    if (!c || curve < 0 || curve > 3) return nullptr;
+    return c->cl[curve];
+}
+bool resolve_compress(const CurveLaunch* cl, uint32_t flags) {
+    if (flags & ECB200_FLAG_COMPRESSED) return true;
+    if (flags & ECB200_FLAG_UNCOMPRESSED) return false;
+    return cl->compress_default;
+}
+size_t slot_bytes(const CurveLaunch* cl, uint32_t flags) { return 1 + (resolve_compress(cl, flags) ? cl->FB : 2 * cl->FB); }
+
+// Build affine tables of multiples of G on the device with the ordinary kernels:
+// entry e = scalar[e] * G, scalars given as big-endian bytes.
+int build_table(ecb200_ctx* c, const CurveLaunch* cl, const std::vector<uint8_t>& scalars, int entries, uint32_t** out_tab,
+                const std::vector<uint8_t>& gxy) {
+    const int FB = cl->FB, L = cl->L;
+    std::vector<uint8_t> pts((size_t)entries * 2 * FB);
+    for (int e = 0; e < entries; e++) memcpy(&pts[(size_t)e * 2 * FB], gxy.data(), 2 * FB);
+    uint8_t *d_pts = nullptr, *d_k = nullptr;
+    uint32_t* d_proj = nullptr;
+    CU(c, cudaMalloc(&d_pts, pts.size()));
+    CU(c, cudaMalloc(&d_k, scalars.size()));
+    CU(c, cudaMalloc(&d_proj, (size_t)entries * 3 * L * 4));
+    CU(c, cudaMalloc(out_tab, (size_t)entries * 2 * L * 4));
+    CU(c, cudaMemcpyAsync(d_pts, pts.data(), pts.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d_k, scalars.data(), scalars.size(), cudaMemcpyHostToDevice, c->stream));
+    cl->mul_var(c->stream, false, entries, 0, d_pts, nullptr, d_k, d_proj, nullptr);
+    cl->normalize(c->stream, entries, d_proj, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, *out_tab);
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_pts);
+    cudaFree(d_k);
+    cudaFree(d_proj);
+    return 0;
+}
+
+// generator coordinates as canonical bytes
+const char* GX[4] = {
+    "79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798",
+    "6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296",
+    "AA87CA22BE8B05378EB1C71EF320AD746E1D3B628BA79B9859F741E082542A385502F25DBF55296C3A545E3872760AB7",
+    "32C4AE2C1F1981195F9904466A39C9948FE30BBFF2660BE1715A4589334C74C7"};
+const char* GY[4] = {
+    "483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8",
+    "4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5",
+    "3617DE4A96262C6F5D9E98BF9292DC29F8F41DBD289A147CE9DA3113B5F0B8C00A60B1CE1D7E819D7A431D7C90EA0E5F",
+    "BC3736A2F4F6779C59BDCEE36B692153D0A9877CC62A474002DF32E52139F0A0"};
+// 2^256 mod n for secp256k1 (the scalar of window 64 of the fixed-base table)
+const char* K256_2_256_MOD_N = "000000000000000000000000000000014551231950B75FC4402DA1732FC9BEBF";
+
+void hex_to(uint8_t* dst, const char* hex, int nbytes) {
+    for (int i = 0; i < nbytes; i++) {
+        unsigned v;
+        sscanf(hex + 2 * i, "%2x", &v);
+        dst[i] = (uint8_t)v;
+    }
+}
+
+int build_tables(ecb200_ctx* c) {
+    for (int id = 0; id < 4; id++) {
+        const CurveLaunch* cl = c->cl[id];
+        const int FB = cl->FB;
+        std::vector<uint8_t> gxy(2 * FB);
+        hex_to(gxy.data(), GX[id], FB);
+        hex_to(gxy.data() + FB, GY[id], FB);
+        {   // small table: j*G, j = 1..ngtab
+            std::vector<uint8_t> sc((size_t)cl->ngtab * FB, 0);
+            for (int j = 0; j < cl->ngtab; j++) sc[(size_t)j * FB + FB - 1] = (uint8_t)(j + 1);
+            int r = build_table(c, cl, sc, cl->ngtab, &c->gtab[id], gxy);
+            if (r) return r;
+        }
+        if (cl->gen_windows) {   // (j+1) * 16^i * G, i < 65, j < 8
+            const int ne = cl->gen_windows * cl->gen_entries;
+            std::vector<uint8_t> sc((size_t)ne * FB, 0);
+            uint8_t top[32];
+            hex_to(top, K256_2_256_MOD_N, 32);
+            for (int e = 0; e < ne; e++) {
+                int i = e / cl->gen_entries, j = e % cl->gen_entries;
+                uint8_t* s = &sc[(size_t)e * FB];
+                int bit = 4 * i;
+                unsigned v = (unsigned)(j + 1);
+                if (bit < 8 * FB) {
+                    int byte = bit / 8, sh = bit % 8;
+                    unsigned w = v << sh;
+                    s[FB - 1 - byte] |= (uint8_t)w;
+                    if (byte + 1 < FB) s[FB - 2 - byte] |= (uint8_t)(w >> 8);
+                } else {
+                    // (j+1) * (2^256 mod n): small multiple of a 129-bit value, no reduction needed
+                    unsigned carry = 0;
+                    for (int b = FB - 1; b >= 0; b--) {
+                        unsigned t = (unsigned)top[b] * v + carry;
+                        s[b] = (uint8_t)t;
+                        carry = t >> 8;
+                    }
+                }
+            }
+            int r = build_table(c, cl, sc, ne, &c->gentab[id], gxy);
+            if (r) return r;
+        }
+    }
+    return 0;
+}
+
+cudaStream_t pick(ecb200_ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->stream; }
+
+// -------------------------------------------------------------------------------------------
+// device-pointer cores (enqueue only)
+
+int mul_gen_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_k, uint8_t* d_out, uint32_t flags, cudaStream_t s) {
+    CU(c, c->proj.reserve(n * 3 * cl->L * 4));
+    cl->mul_gen(s, (flags & ECB200_FLAG_CT) != 0, (int)n, d_k, c->gentab[cl->id], (uint32_t*)c->proj.p);
+    cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 0, resolve_compress(cl, flags) ? 1 : 0, d_out, nullptr, nullptr);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+int mul_var_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_pts, const uint8_t* d_inf, const uint8_t* d_k,
+                 uint8_t* d_out, uint8_t* d_invalid, uint32_t flags, cudaStream_t s) {
+    CU(c, c->proj.reserve(n * 3 * cl->L * 4));
+    cl->mul_var(s, (flags & ECB200_FLAG_CT) != 0, (int)n, flags, d_pts, (flags & ECB200_FLAG_PROJ) ? nullptr : d_inf, d_k,
+                (uint32_t*)c->proj.p, d_invalid);
+    cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 0, resolve_compress(cl, flags) ? 1 : 0, d_out, nullptr, nullptr);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+int batch_normalize_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_xyz, uint8_t* d_xy, uint8_t* d_inf, cudaStream_t s) {
+    CU(c, c->proj.reserve(n * 3 * cl->L * 4));
+    cl->load_proj(s, (int)n, d_xyz, (uint32_t*)c->proj.p, nullptr);
+    cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 1, 0, d_xy, d_inf, nullptr);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q, const uint8_t* d_z, const uint8_t* d_rs, uint8_t* d_ok, cudaStream_t s) {
+    cl->verify(s, (int)n, d_q, d_z, d_rs, c->gtab[cl->id], d_ok);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------
+// Host-pointer pipeline: the batch is cut into CHUNK-element pieces; piece i is copied into pinned
+// memory and sent H2D on the copy-in stream while piece i-1 computes and piece i-2 drains D2H.
+// in[k]/out[k]: host arrays with per-element byte sizes in_sz[k]/out_sz[k] (0 = unused, NULL allowed).
+template <class Fn>
+int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, const size_t* in_sz, int n_out, uint8_t* const* out,
+                 const size_t* out_sz, Fn&& enqueue) {
+    if (n == 0) return 0;
+    size_t nchunks = (n + CHUNK - 1) / CHUNK;
+    const size_t cap = std::min(n, CHUNK);   // staging capacity in elements
+    for (size_t ch = 0; ch < nchunks + 1; ch++) {
+        if (ch < nchunks) {
+            int slot = (int)(ch % NSLOT);
+            size_t off = ch * CHUNK, cnt = std::min(CHUNK, n - off);
+            // slot reuse: its previous D2H must have drained (host copy-out below waits on it) — ensured
+            // because chunk ch-NSLOT was fully retired in an earlier iteration.
+            for (int k = 0; k < n_in; k++) {
+                if (!in[k] || !in_sz[k]) continue;
+                size_t bytes = cnt * in_sz[k];
+                CU(c, c->d_in[slot][k].reserve(cap * in_sz[k]));
+                CU(c, c->h_in[slot][k].reserve(cap * in_sz[k]));
+                memcpy(c->h_in[slot][k].p, in[k] + off * in_sz[k], bytes);
+                CU(c, cudaMemcpyAsync(c->d_in[slot][k].p, c->h_in[slot][k].p, bytes, cudaMemcpyHostToDevice, c->copy_in));
+            }
+            for (int k = 0; k < n_out; k++) {
+                if (!out[k] || !out_sz[k]) continue;
+                CU(c, c->d_out[slot][k].reserve(cap * out_sz[k]));
+                CU(c, c->h_out[slot][k].reserve(cap * out_sz[k]));
+            }
+            CU(c, cudaEventRecord(c->ev_in[slot], c->copy_in));
+            CU(c, cudaStreamWaitEvent(c->stream, c->ev_in[slot], 0));
+            const uint8_t* di[4];
+            uint8_t* dout_[2];
+            for (int k = 0; k < 4; k++) di[k] = (k < n_in && in[k] && in_sz[k]) ? (const uint8_t*)c->d_in[slot][k].p : nullptr;
+            for (int k = 0; k < 2; k++) dout_[k] = (k < n_out && out[k] && out_sz[k]) ? (uint8_t*)c->d_out[slot][k].p : nullptr;
+            int r = enqueue(cnt, di, dout_, c->stream);
+            if (r) return r;
+            CU(c, cudaEventRecord(c->ev_done[slot], c->stream));
+            CU(c, cudaStreamWaitEvent(c->copy_out, c->ev_done[slot], 0));
+            for (int k = 0; k < n_out; k++) {
+                if (!out[k] || !out_sz[k]) continue;
+                CU(c, cudaMemcpyAsync(c->h_out[slot][k].p, c->d_out[slot][k].p, cnt * out_sz[k], cudaMemcpyDeviceToHost, c->copy_out));
+            }
+            CU(c, cudaEventRecord(c->ev_out[slot], c->copy_out));
+        }
+        if (ch >= 1) {   // retire chunk ch-1: wait for its D2H and copy out of pinned memory
+            size_t pc = ch - 1;
+            int slot = (int)(pc % NSLOT);
+            size_t off = pc * CHUNK, cnt = std::min(CHUNK, n - off);
+            CU(c, cudaEventSynchronize(c->ev_out[slot]));
+            for (int k = 0; k < n_out; k++) {
+                if (!out[k] || !out_sz[k]) continue;
+                memcpy(out[k] + off * out_sz[k], c->h_out[slot][k].p, cnt * out_sz[k]);
+            }
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ===============================================================================================
+extern "C" {
+
+size_t ecb200_field_bytes(int curve) { return curve == ECB200_P384 ? 48 : (curve >= 0 && curve <= 3 ? 32 : 0); }
+size_t ecb200_point_slot_bytes(int curve, uint32_t flags) {
+    size_t fb = ecb200_field_bytes(curve);
+    if (!fb) return 0;
+    bool comp = (flags & ECB200_FLAG_COMPRESSED) ? true : (flags & ECB200_FLAG_UNCOMPRESSED) ? false : (curve == ECB200_K256);
+    return 1 + (comp ? fb : 2 * fb);
+}
+const char* ecb200_version(void) { return "ecb200 0.1 (sm_100a)"; }
+
+int ecb200_init(int device, ecb200_ctx** out) {
+    if (!out) return ECB200_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return ECB200_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ECB200_ERR_CUDA;
+    ecb200_ctx* c = new ecb200_ctx();
+    c->device = device;
+    c->cl[0] = launch_k256();
+    c->cl[1] = launch_p256();
+    c->cl[2] = launch_p384();
+    c->cl[3] = launch_sm2();
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < NSLOT; i++)
+        ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok || build_tables(c) != 0) {
+        fprintf(stderr, "ecb200_init failed: %s (%s)\n", c->err.c_str(), cudaGetErrorString(cudaGetLastError()));
+        ecb200_destroy(c);
+        return ECB200_ERR_CUDA;
+    }
+    c->launches_base = g_launch_count;
+    *out = c;
+    return 0;
+}
+
+void ecb200_destroy(ecb200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 4; i++) {
+        if (c->gtab[i]) cudaFree(c->gtab[i]);
+        if (c->gentab[i]) cudaFree(c->gentab[i]);
+    }
+    c->proj.release();
+    c->partial.release();
+    c->one_point.release();
+    for (int s = 0; s < NSLOT; s++) {
+        for (int k = 0; k < 4; k++) { c->d_in[s][k].release(); c->h_in[s][k].release(); }
+        for (int k = 0; k < 2; k++) { c->d_out[s][k].release(); c->h_out[s][k].release(); }
+        if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]);
+        if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]);
+        if (c->ev_out[s]) cudaEventDestroy(c->ev_out[s]);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
+    delete c;
+}
+
+const char* ecb200_last_error(const ecb200_ctx* c) { return c ? c->err.c_str() : "null context"; }
+uint64_t ecb200_launch_count(const ecb200_ctx* c) { return c ? g_launch_count - c->launches_base : 0; }
+int ecb200_sync(ecb200_ctx* c) {
+    if (!c) return ECB200_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- device-pointer entry points
+int ecb200_mul_gen_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_k, uint8_t* d_out, uint32_t flags, void* stream) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!d_k || !d_out))) return fail(c, ECB200_ERR_ARG, "mul_gen_dev: bad argument");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return mul_gen_core(c, cl, n, d_k, d_out, flags, pick(c, stream));
+}
+int ecb200_mul_var_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_pts, const uint8_t* d_inf, const uint8_t* d_k,
+                       uint8_t* d_out, uint8_t* d_invalid, uint32_t flags, void* stream) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!d_pts || !d_k || !d_out))) return fail(c, ECB200_ERR_ARG, "mul_var_dev: bad argument");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return mul_var_core(c, cl, n, d_pts, d_inf, d_k, d_out, d_invalid, flags, pick(c, stream));
+}
+int ecb200_batch_normalize_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_xyz, uint8_t* d_xy, uint8_t* d_inf, void* stream) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!d_xyz || !d_xy))) return fail(c, ECB200_ERR_ARG, "batch_normalize_dev: bad argument");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return batch_normalize_core(c, cl, n, d_xyz, d_xy, d_inf, pick(c, stream));
+}
+int ecb200_ecdsa_verify_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_q, const uint8_t* d_z, const uint8_t* d_rs,
+                            uint8_t* d_ok, void* stream) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!d_q || !d_z || !d_rs || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_verify_dev: bad argument");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return verify_core(c, cl, n, d_q, d_z, d_rs, d_ok, pick(c, stream));
+}
+
+// ---- host-pointer entry points
+int ecb200_mul_gen(ecb200_ctx* c, int curve, size_t n, const uint8_t* k, uint8_t* out, uint32_t flags) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!k || !out))) return fail(c, ECB200_ERR_ARG, "mul_gen: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[1] = {k};
+    size_t in_sz[1] = {(size_t)cl->FB};
+    uint8_t* o[1] = {out};
+    size_t o_sz[1] = {slot_bytes(cl, flags)};
+    return run_pipeline(c, n, 1, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return mul_gen_core(c, cl, cnt, di[0], dout[0], flags, s);
+    });
+}
+int ecb200_mul_var(ecb200_ctx* c, int curve, size_t n, const uint8_t* pts, const uint8_t* inf, const uint8_t* k, uint8_t* out,
+                   uint8_t* invalid, uint32_t flags) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!pts || !k || !out))) return fail(c, ECB200_ERR_ARG, "mul_var: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const bool proj = (flags & ECB200_FLAG_PROJ) != 0;
+    const uint8_t* in[3] = {pts, k, proj ? nullptr : inf};
+    size_t in_sz[3] = {(size_t)cl->FB * (proj ? 3 : 2), (size_t)cl->FB, 1};
+    uint8_t* o[2] = {out, invalid};
+    size_t o_sz[2] = {slot_bytes(cl, flags), 1};
+    return run_pipeline(c, n, 3, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return mul_var_core(c, cl, cnt, di[0], di[2], di[1], dout[0], dout[1], flags, s);
+    });
+}
+int ecb200_batch_normalize(ecb200_ctx* c, int curve, size_t n, const uint8_t* xyz, uint8_t* xy, uint8_t* inf) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!xyz || !xy))) return fail(c, ECB200_ERR_ARG, "batch_normalize: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[1] = {xyz};
+    size_t in_sz[1] = {(size_t)cl->FB * 3};
+    uint8_t* o[2] = {xy, inf};
+    size_t o_sz[2] = {(size_t)cl->FB * 2, 1};
+    return run_pipeline(c, n, 1, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return batch_normalize_core(c, cl, cnt, di[0], dout[0], dout[1], s);
+    });
+}
+int ecb200_ecdsa_verify(ecb200_ctx* c, int curve, size_t n, const uint8_t* q, const uint8_t* z, const uint8_t* rs, uint8_t* ok) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!q || !z || !rs || !ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_verify: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[3] = {q, z, rs};
+    size_t in_sz[3] = {(size_t)cl->FB * 2, (size_t)cl->FB, (size_t)cl->FB * 2};
+    uint8_t* o[1] = {ok};
+    size_t o_sz[1] = {1};
+    return run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return verify_core(c, cl, cnt, di[0], di[1], di[2], dout[0], s);
+    });
+}
+int ecb200_field_op(ecb200_ctx* c, int curve, int which, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* ok) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || which < 0 || which > 1 || op < 0 || op > 6 || (n && (!a || !out || !ok))) return fail(c, ECB200_ERR_ARG, "field_op: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[2] = {a, b};
+    size_t in_sz[2] = {(size_t)cl->FB, (size_t)cl->FB};
+    uint8_t* o[2] = {out, ok};
+    size_t o_sz[2] = {(size_t)cl->FB, 1};
+    return run_pipeline(c, n, 2, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        cl->field_op(s, (int)cnt, which, op, di[0], di[1], dout[0], dout[1]);
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : fail(c, ECB200_ERR_CUDA, "field_op launch", e);
+    });
+}
+int ecb200_lincomb(ecb200_ctx* c, int curve, size_t n_terms, const uint8_t* pts, const uint8_t* k, uint8_t* out_point, uint32_t flags,
+                   uint32_t out_flags_proj) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || !out_point || (n_terms && (!pts || !k))) return fail(c, ECB200_ERR_ARG, "lincomb: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const int L = cl->L, FB = cl->FB;
+    const bool proj = (flags & ECB200_FLAG_PROJ) != 0;
+    const size_t psz = (size_t)FB * (proj ? 3 : 2);
+    cudaStream_t s = c->stream;
+    CU(c, c->proj.reserve(std::max<size_t>(n_terms, 1) * 3 * L * 4));
+    CU(c, c->partial.reserve((size_t)cl->sum_blocks * 3 * L * 4));
+    CU(c, c->one_point.reserve((size_t)3 * L * 4 + 3 * FB + 256));
+    // terms are processed in CHUNK pieces; each piece's products land in c->proj at its offset
+    for (size_t off = 0; off < n_terms; off += CHUNK) {
+        size_t cnt = std::min(CHUNK, n_terms - off);
+        CU(c, c->d_in[0][0].reserve(cnt * psz));
+        CU(c, c->d_in[0][1].reserve(cnt * FB));
+        CU(c, cudaMemcpyAsync(c->d_in[0][0].p, pts + off * psz, cnt * psz, cudaMemcpyHostToDevice, s));
+        CU(c, cudaMemcpyAsync(c->d_in[0][1].p, k + off * FB, cnt * FB, cudaMemcpyHostToDevice, s));
+        cl->mul_var(s, (flags & ECB200_FLAG_CT) != 0, (int)cnt, flags, (const uint8_t*)c->d_in[0][0].p, nullptr,
+                    (const uint8_t*)c->d_in[0][1].p, (uint32_t*)c->proj.p + off * 3 * L, nullptr);
+        CU(c, cudaStreamSynchronize(s));   // staging buffers are reused by the next piece
+    }
+    uint32_t* d_sum = (uint32_t*)c->one_point.p;
+    uint8_t* d_bytes = (uint8_t*)c->one_point.p + 3 * L * 4;
+    cl->sum(s, (int)n_terms, (const uint32_t*)c->proj.p, (uint32_t*)c->partial.p, d_sum);
+    size_t out_bytes;
+    if (out_flags_proj & ECB200_FLAG_PROJ) {
+        cl->proj_to_bytes(s, 1, d_sum, d_bytes);
+        out_bytes = (size_t)3 * FB;
+    } else {
+        cl->normalize(s, 1, d_sum, 0, resolve_compress(cl, flags) ? 1 : 0, d_bytes, nullptr, nullptr);
+        out_bytes = slot_bytes(cl, flags);
+    }
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(out_point, d_bytes, out_bytes, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+// bigint.cuh — 32-bit-limb multiprecision primitives for sm_100a.
+//
+// Everything the field layers need: PTX carry-chain wrappers (add.cc/addc, sub.cc/subc,
+// mad.lo.cc/madc.hi.cc — ptxas fuses a {mad.lo.cc, madc.hi.cc} pair on the same operands into one
+// IMAD.WIDE.U32(.X), see profiles/), an even/odd-column schoolbook multiplier that keeps two
+// independent carry chains in flight, and small helpers (compare, select, byte I/O).
+//
+// Limb order is little-endian (v[0] least significant), as in the reference's 32-bit backends
+// (k256/src/arithmetic/field/field_8x32_risc0.rs, scalar/wide32.rs).
+//
+// ECB_EMU: when this header is compiled by a plain host compiler for the CPU-only logic tests
+// (tests/emu), the PTX wrappers are replaced by a carry-flag emulation.  The product library is
+// always built by nvcc for sm_100a and contains no host arithmetic path.
+#pragma once
+#include <cstdint>
+
+namespace ecb {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef uint8_t u8;
+
+#if defined(__CUDACC__) && !defined(ECB_EMU)
+#define ECB_DEV __device__ __forceinline__
+#define ECB_HD __host__ __device__ __forceinline__
+#define ECB_UNROLL _Pragma("unroll")
+#else
+#define ECB_DEV inline
+#define ECB_HD inline
+#define ECB_UNROLL
+struct uint4 { u32 x, y, z, w; };
+#endif
+
+// ------------------------------------------------------------------------------------------
+// carry-chain primitives
+#if defined(__CUDA_ARCH__) && !defined(ECB_EMU)
+ECB_DEV u32 add_cc(u32 a, u32 b) { u32 r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ECB_DEV u32 addc_cc(u32 a, u32 b) { u32 r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ECB_DEV u32 addc(u32 a, u32 b) { u32 r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ECB_DEV u32 sub_cc(u32 a, u32 b) { u32 r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ECB_DEV u32 subc_cc(u32 a, u32 b) { u32 r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ECB_DEV u32 subc(u32 a, u32 b) { u32 r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ECB_DEV u32 madlo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ECB_DEV u32 madloc_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ECB_DEV u32 madhi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ECB_DEV u32 madhic_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ECB_DEV u32 madhic(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ECB_DEV u32 mulhi(u32 a, u32 b) { return __umulhi(a, b); }
+ECB_DEV u32 bswap32(u32 x) { return __byte_perm(x, 0, 0x0123); }
+#else
+// host emulation of the PTX condition-code register (tests/emu only)
+static thread_local u32 ecb_cf_ = 0;
+inline u32 add_cc(u32 a, u32 b) { u64 t = (u64)a + b; ecb_cf_ = (u32)(t >> 32); return (u32)t; }
+inline u32 addc_cc(u32 a, u32 b) { u64 t = (u64)a + b + ecb_cf_; ecb_cf_ = (u32)(t >> 32); return (u32)t; }
+inline u32 addc(u32 a, u32 b) { return a + b + ecb_cf_; }
+inline u32 sub_cc(u32 a, u32 b) { u64 t = (u64)a - b; ecb_cf_ = (u32)((t >> 32) & 1); return (u32)t; }
+inline u32 subc_cc(u32 a, u32 b) { u64 t = (u64)a - b - ecb_cf_; ecb_cf_ = (u32)((t >> 32) & 1); return (u32)t; }
+inline u32 subc(u32 a, u32 b) { return a - b - ecb_cf_; }
+inline u32 madlo_cc(u32 a, u32 b, u32 c) { u64 t = (u64)(u32)((u64)a * b) + c; ecb_cf_ = (u32)(t >> 32); return (u32)t; }
+inline u32 madloc_cc(u32 a, u32 b, u32 c) { u64 t = (u64)(u32)((u64)a * b) + c + ecb_cf_; ecb_cf_ = (u32)(t >> 32); return (u32)t; }
+inline u32 madhi_cc(u32 a, u32 b, u32 c) { u64 t = (((u64)a * b) >> 32) + c; ecb_cf_ = (u32)(t >> 32); return (u32)t; }
+inline u32 madhic_cc(u32 a, u32 b, u32 c) { u64 t = (((u64)a * b) >> 32) + c + ecb_cf_; ecb_cf_ = (u32)(t >> 32); return (u32)t; }
+inline u32 madhic(u32 a, u32 b, u32 c) { return (u32)((((u64)a * b) >> 32) + c + ecb_cf_); }
+inline u32 mulhi(u32 a, u32 b) { return (u32)(((u64)a * b) >> 32); }
+inline u32 bswap32(u32 x) { return __builtin_bswap32(x); }
+#endif
+
+// ------------------------------------------------------------------------------------------
+// n-limb helpers (all loops fully unrolled; L is a compile-time constant)
+
+template <int L> ECB_DEV u32 add_n(u32* r, const u32* a, const u32* b) {   // returns carry
+    r[0] = add_cc(a[0], b[0]);
+    ECB_UNROLL
+    for (int i = 1; i < L; i++) r[i] = addc_cc(a[i], b[i]);
+    return addc(0, 0);
+}
+template <int L> ECB_DEV u32 sub_n(u32* r, const u32* a, const u32* b) {   // returns borrow (0/1)
+    r[0] = sub_cc(a[0], b[0]);
+    ECB_UNROLL
+    for (int i = 1; i < L; i++) r[i] = subc_cc(a[i], b[i]);
+    return subc(0, 0) & 1;
+}
+template <int L> ECB_DEV bool is_zero_n(const u32* a) {
+    u32 t = a[0];
+    ECB_UNROLL
+    for (int i = 1; i < L; i++) t |= a[i];
+    return t == 0;
+}
+template <int L> ECB_DEV bool eq_n(const u32* a, const u32* b) {
+    u32 t = a[0] ^ b[0];
+    ECB_UNROLL
+    for (int i = 1; i < L; i++) t |= a[i] ^ b[i];
+    return t == 0;
+}
+// a >= b  (borrow-free subtraction test)
+template <int L> ECB_DEV bool geq_n(const u32* a, const u32* b) {
+    u32 t[L];
+    return sub_n<L>(t, a, b) == 0;
+}
+template <int L> ECB_DEV void copy_n(u32* r, const u32* a) {
+    ECB_UNROLL
+    for (int i = 0; i < L; i++) r[i] = a[i];
+}
+template <int L> ECB_DEV void zero_n(u32* r) {
+    ECB_UNROLL
+    for (int i = 0; i < L; i++) r[i] = 0;
+}
+// r = c ? a : b   (branch-free; SEL in SASS)
+template <int L> ECB_DEV void select_n(u32* r, bool c, const u32* a, const u32* b) {
+    ECB_UNROLL
+    for (int i = 0; i < L; i++) r[i] = c ? a[i] : b[i];
+}
+// r = mask ? a : r  with an all-ones/zero mask (constant-time table scans)
+template <int L> ECB_DEV void cmov_n(u32* r, const u32* a, u32 mask) {
+    ECB_UNROLL
+    for (int i = 0; i < L; i++) r[i] = (a[i] & mask) | (r[i] & ~mask);
+}
+
+// ------------------------------------------------------------------------------------------
+// r[0..2L) = a * b.  Even/odd-column schoolbook: products whose weight i+j is even accumulate in
+// e[], odd-weight products in o[] (o[k] has weight k+1), so every IMAD.WIDE lands on an aligned
+// register pair and two carry chains run independently; r = e + (o << 32) at the end.
+template <int L> ECB_DEV void mul_wide(u32* r, const u32* a, const u32* b) {
+    static_assert(L % 2 == 0, "even limb counts only");
+    u32 e[2 * L], o[2 * L];
+    ECB_UNROLL
+    for (int i = 0; i < 2 * L; i++) { e[i] = 0; o[i] = 0; }
+    ECB_UNROLL
+    for (int i = 0; i < L; i++) {
+        const u32 bi = b[i];
+        if ((i & 1) == 0) {
+            ECB_UNROLL
+            for (int j = 0; j < L; j += 2) {
+                e[i + j] = (j == 0) ? madlo_cc(a[j], bi, e[i + j]) : madloc_cc(a[j], bi, e[i + j]);
+                e[i + j + 1] = madhic_cc(a[j], bi, e[i + j + 1]);
+            }
+            if (i + L < 2 * L) e[i + L] = addc(e[i + L], 0);
+            ECB_UNROLL
+            for (int j = 1; j < L; j += 2) {
+                o[i + j - 1] = (j == 1) ? madlo_cc(a[j], bi, o[i + j - 1]) : madloc_cc(a[j], bi, o[i + j - 1]);
+                o[i + j] = madhic_cc(a[j], bi, o[i + j]);
+            }
+            if (i + L < 2 * L) o[i + L] = addc(o[i + L], 0);
+        } else {
+            ECB_UNROLL
+            for (int j = 0; j < L; j += 2) {
+                o[i + j - 1] = (j == 0) ? madlo_cc(a[j], bi, o[i + j - 1]) : madloc_cc(a[j], bi, o[i + j - 1]);
+                o[i + j] = madhic_cc(a[j], bi, o[i + j]);
+            }
+            if (i + L - 1 < 2 * L) o[i + L - 1] = addc(o[i + L - 1], 0);
+            ECB_UNROLL
+            for (int j = 1; j < L; j += 2) {
+                e[i + j] = (j == 1) ? madlo_cc(a[j], bi, e[i + j]) : madloc_cc(a[j], bi, e[i + j]);
+                e[i + j + 1] = madhic_cc(a[j], bi, e[i + j + 1]);
+            }
+            if (i + L + 1 < 2 * L) e[i + L + 1] = addc(e[i + L + 1], 0);
+        }
+    }
+    r[0] = e[0];
+    r[1] = add_cc(e[1], o[0]);
+    ECB_UNROLL
+    for (int i = 2; i < 2 * L - 1; i++) r[i] = addc_cc(e[i], o[i - 1]);
+    r[2 * L - 1] = addc(e[2 * L - 1], o[2 * L - 2]);
+}
+
+// r[0..2L) = a^2: off-diagonal products once (same even/odd scheme), doubled, plus the diagonal.
+template <int L> ECB_DEV void sqr_wide(u32* r, const u32* a) {
+    static_assert(L % 2 == 0, "even limb counts only");
+    u32 e[2 * L], o[2 * L];
+    ECB_UNROLL
+    for (int i = 0; i < 2 * L; i++) { e[i] = 0; o[i] = 0; }
+    // off-diagonal: sum_{i<j} a[i]*a[j] * 2^(32(i+j))
+    ECB_UNROLL
+    for (int i = 0; i < L - 1; i++) {
+        const u32 ai = a[i];
+        // j = i+1, i+3, ... : weight i+j odd -> o[i+j-1], o[i+j]
+        {
+            bool first = true;
+            ECB_UNROLL
+            for (int j = i + 1; j < L; j += 2) {
+                o[i + j - 1] = first ? madlo_cc(a[j], ai, o[i + j - 1]) : madloc_cc(a[j], ai, o[i + j - 1]);
+                o[i + j] = madhic_cc(a[j], ai, o[i + j]);
+                first = false;
+            }
+            // carry out goes to the next o limb above the last pair touched
+            const int last = i + 1 + 2 * ((L - 1 - (i + 1)) / 2);   // last j used
+            if (i + last + 1 < 2 * L) o[i + last + 1] = addc(o[i + last + 1], 0);
+        }
+        // j = i+2, i+4, ... : weight even -> e[i+j], e[i+j+1]
+        if (i + 2 < L) {
+            bool first = true;
+            ECB_UNROLL
+            for (int j = i + 2; j < L; j += 2) {
+                e[i + j] = first ? madlo_cc(a[j], ai, e[i + j]) : madloc_cc(a[j], ai, e[i + j]);
+                e[i + j + 1] = madhic_cc(a[j], ai, e[i + j + 1]);
+                first = false;
+            }
+            const int last = i + 2 + 2 * ((L - 1 - (i + 2)) / 2);
+            if (i + last + 2 < 2 * L) e[i + last + 2] = addc(e[i + last + 2], 0);
+        }
+    }
+    // t = e + (o << 32)
+    u32 t[2 * L];
+    t[0] = e[0];
+    t[1] = add_cc(e[1], o[0]);
+    ECB_UNROLL
+    for (int i = 2; i < 2 * L - 1; i++) t[i] = addc_cc(e[i], o[i - 1]);
+    t[2 * L - 1] = addc(e[2 * L - 1], o[2 * L - 2]);
+    // t = 2t
+    ECB_UNROLL
+    for (int i = 2 * L - 1; i > 0; i--) t[i] = (t[i] << 1) | (t[i - 1] >> 31);
+    t[0] <<= 1;
+    // r = t + diagonal
+    ECB_UNROLL
+    for (int i = 0; i < L; i++) {
+        r[2 * i] = (i == 0) ? madlo_cc(a[i], a[i], t[0]) : madloc_cc(a[i], a[i], t[2 * i]);
+        r[2 * i + 1] = (i == L - 1) ? madhic(a[i], a[i], t[2 * i + 1]) : madhic_cc(a[i], a[i], t[2 * i + 1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// big-endian byte string <-> little-endian limbs (FB = 4L bytes)
+
+template <int L> ECB_DEV void load_be(u32* v, const u8* p) {
+    ECB_UNROLL
+    for (int i = 0; i < L; i++) {
+        const u8* q = p + 4 * (L - 1 - i);
+        v[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+    }
+}
+template <int L> ECB_DEV void store_be(u8* p, const u32* v) {
+    ECB_UNROLL
+    for (int i = 0; i < L; i++) {
+        u8* q = p + 4 * (L - 1 - i);
+        q[0] = (u8)(v[i] >> 24); q[1] = (u8)(v[i] >> 16); q[2] = (u8)(v[i] >> 8); q[3] = (u8)v[i];
+    }
+}
+// 16-byte aligned variant: p points at 4L bytes, 16-byte aligned (device buffers are)
+template <int L> ECB_DEV void load_be_aligned(u32* v, const u8* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    ECB_UNROLL
+    for (int k = 0; k < L / 4; k++) {
+        uint4 w = q[k];
+        v[L - 1 - 4 * k] = bswap32(w.x);
+        v[L - 2 - 4 * k] = bswap32(w.y);
+        v[L - 3 - 4 * k] = bswap32(w.z);
+        v[L - 4 - 4 * k] = bswap32(w.w);
+    }
+}
+
+}  // namespace ecb

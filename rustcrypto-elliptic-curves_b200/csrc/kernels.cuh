@@ -1,0 +1,394 @@
+// kernels.cuh — per-element bodies of every batch kernel, generic over the curve descriptor.
+//
+// Each body_* function processes the element(s) owned by logical thread `tid` out of `nthreads`;
+// the __global__ wrappers (kernels_impl.cuh) just compute tid.  Keeping the bodies free of CUDA
+// built-ins lets tests/emu run exactly this logic on the CPU in the GPU-less container
+// (logic check only — parity is asserted on the B200 through the C ABI).
+//
+// Device-side data layouts (HBM):
+//   byte inputs / outputs: as the C ABI (include/ecb200.h) — big-endian, AoS, one element after another;
+//   internal projective points: 3L little-endian u32 limbs per element (X|Y|Z, field-internal form,
+//     i.e. Montgomery for the primeorder curves), AoS, 16-byte aligned;
+//   internal affine tables: 2L limbs per entry (x|y).
+#pragma once
+#include "ec.cuh"
+
+namespace ecb {
+
+enum : u32 {
+    F_CT = 1u,             // secret-scalar path: fixed windows, full table scans, no secret-dependent branch/address
+    F_COMPRESSED = 2u,
+    F_UNCOMPRESSED = 4u,
+    F_PROJ = 8u,           // input points are X||Y||Z projective instead of x||y affine
+};
+
+enum : int { NORM_SEC1 = 0, NORM_XY_BYTES = 1, NORM_AFF_LIMBS = 2 };
+
+template <class C> struct Bodies {
+    typedef EC<C> G;
+    typedef typename G::Proj Proj;
+    typedef typename G::Aff Aff;
+    typedef typename G::E E;
+    typedef typename C::F F;
+    typedef typename C::Fn Fn;
+    static constexpr int L = C::L;
+    static constexpr int FB = C::FB;
+
+    ECB_DEV static void store_proj(u32* dst, const Proj& p) {
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) { dst[i] = p.X.v[i]; dst[L + i] = p.Y.v[i]; dst[2 * L + i] = p.Z.v[i]; }
+    }
+    ECB_DEV static void load_proj_limbs(Proj& p, const u32* src) {
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) { p.X.v[i] = src[i]; p.Y.v[i] = src[L + i]; p.Z.v[i] = src[2 * L + i]; }
+    }
+    ECB_DEV static void load_aff_limbs(Aff& a, const u32* src) {
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) { a.x.v[i] = src[i]; a.y.v[i] = src[L + i]; }
+    }
+
+    // ------------------------------------------------------------------ field test hook
+    // which: 0 = base field, 1 = scalar field.  op: 0 add, 1 sub, 2 mul, 3 sqr, 4 neg, 5 inv, 6 sqrt
+    // out = FB bytes canonical; out_ok[i] = 0 when an input was not canonical (>= modulus) or sqrt does not exist
+    template <class FF> ECB_DEV static void field_op_one(int op, const u8* a, const u8* b, u8* out, u8* ok) {
+        typename FF::E x, y, r;
+        u32 t[L];
+        load_be<L>(t, a);
+        bool v = FF::from_limbs(x, t);
+        if (b) { load_be<L>(t, b); v = FF::from_limbs(y, t) && v; } else { y = x; }
+        switch (op) {
+            case 0: FF::add(r, x, y); break;
+            case 1: FF::sub(r, x, y); break;
+            case 2: FF::mul(r, x, y); break;
+            case 3: FF::sqr(r, x); break;
+            case 4: FF::neg(r, x); break;
+            case 5: FF::inv(r, x); break;
+            default: {
+                FF::sqrt_candidate(r, x);
+                typename FF::E c;
+                FF::sqr(c, r);
+                v = v && FF::eq(c, x);
+            }
+        }
+        FF::to_limbs(t, r);
+        store_be<L>(out, t);
+        *ok = v ? 1 : 0;
+    }
+    ECB_DEV static void body_field_op(int tid, int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
+        if (tid >= n) return;
+        const u8* pa = a + (size_t)tid * FB;
+        const u8* pb = b ? b + (size_t)tid * FB : nullptr;
+        if (which == 0) field_op_one<F>(op, pa, pb, out + (size_t)tid * FB, ok + tid);
+        else field_op_one<Fn>(op, pa, pb, out + (size_t)tid * FB, ok + tid);
+    }
+
+    // ------------------------------------------------------------------ variable-base k*P -> projective
+    // pts: n x 2FB (x||y) or n x 3FB (X||Y||Z, F_PROJ); inf: optional n flags (affine identity);
+    // k: n x FB; out: n x 3L limbs.  invalid[i] = 1 when the point fails validation (result = identity).
+    template <bool CT> ECB_DEV static void body_mul_var(int tid, int n, u32 flags, const u8* pts, const u8* inf,
+                                                        const u8* k, u32* out, u8* invalid) {
+        if (tid >= n) return;
+        Proj p;
+        bool ok;
+        if (flags & F_PROJ) {
+            ok = G::load_proj(p, pts + (size_t)tid * 3 * FB);
+        } else {
+            Aff a;
+            ok = G::load_affine(a, pts + (size_t)tid * 2 * FB);
+            G::from_affine(p, a);
+            if (inf && inf[tid]) { ok = true; G::set_identity(p); }
+        }
+        if (!ok) G::set_identity(p);
+        u32 kk[L];
+        G::load_scalar(kk, k + (size_t)tid * FB);
+        Proj r;
+        VarMul<C, CT>::run(r, p, kk);
+        store_proj(out + (size_t)tid * 3 * L, r);
+        if (invalid) invalid[tid] = ok ? 0 : 1;
+    }
+
+    // ------------------------------------------------------------------ projective bytes -> internal limbs
+    ECB_DEV static void body_load_proj(int tid, int n, const u8* xyz, u32* out, u8* invalid) {
+        if (tid >= n) return;
+        Proj p;
+        bool ok = G::load_proj(p, xyz + (size_t)tid * 3 * FB);
+        if (!ok) G::set_identity(p);
+        store_proj(out + (size_t)tid * 3 * L, p);
+        if (invalid) invalid[tid] = ok ? 0 : 1;
+    }
+
+    // ------------------------------------------------------------------ batch normalisation
+    // Montgomery's trick over the EPT elements {tid, tid + nthreads, ...} owned by one thread
+    // (BatchInvert + batch_normalize_generic: k256/src/arithmetic/projective.rs:350-379,
+    // primeorder/src/projective.rs:382-413): zero Z is replaced by ONE in the product chain and the
+    // slot becomes IDENTITY.  One field inversion per thread, 3 mul per element for the trick,
+    // 2 mul for (X*zinv, Y*zinv).
+    static constexpr int EPT = 16;
+    ECB_DEV static void body_normalize(int tid, int nthreads, int n, const u32* proj, int mode, int compress,
+                                       u8* out_bytes, u8* out_inf, u32* out_limbs) {
+        E pref[EPT];
+        E acc;
+        F::set_one(acc);
+        int cnt = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < EPT; j++) {
+            int i = tid + j * nthreads;
+            if (i >= n) break;
+            E z, one;
+            ECB_UNROLL
+            for (int l = 0; l < L; l++) z.v[l] = proj[(size_t)i * 3 * L + 2 * L + l];
+            F::set_one(one);
+            bool zz = F::is_zero(z);
+            F::select(z, zz, one, z);
+            pref[j] = acc;
+            F::mul(acc, acc, z);
+            cnt++;
+        }
+        if (cnt == 0) return;
+        E inv;
+        F::inv(inv, acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = cnt - 1; j >= 0; j--) {
+            int i = tid + j * nthreads;
+            Proj p;
+            load_proj_limbs(p, proj + (size_t)i * 3 * L);
+            bool isinf = F::is_zero(p.Z);
+            E one, z, zinv, x, y;
+            F::set_one(one);
+            F::select(z, isinf, one, p.Z);
+            F::mul(zinv, inv, pref[j]);
+            F::mul(inv, inv, z);
+            F::mul(x, p.X, zinv);
+            F::mul(y, p.Y, zinv);
+            if (mode == NORM_SEC1) {
+                const int stride = compress ? 1 + FB : 1 + 2 * FB;
+                G::encode(out_bytes + (size_t)i * stride, isinf, x, y, compress != 0);
+            } else if (mode == NORM_XY_BYTES) {
+                u32 t[L];
+                u8* o = out_bytes + (size_t)i * 2 * FB;
+                if (isinf) {
+                    for (int b = 0; b < 2 * FB; b++) o[b] = 0;   // AffinePoint::IDENTITY = (0, 0, infinity=1)
+                } else {
+                    F::to_limbs(t, x); store_be<L>(o, t);
+                    F::to_limbs(t, y); store_be<L>(o + FB, t);
+                }
+                if (out_inf) out_inf[i] = isinf ? 1 : 0;
+            } else {
+                u32* o = out_limbs + (size_t)i * 2 * L;
+                ECB_UNROLL
+                for (int l = 0; l < L; l++) { o[l] = isinf ? 0u : x.v[l]; o[L + l] = isinf ? 0u : y.v[l]; }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ sum of points (lincomb tail)
+    // thread-strided partial sums; the wrapper reduces across the block through shared memory
+    ECB_DEV static void body_partial_sum(Proj& acc, int tid, int nthreads, int n, const u32* proj) {
+        G::set_identity(acc);
+        for (int i = tid; i < n; i += nthreads) {
+            Proj p;
+            load_proj_limbs(p, proj + (size_t)i * 3 * L);
+            G::add(acc, acc, p);
+        }
+    }
+
+    // ------------------------------------------------------------------ ECDSA verify
+    // ecdsa::hazmat::verify_prehashed semantics (call sites k256/src/ecdsa.rs:200-209,
+    // p256/src/ecdsa.rs:71-75).  q: x||y, z: FB bytes after bits2field, rs: r||s.
+    // gtab: affine multiples 1..NG of G (NG = 8 for k256, 15 for the primeorder curves), 2L limbs each.
+    ECB_DEV static bool scalar_in_range(const u32* v) {   // 1 <= v < n
+        u32 nn[L];
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) nn[i] = C::n(i);
+        return !is_zero_n<L>(v) && !geq_n<L>(v, nn);
+    }
+    ECB_DEV static bool finish_verify(const Proj& R, const u32* r, bool valid) {
+        // accept <=> Z != 0 and (X == r*Z or (r + n < p and X == (r+n)*Z))   (x mod n == r without inversion)
+        E re, t;
+        bool okr = F::from_limbs(re, r);    // r < n < p
+        F::mul(t, re, R.Z);
+        bool hit = F::eq(t, R.X);
+        u32 pmn[L], nn[L], rn[L];
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) { pmn[i] = C::p_minus_n(i); nn[i] = C::n(i); }
+        bool second = !geq_n<L>(r, pmn);    // r + n < p
+        add_n<L>(rn, r, nn);
+        E rne;
+        F::from_limbs(rne, rn);
+        F::mul(t, rne, R.Z);
+        hit = hit || (second && F::eq(t, R.X));
+        return valid && okr && !F::is_zero(R.Z) && hit;
+    }
+    ECB_DEV static void body_verify(int tid, int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok_out) {
+        if (tid >= n) return;
+        u32 r[L], s[L], zz[L];
+        load_be<L>(r, rs + (size_t)tid * 2 * FB);
+        load_be<L>(s, rs + (size_t)tid * 2 * FB + FB);
+        bool valid = scalar_in_range(r) && scalar_in_range(s);
+        if constexpr (C::LOW_S) {   // k256/src/ecdsa.rs:203-205
+            u32 hn[L];
+            ECB_UNROLL
+            for (int i = 0; i < L; i++) hn[i] = C::half_n(i);
+            valid = valid && geq_n<L>(hn, s);
+        }
+        Aff Q;
+        valid = G::load_affine(Q, q + (size_t)tid * 2 * FB) && valid;
+        if (!valid) { G::generator(Q); s[0] |= 1u; }   // keep the arithmetic well defined; result is masked
+        G::load_scalar(zz, z + (size_t)tid * FB);
+        typename Fn::E sm, wm;
+        Fn::from_limbs(sm, s);
+        Fn::inv(wm, sm);
+        u32 u1[L], u2[L];
+        Fn::mul_plain(u1, zz, wm);
+        Fn::mul_plain(u2, r, wm);
+        Proj R;
+        lincomb_g_q(R, u1, u2, Q, gtab);
+        ok_out[tid] = finish_verify(R, r, valid) ? 1 : 0;
+    }
+
+    // R = u1*G + u2*Q (public inputs: variable time allowed)
+    ECB_DEV static void lincomb_g_q(Proj& R, const u32* u1, const u32* u2, const Aff& Q, const u32* gtab) {
+        Proj pq;
+        G::from_affine(pq, Q);
+        if constexpr (C::A_IS_ZERO) {
+            // 2-term GLV lincomb, the N = 2 case of k256/src/arithmetic/mul.rs:342-393
+            K256Glv::Split sg, sq;
+            K256Glv::decompose(sg, u1);
+            K256Glv::decompose(sq, u2);
+            typename G::template Table<9> tab;
+            G::template build_table<9>(tab, pq);
+            Proj acc, e;
+            G::set_identity(acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int i = 32; i >= 0; i--) {
+                if (i != 32) { G::dbl(acc, acc); G::dbl(acc, acc); G::dbl(acc, acc); G::dbl(acc, acc); }
+                u32 mag, neg;
+                K256Glv::digit(sq.a1, i, mag, neg);
+                e = tab.e[mag];
+                G::cneg(e, neg ^ sq.neg1);
+                G::add(acc, acc, e);
+                K256Glv::digit(sq.a2, i, mag, neg);
+                e = tab.e[mag];
+                K256Glv::endo(e);
+                G::cneg(e, neg ^ sq.neg2);
+                G::add(acc, acc, e);
+                K256Glv::digit(sg.a1, i, mag, neg);
+                if (mag) {
+                    Aff g;
+                    load_aff_limbs(g, gtab + (size_t)(mag - 1) * 2 * L);
+                    E ny;
+                    F::neg(ny, g.y);
+                    F::cmov(g.y, ny, neg ^ sg.neg1);
+                    G::add_mixed(acc, acc, g);
+                }
+                K256Glv::digit(sg.a2, i, mag, neg);
+                if (mag) {
+                    Aff g;
+                    load_aff_limbs(g, gtab + (size_t)(mag - 1) * 2 * L);
+                    E beta, ny;
+                    ECB_UNROLL
+                    for (int l = 0; l < L; l++) beta.v[l] = CurveK256::beta(l);
+                    F::mul(g.x, g.x, beta);
+                    F::neg(ny, g.y);
+                    F::cmov(g.y, ny, neg ^ sg.neg2);
+                    G::add_mixed(acc, acc, g);
+                }
+            }
+            R = acc;
+        } else {
+            // x*k + y*l with shared doublings (primeorder/src/projective.rs:415-420 computes the two
+            // products separately; the sum is the same point)
+            typename G::template Table<16> tab;
+            G::template build_table<16>(tab, pq);
+            Proj acc;
+            G::set_identity(acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int w = 8 * L - 1; w >= 0; w--) {
+                if (w != 8 * L - 1) { G::dbl(acc, acc); G::dbl(acc, acc); G::dbl(acc, acc); G::dbl(acc, acc); }
+                u32 nq = (u2[w >> 3] >> ((w & 7) * 4)) & 15u;
+                G::add(acc, acc, tab.e[nq]);
+                u32 ng = (u1[w >> 3] >> ((w & 7) * 4)) & 15u;
+                if (ng) {
+                    Aff g;
+                    load_aff_limbs(g, gtab + (size_t)(ng - 1) * 2 * L);
+                    G::add_mixed(acc, acc, g);
+                }
+            }
+            R = acc;
+        }
+    }
+
+    // ------------------------------------------------------------------ fixed-base k*G -> projective
+    // k256: 65 signed radix-16 digits, table tab[i][j] = (j+1) * 16^i * G affine (65 x 8 entries),
+    // 65 mixed additions and no doublings (the reference spaces 33 tables by 2^8 and pays 4 doublings,
+    // k256/src/arithmetic/mul.rs:397-439).  Other curves: G*k through the generic multiplication,
+    // as primeorder/src/projective.rs:422-431 does.
+    template <bool CT> ECB_DEV static void body_mul_gen(int tid, int n, const u8* k, const u32* tab, u32* out) {
+        if (tid >= n) return;
+        u32 kk[L];
+        G::load_scalar(kk, k + (size_t)tid * FB);
+        Proj r;
+        if constexpr (C::A_IS_ZERO) {
+            u32 kb[L + 1];
+            kb[0] = add_cc(kk[0], 0x88888888u);
+            ECB_UNROLL
+            for (int i = 1; i < L; i++) kb[i] = addc_cc(kk[i], 0x88888888u);
+            kb[L] = addc(0u, 0u);
+            G::set_identity(r);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int i = 0; i < 65; i++) {
+                u32 mag, neg;
+                if (i == 64) { mag = kb[8]; neg = 0; }
+                else {
+                    int d = (int)((kb[i >> 3] >> ((i & 7) * 4)) & 15u) - 8;
+                    neg = (u32)(d >> 31);
+                    mag = (u32)((d ^ (int)neg) - (int)neg);
+                }
+                const u32* win = tab + (size_t)i * 8 * 2 * L;
+                Aff g;
+                if constexpr (CT) {
+                    F::set_zero(g.x); F::set_zero(g.y);
+                    for (u32 j = 1; j <= 8; j++) {
+                        Aff c;
+                        load_aff_limbs(c, win + (size_t)(j - 1) * 2 * L);
+                        u32 m = (u32)0 - (u32)(j == mag);
+                        F::cmov(g.x, c.x, m); F::cmov(g.y, c.y, m);
+                    }
+                    E ny;
+                    F::neg(ny, g.y);
+                    F::cmov(g.y, ny, neg);
+                    Proj sum;
+                    G::add_mixed(sum, r, g);
+                    G::cmov(r, sum, (u32)0 - (u32)(mag != 0));
+                } else {
+                    if (mag) {
+                        load_aff_limbs(g, win + (size_t)(mag - 1) * 2 * L);
+                        E ny;
+                        F::neg(ny, g.y);
+                        F::cmov(g.y, ny, neg);
+                        G::add_mixed(r, r, g);
+                    }
+                }
+            }
+        } else {
+            Aff g;
+            G::generator(g);
+            Proj pg;
+            G::from_affine(pg, g);
+            VarMul<C, CT>::run(r, pg, kk);
+        }
+        store_proj(out + (size_t)tid * 3 * L, r);
+    }
+};
+
+}  // namespace ecb

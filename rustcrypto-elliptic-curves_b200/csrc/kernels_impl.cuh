@@ -1,0 +1,170 @@
+// kernels_impl.cuh — __global__ wrappers around the bodies in kernels.cuh and the launcher table
+// for one curve.  Included by exactly one translation unit per curve (curve_*.cu).
+#pragma once
+#include "kernels.cuh"
+#include "launch.h"
+
+namespace ecb {
+
+constexpr int BLK = 128;   // threads per CTA of the arithmetic kernels (register-heavy: 2-4 CTAs per SM)
+
+template <class C> __global__ void __launch_bounds__(BLK) k_field_op(int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
+    Bodies<C>::body_field_op(blockIdx.x * BLK + threadIdx.x, n, which, op, a, b, out, ok);
+}
+template <class C, bool CT> __global__ void __launch_bounds__(BLK) k_mul_var(int n, u32 flags, const u8* pts, const u8* inf, const u8* k, u32* proj, u8* invalid) {
+    Bodies<C>::template body_mul_var<CT>(blockIdx.x * BLK + threadIdx.x, n, flags, pts, inf, k, proj, invalid);
+}
+template <class C, bool CT> __global__ void __launch_bounds__(BLK) k_mul_gen(int n, const u8* k, const u32* tab, u32* proj) {
+    Bodies<C>::template body_mul_gen<CT>(blockIdx.x * BLK + threadIdx.x, n, k, tab, proj);
+}
+template <class C> __global__ void __launch_bounds__(BLK) k_load_proj(int n, const u8* xyz, u32* proj, u8* invalid) {
+    Bodies<C>::body_load_proj(blockIdx.x * BLK + threadIdx.x, n, xyz, proj, invalid);
+}
+template <class C> __global__ void __launch_bounds__(BLK) k_normalize(int n, const u32* proj, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
+    Bodies<C>::body_normalize(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, proj, mode, compress, out_bytes, out_inf, out_limbs);
+}
+template <class C> __global__ void __launch_bounds__(BLK) k_verify(int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok) {
+    Bodies<C>::body_verify(blockIdx.x * BLK + threadIdx.x, n, q, z, rs, gtab, ok);
+}
+template <class C> __global__ void __launch_bounds__(BLK) k_proj_to_bytes(int n, const u32* proj, u8* xyz) {
+    int tid = blockIdx.x * BLK + threadIdx.x;
+    if (tid >= n) return;
+    typedef Bodies<C> B;
+    typename B::Proj p;
+    B::load_proj_limbs(p, proj + (size_t)tid * 3 * C::L);
+    u32 t[C::L];
+    C::F::to_limbs(t, p.X); store_be<C::L>(xyz + (size_t)tid * 3 * C::FB, t);
+    C::F::to_limbs(t, p.Y); store_be<C::L>(xyz + (size_t)tid * 3 * C::FB + C::FB, t);
+    C::F::to_limbs(t, p.Z); store_be<C::L>(xyz + (size_t)tid * 3 * C::FB + 2 * C::FB, t);
+}
+// block-level sum of projective points: thread-strided partials, then a shared-memory tree
+template <class C> __global__ void __launch_bounds__(BLK) k_sum(int n, const u32* proj, u32* out) {
+    typedef Bodies<C> B;
+    typedef typename B::Proj Proj;
+    __shared__ u32 sh[BLK * 3 * C::L];
+    Proj acc;
+    B::body_partial_sum(acc, blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, proj);
+    B::store_proj(sh + threadIdx.x * 3 * C::L, acc);
+    __syncthreads();
+    for (int stride = BLK / 2; stride > 0; stride >>= 1) {
+        if ((int)threadIdx.x < stride) {
+            Proj a, b;
+            B::load_proj_limbs(a, sh + threadIdx.x * 3 * C::L);
+            B::load_proj_limbs(b, sh + (threadIdx.x + stride) * 3 * C::L);
+            EC<C>::add(a, a, b);
+            B::store_proj(sh + threadIdx.x * 3 * C::L, a);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 3 * C::L; i++) out[(size_t)blockIdx.x * 3 * C::L + i] = sh[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// secp256k1 fixed-base kernel with the 65x8 affine table staged in shared memory by one TMA bulk
+// copy per CTA (cp.async.bulk global -> shared, completion on an mbarrier; UBLKCP in SASS).
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+template <class C, bool CT> __global__ void __launch_bounds__(BLK) k_mul_gen_smem(int n, const u8* k, const u32* tab, u32 tab_bytes, u32* proj) {
+    extern __shared__ __align__(128) u32 stab[];
+    __shared__ __align__(8) unsigned long long bar;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar)), "r"(tab_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_addr(stab)), "l"(tab), "r"(tab_bytes), "r"(smem_addr(&bar)) : "memory");
+    }
+    u32 done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_addr(&bar)) : "memory");
+    }
+    Bodies<C>::template body_mul_gen<CT>(blockIdx.x * BLK + threadIdx.x, n, k, stab, proj);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class C> struct Launch {
+    static int grid(int n) { return (n + BLK - 1) / BLK; }
+
+    static void field_op(cudaStream_t s, int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
+        if (n <= 0) return;
+        k_field_op<C><<<grid(n), BLK, 0, s>>>(n, which, op, a, b, out, ok);
+        g_launch_count++;
+    }
+    static void mul_var(cudaStream_t s, bool ct, int n, u32 flags, const u8* pts, const u8* inf, const u8* k, u32* proj, u8* invalid) {
+        if (n <= 0) return;
+        if (ct) k_mul_var<C, true><<<grid(n), BLK, 0, s>>>(n, flags, pts, inf, k, proj, invalid);
+        else k_mul_var<C, false><<<grid(n), BLK, 0, s>>>(n, flags, pts, inf, k, proj, invalid);
+        g_launch_count++;
+    }
+    static void mul_gen(cudaStream_t s, bool ct, int n, const u8* k, const u32* tab, u32* proj) {
+        if (n <= 0) return;
+        if constexpr (C::A_IS_ZERO) {
+            const u32 bytes = 65u * 8u * 2u * C::L * 4u;
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(k_mul_gen_smem<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                cudaFuncSetAttribute(k_mul_gen_smem<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                attr_set = true;
+            }
+            if (ct) k_mul_gen_smem<C, true><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
+            else k_mul_gen_smem<C, false><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
+        } else {
+            if (ct) k_mul_gen<C, true><<<grid(n), BLK, 0, s>>>(n, k, tab, proj);
+            else k_mul_gen<C, false><<<grid(n), BLK, 0, s>>>(n, k, tab, proj);
+        }
+        g_launch_count++;
+    }
+    static void load_proj(cudaStream_t s, int n, const u8* xyz, u32* proj, u8* invalid) {
+        if (n <= 0) return;
+        k_load_proj<C><<<grid(n), BLK, 0, s>>>(n, xyz, proj, invalid);
+        g_launch_count++;
+    }
+    static void normalize(cudaStream_t s, int n, const u32* proj, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
+        if (n <= 0) return;
+        // elements per thread: as few as keeps >= ~4 CTAs per SM busy, at most EPT
+        int ept = (n + 148 * 4 * BLK - 1) / (148 * 4 * BLK);
+        if (ept < 1) ept = 1;
+        if (ept > Bodies<C>::EPT) ept = Bodies<C>::EPT;
+        int threads = (n + ept - 1) / ept;
+        k_normalize<C><<<grid(threads), BLK, 0, s>>>(n, proj, mode, compress, out_bytes, out_inf, out_limbs);
+        g_launch_count++;
+    }
+    static constexpr int SUM_BLOCKS = 148;
+    static void sum(cudaStream_t s, int n, const u32* proj, u32* partial, u32* out) {
+        int blocks = grid(n);
+        if (blocks > SUM_BLOCKS) blocks = SUM_BLOCKS;
+        if (blocks < 1) blocks = 1;
+        if (blocks == 1) {
+            k_sum<C><<<1, BLK, 0, s>>>(n, proj, out);
+            g_launch_count++;
+        } else {
+            k_sum<C><<<blocks, BLK, 0, s>>>(n, proj, partial);
+            k_sum<C><<<1, BLK, 0, s>>>(blocks, partial, out);
+            g_launch_count += 2;
+        }
+    }
+    static void proj_to_bytes(cudaStream_t s, int n, const u32* proj, u8* xyz) {
+        if (n <= 0) return;
+        k_proj_to_bytes<C><<<grid(n), BLK, 0, s>>>(n, proj, xyz);
+        g_launch_count++;
+    }
+    static void verify(cudaStream_t s, int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok) {
+        if (n <= 0) return;
+        k_verify<C><<<grid(n), BLK, 0, s>>>(n, q, z, rs, gtab, ok);
+        g_launch_count++;
+    }
+    static const CurveLaunch* table() {
+        static const CurveLaunch t = {
+            C::ID, C::L, C::FB, C::A_IS_ZERO ? 8 : 15, C::A_IS_ZERO ? 65 : 0, C::A_IS_ZERO ? 8 : 0, C::COMPRESS_DEFAULT,
+            &field_op, &mul_var, &mul_gen, &load_proj, &normalize, &sum, &proj_to_bytes, &verify, SUM_BLOCKS};
+        return &t;
+    }
+};
+
+}  // namespace ecb

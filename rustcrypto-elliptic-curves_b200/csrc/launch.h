@@ -1,0 +1,41 @@
+// launch.h — per-curve launcher table: the only interface between the host runtime (abi.cu) and
+// the curve translation units (curve_*.cu), so each curve compiles in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ecb {
+
+struct CurveLaunch {
+    int id;
+    int L;        // 32-bit limbs per field element
+    int FB;       // field bytes
+    int ngtab;    // entries of the small affine generator table used by verify (8 or 15)
+    int gen_windows, gen_entries;   // fixed-base table shape (k256: 65 x 8; others 0)
+    bool compress_default;
+
+    void (*field_op)(cudaStream_t s, int n, int which, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* ok);
+    void (*mul_var)(cudaStream_t s, bool ct, int n, uint32_t flags, const uint8_t* pts, const uint8_t* inf,
+                    const uint8_t* k, uint32_t* proj, uint8_t* invalid);
+    void (*mul_gen)(cudaStream_t s, bool ct, int n, const uint8_t* k, const uint32_t* gentab, uint32_t* proj);
+    void (*load_proj)(cudaStream_t s, int n, const uint8_t* xyz, uint32_t* proj, uint8_t* invalid);
+    void (*normalize)(cudaStream_t s, int n, const uint32_t* proj, int mode, int compress, uint8_t* out_bytes,
+                      uint8_t* out_inf, uint32_t* out_limbs);
+    // sum n projective points into out (3L limbs); partial = scratch of sum_blocks()*3L limbs
+    void (*sum)(cudaStream_t s, int n, const uint32_t* proj, uint32_t* partial, uint32_t* out);
+    void (*proj_to_bytes)(cudaStream_t s, int n, const uint32_t* proj, uint8_t* xyz);
+    void (*verify)(cudaStream_t s, int n, const uint8_t* q, const uint8_t* z, const uint8_t* rs, const uint32_t* gtab,
+                   uint8_t* ok);
+    // launches issued by the last call of each launcher are counted by the callee through this hook
+    int sum_blocks;
+};
+
+const CurveLaunch* launch_k256();
+const CurveLaunch* launch_p256();
+const CurveLaunch* launch_p384();
+const CurveLaunch* launch_sm2();
+
+// incremented by every kernel launch issued through the launchers (host side, not thread safe)
+extern uint64_t g_launch_count;
+
+}  // namespace ecb

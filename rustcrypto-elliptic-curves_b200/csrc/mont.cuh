@@ -1,0 +1,206 @@
+// mont.cuh — word-by-word Montgomery fields on 32-bit limbs (L = 8 or 12), always reduced.
+//
+// One template serves every modulus the primeorder path needs:
+//   base fields  P-256 (p256/src/arithmetic/field.rs:240-319, hand-written 4x64 Montgomery),
+//                P-384 / SM2 (fiat-crypto word-by-word Montgomery, p384/src/arithmetic/field/p384_64.rs:146,
+//                sm2/src/arithmetic/field/sm2_64.rs via primeorder/src/field.rs:48-268);
+//   scalar fields of all four curves (the reference uses Barrett for p256, p256/src/arithmetic/scalar/
+//                scalar64.rs:39-62, and wide reduction for k256, k256/src/arithmetic/scalar/wide32.rs — results
+//                are canonical integers either way, so a Montgomery multiplier is observably identical).
+// Parameters come from a generated struct P (curve_consts.cuh): L, p(i), n0 = -p^-1 mod 2^32,
+// one(i) = R mod p, r2(i) = R^2 mod p.
+#pragma once
+#include "bigint.cuh"
+#include "fp_k256.cuh"   // Fe<L>
+
+namespace ecb {
+
+template <class P> struct Mont {
+    static constexpr int L = P::L;
+    typedef Fe<P::L> E;
+    static constexpr bool MONT = true;
+    typedef P Params;
+
+    ECB_DEV static void set_zero(E& r) { zero_n<L>(r.v); }
+    ECB_DEV static void set_one(E& r) {
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) r.v[i] = P::one(i);
+    }
+    ECB_DEV static bool is_zero(const E& a) { return is_zero_n<L>(a.v); }
+    ECB_DEV static bool eq(const E& a, const E& b) { return eq_n<L>(a.v, b.v); }
+    ECB_DEV static void cmov(E& r, const E& a, u32 mask) { cmov_n<L>(r.v, a.v, mask); }
+    ECB_DEV static void select(E& r, bool c, const E& a, const E& b) { select_n<L>(r.v, c, a.v, b.v); }
+
+    // v + carry*2^(32L) in [0, 2p) -> [0, p)
+    ECB_DEV static void final_sub(u32* r, const u32* v, u32 carry) {
+        u32 u[L];
+        u[0] = sub_cc(v[0], P::p(0));
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) u[i] = subc_cc(v[i], P::p(i));
+        u32 bw = subc(0u, 0u) & 1u;
+        select_n<L>(r, (carry != 0) || (bw == 0), u, v);
+    }
+
+    // Montgomery reduction of t[0..2L): r = t * R^-1 mod p   (t < p * R)
+    ECB_DEV static void redc(u32* r, u32* t) {
+        // Row i adds m_i * p at limb i as two aligned-pair carry chains (even j, odd j).  The chain
+        // carry-outs (weight i+L and i+L+1) never feed a later m_i, so they are collected in cy[]
+        // and added once at the end instead of being rippled to the top in every row.
+        u32 cy[L + 1];
+        ECB_UNROLL
+        for (int i = 0; i <= L; i++) cy[i] = 0;
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) {
+            const u32 m = t[i] * P::n0;
+            ECB_UNROLL
+            for (int j = 0; j < L; j += 2) {
+                t[i + j] = (j == 0) ? madlo_cc(m, P::p(j), t[i + j]) : madloc_cc(m, P::p(j), t[i + j]);
+                t[i + j + 1] = madhic_cc(m, P::p(j), t[i + j + 1]);
+            }
+            cy[i] = addc(cy[i], 0u);            // weight L + i
+            ECB_UNROLL
+            for (int j = 1; j < L; j += 2) {
+                t[i + j] = (j == 1) ? madlo_cc(m, P::p(j), t[i + j]) : madloc_cc(m, P::p(j), t[i + j]);
+                t[i + j + 1] = madhic_cc(m, P::p(j), t[i + j + 1]);
+            }
+            cy[i + 1] = addc(cy[i + 1], 0u);    // weight L + i + 1
+        }
+        u32 v[L];
+        v[0] = add_cc(t[L], cy[0]);
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) v[i] = addc_cc(t[L + i], cy[i]);
+        u32 top = addc(cy[L], 0u);
+        final_sub(r, v, top);
+    }
+
+    ECB_DEV static void mul(E& r, const E& a, const E& b) {
+        u32 t[2 * L];
+        mul_wide<L>(t, a.v, b.v);
+        redc(r.v, t);
+    }
+    ECB_DEV static void sqr(E& r, const E& a) {
+        u32 t[2 * L];
+        sqr_wide<L>(t, a.v);
+        redc(r.v, t);
+    }
+    ECB_DEV static void add(E& r, const E& a, const E& b) {
+        u32 v[L];
+        u32 c = add_n<L>(v, a.v, b.v);
+        final_sub(r.v, v, c);
+    }
+    ECB_DEV static void sub(E& r, const E& a, const E& b) {
+        u32 v[L], u[L];
+        u32 bw = sub_n<L>(v, a.v, b.v);
+        u[0] = add_cc(v[0], P::p(0));
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) u[i] = addc_cc(v[i], P::p(i));
+        select_n<L>(r.v, bw != 0, u, v);
+    }
+    ECB_DEV static void neg(E& r, const E& a) {
+        E z;
+        set_zero(z);
+        sub(r, z, a);
+    }
+    ECB_DEV static void dbl(E& r, const E& a) { add(r, a, a); }
+    // small constant multiples by addition chains (only 2,3,4,8 are needed by the formulas)
+    ECB_DEV static void mul_small(E& r, const E& a, u32 k) {
+        E t;
+        if (k == 2) { dbl(r, a); }
+        else if (k == 3) { dbl(t, a); add(r, t, a); }
+        else if (k == 4) { dbl(t, a); dbl(r, t); }
+        else if (k == 8) { dbl(t, a); dbl(t, t); dbl(r, t); }
+        else {   // generic double-and-add, k >= 1
+            E acc = a;
+            int top = 31;
+            while (!((k >> top) & 1)) top--;
+            for (int i = top - 1; i >= 0; i--) { dbl(acc, acc); if ((k >> i) & 1) add(acc, acc, a); }
+            r = acc;
+        }
+    }
+
+    // plain integer limbs (< p) -> Montgomery form; false when the input is >= p
+    ECB_DEV static bool from_limbs(E& r, const u32* v) {
+        u32 pp[L];
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) pp[i] = P::p(i);
+        bool ok = !geq_n<L>(v, pp);
+        E a, r2;
+        copy_n<L>(a.v, v);
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) r2.v[i] = P::r2(i);
+        mul(r, a, r2);
+        return ok;
+    }
+    // Montgomery form -> canonical integer limbs
+    ECB_DEV static void to_limbs(u32* v, const E& a) {
+        u32 t[2 * L];
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) { t[i] = a.v[i]; t[L + i] = 0; }
+        redc(v, t);
+    }
+    ECB_DEV static bool is_odd(const E& a) {   // canonical LSB (primeorder/src/field.rs:169-172)
+        u32 v[L];
+        to_limbs(v, a);
+        return v[0] & 1;
+    }
+    // mixed-domain product: plain x times Montgomery-form y gives plain x*y (mod p)
+    ECB_DEV static void mul_plain(u32* r, const u32* x_plain, const E& y_mont) {
+        E a, o;
+        copy_n<L>(a.v, x_plain);
+        mul(o, a, y_mont);
+        copy_n<L>(r, o.v);
+    }
+
+    ECB_DEV static void sqr_n(E& r, const E& a, int n) {
+        r = a;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int i = 0; i < n; i++) sqr(r, r);
+    }
+
+    // r = a^e for the public exponent e = p - 2 - (extra) given as limbs; 4-bit fixed window.
+    ECB_DEV static void pow_limbs(E& r, const E& a, const u32* e) {
+        E tab[16];
+        set_one(tab[0]);
+        tab[1] = a;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int i = 2; i < 16; i++) mul(tab[i], tab[i - 1], a);
+        E acc;
+        set_one(acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int w = 8 * L - 1; w >= 0; w--) {
+            u32 nib = (e[w >> 3] >> ((w & 7) * 4)) & 15u;
+            sqr(acc, acc); sqr(acc, acc); sqr(acc, acc); sqr(acc, acc);
+            if (nib) mul(acc, acc, tab[nib]);   // exponent is public and identical across the warp
+        }
+        r = acc;
+    }
+    // a^(p-2) (Fermat).  0 -> 0.  The reference uses Fermat for p256 (field.rs:364-382) and
+    // Bernstein-Yang for p384/sm2 (primeorder/src/field.rs:506-559); the result is the same element.
+    ECB_DEV static void inv(E& r, const E& a) {
+        u32 e[L];
+        e[0] = sub_cc(P::p(0), 2u);
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) e[i] = subc_cc(P::p(i), 0u);
+        pow_limbs(r, a, e);
+    }
+    // a^((p+1)/4) for p = 3 mod 4 (p256 field.rs:385-411, p384 field.rs:95-117, sm2 field.rs sqrt)
+    ECB_DEV static void sqrt_candidate(E& r, const E& a) {
+        u32 e[L];
+        e[0] = add_cc(P::p(0), 1u);
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) e[i] = addc_cc(P::p(i), 0u);
+        u32 c = addc(0u, 0u);
+        ECB_UNROLL
+        for (int i = 0; i < L - 1; i++) e[i] = (e[i] >> 2) | (e[i + 1] << 30);
+        e[L - 1] = (e[L - 1] >> 2) | (c << 30);
+        pow_limbs(r, a, e);
+    }
+};
+
+}  // namespace ecb

@@ -1,0 +1,140 @@
+// emu.cpp — TEST-ONLY host build of the kernel bodies (rustcrypto-elliptic-curves_b200/csrc/*.cuh with
+// ECB_EMU: PTX carry chains replaced by a carry-flag emulation).  Lets the CPU-only test tier check
+// the limb-level algorithms (field reduction, formulas, GLV, windows, verify epilogue) in a container
+// without a GPU.  It is NOT part of the product: the package never loads this library, and all
+// parity claims are made on the B200 through libecb200.so.
+#define ECB_EMU 1
+#include <cstring>
+#include <vector>
+#include "../../rustcrypto-elliptic-curves_b200/csrc/kernels.cuh"
+
+using namespace ecb;
+
+template <class C> struct Emu {
+    typedef Bodies<C> B;
+    static constexpr int L = C::L;
+    static constexpr int FB = C::FB;
+
+    static void normalize(int n, const u32* proj, int mode, int compress, u8* out, u8* inf, u32* limbs, int nthreads) {
+        int need = (n + B::EPT - 1) / B::EPT;
+        if (nthreads < need) nthreads = need;
+        if (nthreads < 1) nthreads = 1;
+        for (int t = 0; t < nthreads; t++) B::body_normalize(t, nthreads, n, proj, mode, compress, out, inf, limbs);
+    }
+    static int ngtab() { return C::A_IS_ZERO ? 8 : 15; }
+    // affine multiples 1..NG of G, via the same kernels the device init uses
+    static std::vector<u32> gtab() {
+        int ng = ngtab();
+        std::vector<u8> pts(2 * FB * ng), ks(FB * ng, 0);
+        typename EC<C>::Aff g;
+        EC<C>::generator(g);
+        u32 t[L];
+        for (int j = 0; j < ng; j++) {
+            C::F::to_limbs(t, g.x); store_be<L>(&pts[2 * FB * j], t);
+            C::F::to_limbs(t, g.y); store_be<L>(&pts[2 * FB * j + FB], t);
+            ks[FB * j + FB - 1] = (u8)(j + 1);
+        }
+        std::vector<u32> proj(3 * L * ng), out(2 * L * ng);
+        for (int i = 0; i < ng; i++) B::template body_mul_var<false>(i, ng, 0, pts.data(), nullptr, ks.data(), proj.data(), nullptr);
+        normalize(ng, proj.data(), NORM_AFF_LIMBS, 0, nullptr, nullptr, out.data(), 0);
+        return out;
+    }
+    // k256 fixed-base table: (j+1) * 16^i * G, i < 65, j < 8
+    static std::vector<u32> gentab() {
+        const int ne = 65 * 8;
+        std::vector<u8> pts(2 * FB * ne), ks(FB * ne, 0);
+        typename EC<C>::Aff g;
+        EC<C>::generator(g);
+        u32 t[L];
+        for (int e = 0; e < ne; e++) {
+            C::F::to_limbs(t, g.x); store_be<L>(&pts[2 * FB * e], t);
+            C::F::to_limbs(t, g.y); store_be<L>(&pts[2 * FB * e + FB], t);
+            int i = e / 8, j = e % 8;
+            // (j+1) << 4i as big-endian bytes; i = 64 would overflow 256 bits -> reduce is wrong, so use mod n arithmetic:
+            // 16^64 = 2^256 = (2^256 - n) mod n handled by load_scalar's single subtraction.
+            int bit = 4 * i;
+            unsigned v = (unsigned)(j + 1);
+            if (bit < 8 * FB) {
+                int byte = bit / 8, sh = bit % 8;
+                unsigned w = v << sh;
+                ks[FB * e + FB - 1 - byte] |= (u8)w;
+                if (byte + 1 < FB) ks[FB * e + FB - 2 - byte] |= (u8)(w >> 8);
+            } else {
+                // (j+1) * (2^256 mod n), j+1 <= 8: computed with the scalar field
+                typename C::Fn::E a, acc;
+                for (int l = 0; l < L; l++) a.v[l] = C::Fn::Params::one(l);   // R mod n = 2^256 mod n (plain value)
+                acc = a;
+                for (unsigned m = 1; m < v; m++) C::Fn::add(acc, acc, a);
+                store_be<L>(&ks[FB * e], acc.v);
+            }
+        }
+        std::vector<u32> proj(3 * L * ne), out(2 * L * ne);
+        for (int i = 0; i < ne; i++) B::template body_mul_var<false>(i, ne, 0, pts.data(), nullptr, ks.data(), proj.data(), nullptr);
+        normalize(ne, proj.data(), NORM_AFF_LIMBS, 0, nullptr, nullptr, out.data(), 0);
+        return out;
+    }
+
+    static void field_op(int which, int op, int n, const u8* a, const u8* b, u8* out, u8* ok) {
+        for (int i = 0; i < n; i++) B::body_field_op(i, n, which, op, a, b, out, ok);
+    }
+    static void mul_var(int ct, int n, u32 flags, const u8* pts, const u8* inf, const u8* k, u8* out, int compress, u8* invalid, int nthreads) {
+        std::vector<u32> proj((size_t)3 * L * n);
+        for (int i = 0; i < n; i++) {
+            if (ct) B::template body_mul_var<true>(i, n, flags, pts, inf, k, proj.data(), invalid);
+            else B::template body_mul_var<false>(i, n, flags, pts, inf, k, proj.data(), invalid);
+        }
+        normalize(n, proj.data(), NORM_SEC1, compress, out, nullptr, nullptr, nthreads);
+    }
+    static void mul_gen(int ct, int n, const u8* k, u8* out, int compress) {
+        static std::vector<u32> tab;
+        if (C::A_IS_ZERO && tab.empty()) tab = gentab();
+        std::vector<u32> proj((size_t)3 * L * n);
+        for (int i = 0; i < n; i++) {
+            if (ct) B::template body_mul_gen<true>(i, n, k, tab.data(), proj.data());
+            else B::template body_mul_gen<false>(i, n, k, tab.data(), proj.data());
+        }
+        normalize(n, proj.data(), NORM_SEC1, compress, out, nullptr, nullptr, 0);
+    }
+    static void batch_normalize(int n, const u8* xyz, u8* xy, u8* inf, int nthreads) {
+        std::vector<u32> proj((size_t)3 * L * n);
+        for (int i = 0; i < n; i++) B::body_load_proj(i, n, xyz, proj.data(), nullptr);
+        normalize(n, proj.data(), NORM_XY_BYTES, 0, xy, inf, nullptr, nthreads);
+    }
+    static void verify(int n, const u8* q, const u8* z, const u8* rs, u8* ok) {
+        static std::vector<u32> gt;
+        if (gt.empty()) gt = gtab();
+        for (int i = 0; i < n; i++) B::body_verify(i, n, q, z, rs, gt.data(), ok);
+    }
+};
+
+#define DISPATCH(curve, CALL)                         \
+    switch (curve) {                                  \
+        case 0: Emu<CurveK256>::CALL; break;          \
+        case 1: Emu<CurveP256>::CALL; break;          \
+        case 2: Emu<CurveP384>::CALL; break;          \
+        case 3: Emu<CurveSM2>::CALL; break;           \
+        default: return -1;                           \
+    }
+
+extern "C" {
+int emu_field_op(int curve, int which, int op, int n, const u8* a, const u8* b, u8* out, u8* ok) {
+    DISPATCH(curve, field_op(which, op, n, a, b, out, ok));
+    return 0;
+}
+int emu_mul_var(int curve, int ct, int n, unsigned flags, const u8* pts, const u8* inf, const u8* k, u8* out, int compress, u8* invalid, int nthreads) {
+    DISPATCH(curve, mul_var(ct, n, flags, pts, inf, k, out, compress, invalid, nthreads));
+    return 0;
+}
+int emu_mul_gen(int curve, int ct, int n, const u8* k, u8* out, int compress) {
+    DISPATCH(curve, mul_gen(ct, n, k, out, compress));
+    return 0;
+}
+int emu_batch_normalize(int curve, int n, const u8* xyz, u8* xy, u8* inf, int nthreads) {
+    DISPATCH(curve, batch_normalize(n, xyz, xy, inf, nthreads));
+    return 0;
+}
+int emu_verify(int curve, int n, const u8* q, const u8* z, const u8* rs, u8* ok) {
+    DISPATCH(curve, verify(n, q, z, rs, ok));
+    return 0;
+}
+}

@@ -1,0 +1,231 @@
+"""CPU-only logic check of the kernel bodies (host emulation of the PTX carry chains) against the
+oracle.  This is NOT the parity gate (that is tests/test_gpu_parity.py on the B200); it keeps the
+limb-level algorithms honest in the GPU-less container."""
+import hashlib
+import random
+
+import pytest
+
+from oracle import ecoracle as o
+from tests import emu_lib
+
+lib = emu_lib.load()
+CUR = ["k256", "p256", "p384", "sm2"]
+
+
+def field_op(c, which, op, a_list, b_list=None):
+    fb = c.fb
+    n = len(a_list)
+    a = b"".join(v.to_bytes(fb, "big") for v in a_list)
+    b = b"".join(v.to_bytes(fb, "big") for v in b_list) if b_list is not None else None
+    out = emu_lib.buf(n * fb)
+    ok = emu_lib.buf(n)
+    assert lib.emu_field_op(c.cid, which, op, n, a, b, out, ok) == 0
+    raw = bytes(out)
+    return [int.from_bytes(raw[i * fb:(i + 1) * fb], "big") for i in range(n)], list(ok)
+
+
+def edge_values(m):
+    vals = [0, 1, 2, 3, m - 1, m - 2, m - 3, (m - 1) // 2, (m + 1) // 2, 2**32, 2**32 - 1, 2**32 + 977, 2**64 - 1,
+            2**128, 2**128 - 1, 2**255 % m, (2**256 - 1) % m, 2**224 % m, (2**192 - 1) % m, 0xFFFFFFFF, m >> 32, m - 2**32]
+    return sorted(set(v % m for v in vals))
+
+
+@pytest.mark.parametrize("cname", CUR)
+@pytest.mark.parametrize("which", [0, 1])
+def test_field_ops(cname, which):
+    c = o.curve(cname)
+    m = c.p if which == 0 else c.n
+    rng = random.Random(which * 10 + c.cid)
+    ev = edge_values(m)
+    A = [x for x in ev for _ in ev] + [rng.randrange(m) for _ in range(400)]
+    B = [y for _ in ev for y in ev] + [rng.randrange(m) for _ in range(400)]
+    for op, fn in ((0, lambda a, b: (a + b) % m), (1, lambda a, b: (a - b) % m), (2, lambda a, b: a * b % m)):
+        got, ok = field_op(c, which, op, A, B)
+        assert all(ok)
+        exp = [fn(a, b) for a, b in zip(A, B)]
+        assert got == exp, (cname, which, op, [i for i in range(len(A)) if got[i] != exp[i]][:3])
+    got, _ = field_op(c, which, 3, A)
+    assert got == [a * a % m for a in A]
+    got, _ = field_op(c, which, 4, A)
+    assert got == [(-a) % m for a in A]
+    A2 = ev + [rng.randrange(m) for _ in range(20)]
+    got, _ = field_op(c, which, 5, A2)
+    assert got == [pow(a, m - 2, m) for a in A2]
+    # non-canonical input is flagged
+    _, ok = field_op(c, which, 0, [m, 2**(8 * c.fb) - 1], [0, 0])
+    assert ok == [0, 0]
+
+
+@pytest.mark.parametrize("cname", CUR)
+def test_sqrt(cname):
+    c = o.curve(cname)
+    rng = random.Random(7)
+    xs = [rng.randrange(c.p) for _ in range(12)]
+    sq = [x * x % c.p for x in xs]
+    got, ok = field_op(c, 0, 6, sq)
+    assert all(ok)
+    assert all(g * g % c.p == s for g, s in zip(got, sq))
+
+
+def test_k256_golden_field(golden):
+    c = o.K256
+    k = golden["field"]["k256_risc0_8x32"]
+    a, b = int(k["a"], 16), int(k["b"], 16)
+    assert field_op(c, 0, 0, [a], [b])[0] == [int(k["add"], 16)]
+    assert field_op(c, 0, 2, [a], [b])[0] == [int(k["mul"], 16)]
+    assert field_op(c, 0, 3, [a])[0] == [int(k["square"], 16)]
+    assert field_op(c, 0, 4, [a])[0] == [int(k["negate"], 16)]
+    dbl = [int(h, 16) for h in golden["field"]["k256"]["dbl"]]
+    assert field_op(c, 0, 0, dbl[:-1], dbl[:-1])[0] == dbl[1:]
+
+
+def scalars_edge(c, rng, n):
+    base = [0, 1, 2, c.n - 1, c.n - 2, c.n >> 1, (c.n >> 1) + 1, 1 << 128, (1 << 128) - 1, c.n, c.n + 1, 15, 16, 17]
+    return base + [rng.randrange(c.n) for _ in range(n)]
+
+
+@pytest.mark.parametrize("cname", CUR)
+@pytest.mark.parametrize("ct", [0, 1])
+def test_mul_var(cname, ct):
+    c = o.curve(cname)
+    rng = random.Random(11 + c.cid)
+    ks = scalars_edge(c, rng, 6 if c.fb == 48 else 10)
+    pts = [o.mul_gen(c, rng.randrange(1, c.n)) for _ in ks]
+    pts[3] = c.G
+    pts[4] = o.pt_neg(c, c.G)
+    inf = [0] * len(ks)
+    inf[5] = 1
+    fb = c.fb
+    pb = b"".join(P[0].to_bytes(fb, "big") + P[1].to_bytes(fb, "big") for P in pts)
+    kb = b"".join((k % (1 << (8 * fb))).to_bytes(fb, "big") for k in ks)
+    for compress in (0, 1):
+        stride = 1 + (fb if compress else 2 * fb)
+        out = emu_lib.buf(len(ks) * stride)
+        invalid = emu_lib.buf(len(ks))
+        assert lib.emu_mul_var(c.cid, ct, len(ks), 0, pb, bytes(inf), kb, out, compress, invalid, 3) == 0
+        exp = o.batch_mul_var_affine(c, pb, bytes(inf), kb, bool(compress))
+        assert bytes(out) == exp
+        assert not any(invalid)
+    # projective inputs with random Z, incl. Z = 0
+    xyz = bytearray()
+    for i, P in enumerate(pts):
+        lam = rng.randrange(1, c.p)
+        if i == 2:
+            xyz += (0).to_bytes(fb, "big") + (7).to_bytes(fb, "big") + (0).to_bytes(fb, "big")
+        else:
+            xyz += (P[0] * lam % c.p).to_bytes(fb, "big") + (P[1] * lam % c.p).to_bytes(fb, "big") + lam.to_bytes(fb, "big")
+    stride = 1 + (fb if c.compress else 2 * fb)
+    out = emu_lib.buf(len(ks) * stride)
+    assert lib.emu_mul_var(c.cid, ct, len(ks), 8, bytes(xyz), None, kb, out, int(c.compress), None, 0) == 0
+    assert bytes(out) == o.batch_mul_var_proj(c, bytes(xyz), kb)
+    # off-curve point is flagged invalid and yields the identity slot
+    bad = (1).to_bytes(fb, "big") + (1).to_bytes(fb, "big")
+    out = emu_lib.buf(stride)
+    invalid = emu_lib.buf(1)
+    lib.emu_mul_var(c.cid, ct, 1, 0, bad, None, (5).to_bytes(fb, "big"), out, int(c.compress), invalid, 0)
+    assert list(invalid) == [1] and bytes(out) == bytes(stride)
+
+
+@pytest.mark.parametrize("cname", ["k256", "p256"])
+@pytest.mark.parametrize("ct", [0, 1])
+def test_mul_gen(cname, ct, golden):
+    c = o.curve(cname)
+    rng = random.Random(3)
+    ks = scalars_edge(c, rng, 12) + [int(k, 16) for k, _, _ in golden["group"][cname]["mul"]]
+    fb = c.fb
+    kb = b"".join((k % (1 << (8 * fb))).to_bytes(fb, "big") for k in ks)
+    stride = 1 + (fb if c.compress else 2 * fb)
+    out = emu_lib.buf(len(ks) * stride)
+    assert lib.emu_mul_gen(c.cid, ct, len(ks), kb, out, int(c.compress)) == 0
+    assert bytes(out) == o.batch_mul_gen(c, kb)
+
+
+@pytest.mark.parametrize("cname", CUR)
+def test_batch_normalize(cname):
+    c = o.curve(cname)
+    rng = random.Random(21)
+    fb = c.fb
+    pts = []
+    for i in range(37):
+        if i in (0, 17, 36):
+            pts.append((rng.randrange(c.p), rng.randrange(1, c.p), 0))
+        else:
+            P = o.mul_gen(c, rng.randrange(1, c.n))
+            lam = rng.randrange(1, c.p)
+            pts.append((P[0] * lam % c.p, P[1] * lam % c.p, lam))
+    xyz = b"".join(v.to_bytes(fb, "big") for P in pts for v in P)
+    exp = o.batch_normalize(c, pts)
+    for nthreads in (1, 4, 0):
+        xy = emu_lib.buf(len(pts) * 2 * fb)
+        inf = emu_lib.buf(len(pts))
+        assert lib.emu_batch_normalize(c.cid, len(pts), xyz, xy, inf, nthreads) == 0
+        raw = bytes(xy)
+        for i, P in enumerate(exp):
+            if P is None:
+                assert inf[i] == 1 and raw[i * 2 * fb:(i + 1) * 2 * fb] == bytes(2 * fb)
+            else:
+                assert inf[i] == 0
+                assert raw[i * 2 * fb:(i + 1) * 2 * fb] == P[0].to_bytes(fb, "big") + P[1].to_bytes(fb, "big")
+
+
+def run_verify(c, rows):
+    fb = c.fb
+    q = b"".join(r[0][0].to_bytes(fb, "big") + r[0][1].to_bytes(fb, "big") for r in rows)
+    z = b"".join(r[1] for r in rows)
+    rs = b"".join((r[2] % (1 << 8 * fb)).to_bytes(fb, "big") + (r[3] % (1 << 8 * fb)).to_bytes(fb, "big") for r in rows)
+    ok = emu_lib.buf(len(rows))
+    assert lib.emu_verify(c.cid, len(rows), q, z, rs, ok) == 0
+    return list(ok), o.batch_verify(c, q, z, rs)
+
+
+@pytest.mark.parametrize("cname", ["k256", "p256", "p384"])
+def test_verify_wycheproof_sample(golden, cname):
+    c = o.curve(cname)
+    blob = golden["wycheproof"][cname]
+    hf = getattr(hashlib, blob["hash"])
+    rows = []
+    for wx, wy, msg, sig, flag in blob["rows"]:
+        rsv = o.der_parse_strict(bytes.fromhex(sig), c)
+        if rsv is None:
+            continue
+        r, s = rsv
+        if r >> (8 * c.fb) or s >> (8 * c.fb):
+            continue
+        wxb, wyb = bytes.fromhex(wx)[-c.fb:], bytes.fromhex(wy)[-c.fb:]
+        Q = (int.from_bytes(wxb, "big"), int.from_bytes(wyb, "big"))
+        zb = o.bits2field(c, hf(bytes.fromhex(msg)).digest())
+        rows.append((Q, zb, r, s))
+        if c.low_s and s > c.n >> 1 and 1 <= s < c.n:
+            rows.append((Q, zb, r, c.n - s))
+    rows = rows[::3] if cname == "p384" else rows[::2]
+    got, exp = run_verify(c, rows)
+    assert got == list(exp)
+    assert sum(got) > 20
+
+
+@pytest.mark.parametrize("cname", CUR)
+def test_verify_synthetic(cname):
+    c = o.curve(cname)
+    rng = random.Random(77)
+    rows = []
+    for i in range(10):
+        d = rng.randrange(1, c.n)
+        Q = o.mul_gen(c, d)
+        z = rng.randrange(1 << (8 * c.fb)).to_bytes(c.fb, "big")
+        k = rng.randrange(1, c.n)
+        r = o.mul_gen(c, k)[0] % c.n
+        s = pow(k, -1, c.n) * (o.reduce_once(c, int.from_bytes(z, "big")) + r * d) % c.n
+        if c.low_s and s > c.n >> 1:
+            s = c.n - s
+        rows.append((Q, z, r, s))
+        if i % 3 == 0:
+            rows.append((Q, z, r, c.n - s))          # high-s twin: reject on k256, accept elsewhere
+        if i % 4 == 0:
+            rows.append((Q, z, r ^ 1, s))
+            rows.append((Q, z, 0, s))
+            rows.append((Q, z, r, c.n))
+            rows.append(((Q[0], Q[1] ^ 1), z, r, s))  # off-curve key
+    got, exp = run_verify(c, rows)
+    assert got == list(exp)
+    assert 0 < sum(got) < len(got)
