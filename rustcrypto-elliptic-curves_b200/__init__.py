@@ -21,7 +21,7 @@ import os
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libecb200.so")
+LIB_PATH = os.environ.get("ECB200_LIB") or os.path.join(HERE, "libecb200.so")
 
 K256, P256, P384, SM2 = 0, 1, 2, 3
 CURVE_IDS = {"k256": K256, "secp256k1": K256, "p256": P256, "p384": P384, "sm2": SM2}

@@ -12,6 +12,16 @@
 
 namespace ecb {
 
+// Point-level operations are real (non-inlined) device functions: one copy of add / add_mixed / dbl per
+// kernel keeps the instruction footprint of the window loops small (the bodies are 2-6 k SASS
+// instructions each) and the build time bounded; the ~100 local-memory moves per call are noise next
+// to the ~14 field multiplications inside.
+#if defined(__CUDACC__) && !defined(ECB_EMU)
+#define ECB_POINT_FN __device__ __noinline__
+#else
+#define ECB_POINT_FN inline
+#endif
+
 template <class C> struct EC {
     typedef typename C::F F;
     typedef typename F::E E;
@@ -62,7 +72,7 @@ template <class C> struct EC {
     }
 
     // ---------------------------------------------------------------- complete addition
-    ECB_DEV static void add(Proj& r, const Proj& p, const Proj& q) {
+    ECB_POINT_FN static void add(Proj& r, const Proj& p, const Proj& q) {
         E xx, yy, zz, xy, yz, xz, t0, t1;
         F::mul(xx, p.X, q.X);
         F::mul(yy, p.Y, q.Y);
@@ -73,7 +83,7 @@ template <class C> struct EC {
         finish_add(r, xx, yy, zz, xy, yz, xz);
     }
     // p + (affine q); q must not be the identity
-    ECB_DEV static void add_mixed(Proj& r, const Proj& p, const Aff& q) {
+    ECB_POINT_FN static void add_mixed(Proj& r, const Proj& p, const Aff& q) {
         E xx, yy, zz, xy, yz, xz, t0, t1;
         F::mul(xx, p.X, q.x);
         F::mul(yy, p.Y, q.y);
@@ -117,7 +127,7 @@ template <class C> struct EC {
             r.X = t2; r.Y = t3; F::add(r.Z, t0, t1);
         }
     }
-    ECB_DEV static void dbl(Proj& r, const Proj& p) {
+    ECB_POINT_FN static void dbl(Proj& r, const Proj& p) {
         if constexpr (C::A_IS_ZERO) {
             // X3 = 2XY(Y^2 - 9bZ^2) ; Y3 = (Y^2 - 9bZ^2)(Y^2 + 3bZ^2) + 24b Y^2 Z^2 ; Z3 = 8 Y^3 Z
             E yy, zz, xy, yz, bzz, bzz3, m, pp, t0, t1;

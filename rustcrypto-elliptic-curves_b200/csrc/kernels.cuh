@@ -314,7 +314,9 @@ template <class C> struct Bodies {
             for (int w = 8 * L - 1; w >= 0; w--) {
                 if (w != 8 * L - 1) { G::dbl(acc, acc); G::dbl(acc, acc); G::dbl(acc, acc); G::dbl(acc, acc); }
                 u32 nq = (u2[w >> 3] >> ((w & 7) * 4)) & 15u;
-                G::add(acc, acc, tab.e[nq]);
+                { Proj e_ = tab.e[nq]; G::add(acc, acc, e_); }   // copy first: passing the dynamically indexed
+                                                                // local-array element by reference to the non-inlined add
+                                                                // produced wrong results on sm_100a (nvcc 12.9)
                 u32 ng = (u1[w >> 3] >> ((w & 7) * 4)) & 15u;
                 if (ng) {
                     Aff g;

@@ -8,7 +8,10 @@ from oracle import ecoracle as o
 
 eng = ecb200.Engine(0)
 dev = torch.device("cuda:0")
-stream = torch.cuda.current_stream().cuda_stream
+ts = torch.cuda.Stream()
+torch.cuda.set_stream(ts)
+stream = ts.cuda_stream
+assert stream != 0
 
 
 def timeit(fn, reps=3):

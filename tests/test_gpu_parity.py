@@ -294,8 +294,7 @@ def make_sigs(c, rng, n, nkeys=16):
         s = r * pow(b, -1, c.n) % c.n
         z = a * s % c.n
         if c.low_s and s > c.n >> 1:
-            s = c.n - s
-            z = (-z) % c.n
+            s = c.n - s          # R -> -R: same x, still valid
         rows.append([Q, z.to_bytes(c.fb, "big"), r, s])
     return rows
 
