@@ -13,6 +13,12 @@ namespace ecb {
 
 template <int L_> struct Fe { u32 v[L_]; };
 
+#if defined(__CUDACC__) && !defined(ECB_EMU)
+#define ECB_FIELD_FN __device__ __noinline__
+#else
+#define ECB_FIELD_FN inline
+#endif
+
 struct FpK256 {
     static constexpr int L = 8;
     typedef Fe<8> E;
@@ -88,16 +94,27 @@ struct FpK256 {
         fold_top(r, acc, acc[8], acc[9]);
     }
 
-    ECB_DEV static void mul(E& r, const E& a, const E& b) {
+    // The multiplier and squarer are real functions with by-value (register) arguments: one ~150
+    // instruction copy each per kernel instead of one per call site, so the window loops of the
+    // point kernels stay inside the instruction cache (ncu showed "no instruction" as the top stall
+    // of the fully inlined build, profiles/).  ptxas passes the 8-limb structs in registers: no
+    // local-memory traffic at the call.
+    ECB_FIELD_FN static E mul_fn(E a, E b) {
+        E r;
         u32 t[16];
         mul_wide<8>(t, a.v, b.v);
         reduce512(r.v, t);
+        return r;
     }
-    ECB_DEV static void sqr(E& r, const E& a) {
+    ECB_FIELD_FN static E sqr_fn(E a) {
+        E r;
         u32 t[16];
         sqr_wide<8>(t, a.v);
         reduce512(r.v, t);
+        return r;
     }
+    ECB_DEV static void mul(E& r, const E& a, const E& b) { r = mul_fn(a, b); }
+    ECB_DEV static void sqr(E& r, const E& a) { r = sqr_fn(a); }
     ECB_DEV static void add(E& r, const E& a, const E& b) {
         u32 v[8];
         u32 c = add_n<8>(v, a.v, b.v);

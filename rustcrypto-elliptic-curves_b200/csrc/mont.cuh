@@ -73,16 +73,23 @@ template <class P> struct Mont {
         final_sub(r, v, top);
     }
 
-    ECB_DEV static void mul(E& r, const E& a, const E& b) {
+    // real functions with register arguments (see fp_k256.cuh for why)
+    ECB_FIELD_FN static E mul_fn(E a, E b) {
+        E r;
         u32 t[2 * L];
         mul_wide<L>(t, a.v, b.v);
         redc(r.v, t);
+        return r;
     }
-    ECB_DEV static void sqr(E& r, const E& a) {
+    ECB_FIELD_FN static E sqr_fn(E a) {
+        E r;
         u32 t[2 * L];
         sqr_wide<L>(t, a.v);
         redc(r.v, t);
+        return r;
     }
+    ECB_DEV static void mul(E& r, const E& a, const E& b) { r = mul_fn(a, b); }
+    ECB_DEV static void sqr(E& r, const E& a) { r = sqr_fn(a); }
     ECB_DEV static void add(E& r, const E& a, const E& b) {
         u32 v[L];
         u32 c = add_n<L>(v, a.v, b.v);
