@@ -11,8 +11,9 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cuda_runtime.h>
+#include "../rustcrypto-elliptic-curves_b200/csrc/fp_k256.cuh"
 
-typedef uint32_t u32;
+using ecb::u32;
 typedef unsigned long long u64;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
@@ -20,11 +21,12 @@ typedef unsigned long long u64;
 constexpr int ITERS = 2048;
 constexpr int CH = 8;   // independent chains per thread
 
-enum Mix { IMAD_LO, IMAD_HI, IMAD_WIDE, IMAD_WIDE_X, IADD3_, WIDE_PLUS_IADD3, LOHI_PAIR, FFMA_, DFMA_, WIDE_X_PLUS_2IADD3, NMIX };
+enum Mix { IMAD_LO, IMAD_HI, IMAD_WIDE, IMAD_WIDE_X, IADD3_, WIDE_PLUS_IADD3, LOHI_PAIR, FFMA_, DFMA_, WIDE_X_PLUS_2IADD3, WIDE_X_SHARED_B, MULWIDE8, FPMUL_K256, NMIX };
 static const char* MIXNAME[NMIX] = {"imad_lo", "imad_hi", "imad_wide", "imad_wide_carry_chain", "iadd3", "imad_wide+iadd3",
-                                    "imad_lo+imad_hi", "ffma", "dfma", "imad_wide_carry+2iadd3"};
+                                    "imad_lo+imad_hi", "ffma", "dfma", "imad_wide_carry+2iadd3", "imad_wide_carry_chain_shared_multiplicand",
+                                    "mul_wide8_macs(64/iter)", "fp_k256_mul_macs(73/iter)"};
 // "ops" counted per loop body per chain
-static const int MIXOPS[NMIX] = {1, 1, 1, 1, 1, 2, 2, 1, 1, 3};
+static const int MIXOPS[NMIX] = {1, 1, 1, 1, 1, 2, 2, 1, 1, 3, 1, 8, 0};
 
 template <int MIX>
 __global__ void __launch_bounds__(512, 2) k_mix(u32* sink, u64* cycles, u32 seed) {
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(512, 2) k_mix(u32* sink, u64* cycles, u32 seed
 #pragma unroll 4
     for (int it = 0; it < ITERS; it++) {
 #pragma unroll
-        for (int i = 0; i < CH; i++) {
+        for (int i = 0; i < CH && MIX != MULWIDE8 && MIX != FPMUL_K256; i++) {
             if (MIX == IMAD_LO) a[i] = a[i] * b[i] + c[i];
             if (MIX == IMAD_HI) a[i] = __umulhi(a[i], b[i]) + c[i];
             if (MIX == IMAD_WIDE) w[i] = (u64)(u32)w[i] * b[i] + w[i];
@@ -48,6 +50,11 @@ __global__ void __launch_bounds__(512, 2) k_mix(u32* sink, u64* cycles, u32 seed
                 if (i == 0) asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi}, %0; mad.lo.cc.u32 lo, %1, %2, lo; madc.hi.cc.u32 hi, %1, %2, hi; mov.b64 %0, {lo,hi};}" : "+l"(w[i]) : "r"(b[i]), "r"(d[i]));
                 else if (i < CH - 1) asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi}, %0; madc.lo.cc.u32 lo, %1, %2, lo; madc.hi.cc.u32 hi, %1, %2, hi; mov.b64 %0, {lo,hi};}" : "+l"(w[i]) : "r"(b[i]), "r"(d[i]));
                 else asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi}, %0; madc.lo.cc.u32 lo, %1, %2, lo; madc.hi.u32 hi, %1, %2, hi; mov.b64 %0, {lo,hi};}" : "+l"(w[i]) : "r"(b[i]), "r"(d[i]));
+            }
+            if (MIX == WIDE_X_SHARED_B) {   // same multiplicand for the whole row, as in one row of the field multiplier
+                if (i == 0) asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi}, %0; mad.lo.cc.u32 lo, %1, %2, lo; madc.hi.cc.u32 hi, %1, %2, hi; mov.b64 %0, {lo,hi};}" : "+l"(w[i]) : "r"(d[i]), "r"(b[0]));
+                else if (i < CH - 1) asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi}, %0; madc.lo.cc.u32 lo, %1, %2, lo; madc.hi.cc.u32 hi, %1, %2, hi; mov.b64 %0, {lo,hi};}" : "+l"(w[i]) : "r"(d[i]), "r"(b[0]));
+                else asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi}, %0; madc.lo.cc.u32 lo, %1, %2, lo; madc.hi.u32 hi, %1, %2, hi; mov.b64 %0, {lo,hi};}" : "+l"(w[i]) : "r"(d[i]), "r"(b[0]));
             }
             if (MIX == IADD3_) a[i] = a[i] + b[i] + c[i];
             if (MIX == WIDE_PLUS_IADD3) {
@@ -66,6 +73,20 @@ __global__ void __launch_bounds__(512, 2) k_mix(u32* sink, u64* cycles, u32 seed
                 else if (i < CH - 1) asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi}, %0; madc.lo.cc.u32 lo, %1, %2, lo; madc.hi.cc.u32 hi, %1, %2, hi; mov.b64 %0, {lo,hi};}" : "+l"(w[i]) : "r"(b[i]), "r"(d[i]));
                 else asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi}, %0; madc.lo.cc.u32 lo, %1, %2, lo; madc.hi.u32 hi, %1, %2, hi; mov.b64 %0, {lo,hi};}" : "+l"(w[i]) : "r"(b[i]), "r"(d[i]));
             }
+        }
+        if (MIX == MULWIDE8) {
+            u32 r[16];
+            ecb::mul_wide<8>(r, a, b);
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = r[i] ^ r[i + 8];
+        }
+        if (MIX == FPMUL_K256) {
+            ecb::FpK256::E x, y, z;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }
+            z = ecb::FpK256::mul_fn(x, y);
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = z.v[i];
         }
         if (MIX == WIDE_X_PLUS_2IADD3) {
 #pragma unroll
@@ -101,7 +122,7 @@ static void run(int nsm, u32* sink, u64* cyc_d, double clk_mhz, bool last) {
     CK(cudaMemcpy(cyc, cyc_d, sizeof(u64) * grid, cudaMemcpyDeviceToHost));
     double avg = 0; for (int i = 0; i < grid; i++) avg += (double)cyc[i]; avg /= grid;
     free(cyc);
-    double ops_per_thread = (double)ITERS * CH * MIXOPS[MIX];
+    double ops_per_thread = (MIX == FPMUL_K256) ? (double)ITERS * 73 : (double)ITERS * CH * MIXOPS[MIX];
     double ops_per_sm = ops_per_thread * block * 2;      // 2 CTAs resident per SM
     double per_clk_sm = ops_per_sm / avg;
     double gops = ops_per_thread * block * (double)grid / (ms * 1e-3) / 1e9;
@@ -128,7 +149,10 @@ int main() {
     run<LOHI_PAIR>(nsm, sink, cyc, clk_khz / 1e3, false);
     run<FFMA_>(nsm, sink, cyc, clk_khz / 1e3, false);
     run<DFMA_>(nsm, sink, cyc, clk_khz / 1e3, false);
-    run<WIDE_X_PLUS_2IADD3>(nsm, sink, cyc, clk_khz / 1e3, true);
+    run<WIDE_X_PLUS_2IADD3>(nsm, sink, cyc, clk_khz / 1e3, false);
+    run<WIDE_X_SHARED_B>(nsm, sink, cyc, clk_khz / 1e3, false);
+    run<MULWIDE8>(nsm, sink, cyc, clk_khz / 1e3, false);
+    run<FPMUL_K256>(nsm, sink, cyc, clk_khz / 1e3, true);
     printf(" }\n}\n");
     return 0;
 }

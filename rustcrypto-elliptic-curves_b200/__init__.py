@@ -109,6 +109,10 @@ def bits2field(curve, prehash: bytes) -> bytes:
     return prehash[:fb]
 
 
+def _nbytes(b) -> int:
+    return int(b.nbytes) if hasattr(b, "nbytes") else len(b)
+
+
 def _as_buf(b) -> Tuple[ctypes.c_void_p, object]:
     """bytes / bytearray / numpy uint8 array -> (void*, keep-alive)"""
     if b is None:
@@ -162,7 +166,7 @@ class Engine:
     def mul_by_generator_batch(self, curve, ks: bytes, flags: int = 0) -> bytes:
         """[k_i * G] as SEC1 slots.  ks = n x FB big-endian scalars."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = len(ks) // fb
+        n = _nbytes(ks) // fb
         out = bytearray(n * slot_bytes(cid, flags))
         pk, k1 = _as_buf(ks)
         po, k2 = _as_buf(out)
@@ -172,7 +176,7 @@ class Engine:
     def mul_batch(self, curve, points: bytes, ks: bytes, inf: Optional[bytes] = None, flags: int = 0) -> Tuple[bytes, bytes]:
         """[k_i * P_i] as SEC1 slots, plus the per-element invalid-point flags."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = len(ks) // fb
+        n = _nbytes(ks) // fb
         out = bytearray(n * slot_bytes(cid, flags))
         invalid = bytearray(n)
         pp, a = _as_buf(points)
@@ -185,7 +189,7 @@ class Engine:
 
     def batch_normalize(self, curve, xyz: bytes) -> Tuple[bytes, bytes]:
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = len(xyz) // (3 * fb)
+        n = _nbytes(xyz) // (3 * fb)
         xy = bytearray(n * 2 * fb)
         inf = bytearray(n)
         pi, a = _as_buf(xyz)
@@ -197,7 +201,7 @@ class Engine:
     def lincomb(self, curve, points: bytes, ks: bytes, flags: int = 0, out_proj: bool = False) -> bytes:
         """sum_i k_i * P_i as one SEC1 slot (or X||Y||Z when out_proj)."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = len(ks) // fb
+        n = _nbytes(ks) // fb
         out = bytearray(3 * fb if out_proj else slot_bytes(cid, flags))
         pp, a = _as_buf(points)
         pk, b = _as_buf(ks)
@@ -208,7 +212,7 @@ class Engine:
     def ecdsa_verify(self, curve, q: bytes, z: bytes, rs: bytes) -> bytes:
         """ok bytes for n x (Q = x||y, z = bits2field(prehash), r||s)."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = len(z) // fb
+        n = _nbytes(z) // fb
         ok = bytearray(n)
         pq, a = _as_buf(q)
         pz, b = _as_buf(z)
@@ -242,7 +246,7 @@ class Engine:
 
     def field_op(self, curve, which: int, op: int, a: bytes, b: Optional[bytes] = None) -> Tuple[bytes, bytes]:
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = len(a) // fb
+        n = _nbytes(a) // fb
         out = bytearray(n * fb)
         ok = bytearray(n)
         pa, k1 = _as_buf(a)
