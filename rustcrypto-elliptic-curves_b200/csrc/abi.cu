@@ -3,6 +3,7 @@
 // the host; every entry point fails loudly when CUDA is unavailable.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -70,6 +71,10 @@ struct ecb200_ctx {
     const CurveLaunch* cl[4] = {};
     uint32_t* gtab[4] = {};                  // affine multiples 1..ngtab of G (internal limbs)
     uint32_t* gentab[4] = {};                // fixed-base window tables (k256)
+    uint32_t* gbig[4] = {};                  // big fixed-base tables of the public-input fast path (built on first use)
+    int gw = 16;                             // window width of gbig (ECB200_GW = 4, 8 or 16)
+    bool verify_v1 = false;                  // ECB200_VERIFY_V1=1: complete-formula verify kernel (A/B comparisons)
+    DevBuf prep, aff;                        // verify_prep scratch; affine limbs of normalised projective inputs
     DevBuf proj;                             // projective scratch (n x 3L limbs) — shared by all entry points
     DevBuf partial, one_point;
     DevBuf d_in[NSLOT][4], d_out[NSLOT][2];  // staging for host-pointer entry points
@@ -198,6 +203,50 @@ int build_tables(ecb200_ctx* c) {
 
 cudaStream_t pick(ecb200_ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->stream; }
 
+// Big fixed-base table for u1*G on the public-input path: entry (w << gw) + v = v * 2^(gw*w) * G in affine
+// internal limbs (64 MiB for a 256-bit curve at gw = 16; it lives in HBM/L2 and is gathered 64-96 B at a time).
+// Built on first use with the engine's own kernels: scalar v << (gw*w), point G, Jacobian fast path, normalise.
+int ensure_gbig(ecb200_ctx* c, const CurveLaunch* cl) {
+    if (c->gbig[cl->id]) return 0;
+    const int FB = cl->FB, L = cl->L, gw = c->gw;
+    const int nwin = (8 * FB + gw - 1) / gw;
+    const size_t per = (size_t)1 << gw, ne = (size_t)nwin * per;
+    std::vector<uint8_t> gxy(2 * FB);
+    hex_to(gxy.data(), GX[cl->id], FB);
+    hex_to(gxy.data() + FB, GY[cl->id], FB);
+    CU(c, cudaMalloc(&c->gbig[cl->id], ne * 2 * L * 4));
+    const size_t chunk = std::min<size_t>(ne, (size_t)1 << 18);
+    std::vector<uint8_t> pts(chunk * 2 * FB), sc(chunk * FB);
+    for (size_t e = 0; e < chunk; e++) memcpy(&pts[e * 2 * FB], gxy.data(), 2 * FB);
+    uint8_t *d_pts = nullptr, *d_k = nullptr;
+    uint32_t* d_proj = nullptr;
+    CU(c, cudaMalloc(&d_pts, pts.size()));
+    CU(c, cudaMalloc(&d_k, sc.size()));
+    CU(c, cudaMalloc(&d_proj, chunk * 3 * L * 4));
+    CU(c, cudaMemcpyAsync(d_pts, pts.data(), pts.size(), cudaMemcpyHostToDevice, c->stream));
+    for (size_t off = 0; off < ne; off += chunk) {
+        size_t cnt = std::min(chunk, ne - off);
+        std::fill(sc.begin(), sc.end(), 0);
+        for (size_t e = 0; e < cnt; e++) {
+            size_t idx = off + e;
+            size_t w = idx >> gw, v = idx & (per - 1);
+            int bit = (int)w * gw;
+            uint8_t* s = &sc[e * FB];
+            for (int b = 0; b < gw; b++)
+                if ((v >> b) & 1) { int pos = bit + b; s[FB - 1 - pos / 8] |= (uint8_t)(1u << (pos % 8)); }
+        }
+        CU(c, cudaMemcpyAsync(d_k, sc.data(), cnt * FB, cudaMemcpyHostToDevice, c->stream));
+        cl->mul_var_fast(c->stream, (int)cnt, d_pts, nullptr, nullptr, d_k, d_proj, nullptr);
+        cl->normalize(c->stream, (int)cnt, d_proj, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, c->gbig[cl->id] + off * 2 * L);
+        CU(c, cudaGetLastError());
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(d_pts);
+    cudaFree(d_k);
+    cudaFree(d_proj);
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------
 // device-pointer cores (enqueue only)
 
@@ -211,9 +260,20 @@ int mul_gen_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* 
 int mul_var_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_pts, const uint8_t* d_inf, const uint8_t* d_k,
                  uint8_t* d_out, uint8_t* d_invalid, uint32_t flags, cudaStream_t s) {
     CU(c, c->proj.reserve(n * 3 * cl->L * 4));
-    cl->mul_var(s, (flags & ECB200_FLAG_CT) != 0, (int)n, flags, d_pts, (flags & ECB200_FLAG_PROJ) ? nullptr : d_inf, d_k,
-                (uint32_t*)c->proj.p, d_invalid);
-    cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 0, resolve_compress(cl, flags) ? 1 : 0, d_out, nullptr, nullptr);
+    uint32_t* proj = (uint32_t*)c->proj.p;
+    if (flags & ECB200_FLAG_CT) {
+        // secret scalars: complete formulas, fixed windows, full table scans
+        cl->mul_var(s, true, (int)n, flags, d_pts, (flags & ECB200_FLAG_PROJ) ? nullptr : d_inf, d_k, proj, d_invalid);
+    } else if (flags & ECB200_FLAG_PROJ) {
+        // public scalars, projective inputs: normalise once (Montgomery trick), then the Jacobian fast path
+        CU(c, c->aff.reserve(n * 2 * cl->L * 4));
+        cl->load_proj(s, (int)n, d_pts, proj, nullptr);
+        cl->normalize(s, (int)n, proj, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, (uint32_t*)c->aff.p);
+        cl->mul_var_fast(s, (int)n, nullptr, (const uint32_t*)c->aff.p, nullptr, d_k, proj, d_invalid);
+    } else {
+        cl->mul_var_fast(s, (int)n, d_pts, nullptr, d_inf, d_k, proj, d_invalid);
+    }
+    cl->normalize(s, (int)n, proj, 0, resolve_compress(cl, flags) ? 1 : 0, d_out, nullptr, nullptr);
     CU(c, cudaGetLastError());
     return 0;
 }
@@ -225,7 +285,15 @@ int batch_normalize_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const u
     return 0;
 }
 int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q, const uint8_t* d_z, const uint8_t* d_rs, uint8_t* d_ok, cudaStream_t s) {
-    cl->verify(s, (int)n, d_q, d_z, d_rs, c->gtab[cl->id], d_ok);
+    if (c->verify_v1) {
+        cl->verify(s, (int)n, d_q, d_z, d_rs, c->gtab[cl->id], d_ok);
+    } else {
+        int r = ensure_gbig(c, cl);
+        if (r) return r;
+        CU(c, c->prep.reserve(n * (size_t)cl->prep_words * 4));
+        cl->verify_prep(s, (int)n, d_z, d_rs, (uint32_t*)c->prep.p);
+        cl->verify_main(s, (int)n, d_q, d_rs, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok);
+    }
     CU(c, cudaGetLastError());
     return 0;
 }
@@ -322,6 +390,8 @@ int ecb200_init(int device, ecb200_ctx** out) {
         ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+    if (const char* e = getenv("ECB200_GW")) { int g = atoi(e); if (g == 4 || g == 8 || g == 16) c->gw = g; }
+    if (const char* e = getenv("ECB200_VERIFY_V1")) c->verify_v1 = atoi(e) != 0;
     if (!ok || build_tables(c) != 0) {
         fprintf(stderr, "ecb200_init failed: %s (%s)\n", c->err.c_str(), cudaGetErrorString(cudaGetLastError()));
         ecb200_destroy(c);
@@ -339,7 +409,10 @@ void ecb200_destroy(ecb200_ctx* c) {
     for (int i = 0; i < 4; i++) {
         if (c->gtab[i]) cudaFree(c->gtab[i]);
         if (c->gentab[i]) cudaFree(c->gentab[i]);
+        if (c->gbig[i]) cudaFree(c->gbig[i]);
     }
+    c->prep.release();
+    c->aff.release();
     c->proj.release();
     c->partial.release();
     c->one_point.release();
@@ -481,8 +554,12 @@ int ecb200_lincomb(ecb200_ctx* c, int curve, size_t n_terms, const uint8_t* pts,
         CU(c, c->d_in[0][1].reserve(cnt * FB));
         CU(c, cudaMemcpyAsync(c->d_in[0][0].p, pts + off * psz, cnt * psz, cudaMemcpyHostToDevice, s));
         CU(c, cudaMemcpyAsync(c->d_in[0][1].p, k + off * FB, cnt * FB, cudaMemcpyHostToDevice, s));
-        cl->mul_var(s, (flags & ECB200_FLAG_CT) != 0, (int)cnt, flags, (const uint8_t*)c->d_in[0][0].p, nullptr,
-                    (const uint8_t*)c->d_in[0][1].p, (uint32_t*)c->proj.p + off * 3 * L, nullptr);
+        if ((flags & ECB200_FLAG_CT) || proj)
+            cl->mul_var(s, (flags & ECB200_FLAG_CT) != 0, (int)cnt, flags, (const uint8_t*)c->d_in[0][0].p, nullptr,
+                        (const uint8_t*)c->d_in[0][1].p, (uint32_t*)c->proj.p + off * 3 * L, nullptr);
+        else
+            cl->mul_var_fast(s, (int)cnt, (const uint8_t*)c->d_in[0][0].p, nullptr, nullptr, (const uint8_t*)c->d_in[0][1].p,
+                             (uint32_t*)c->proj.p + off * 3 * L, nullptr);
         CU(c, cudaStreamSynchronize(s));   // staging buffers are reused by the next piece
     }
     uint32_t* d_sum = (uint32_t*)c->one_point.p;

@@ -1,0 +1,303 @@
+// jac.cuh — variable-time fast path for PUBLIC inputs (ECDSA verification, vartime scalar mul).
+//
+// The reference computes everything with the complete projective formulas and constant-time scans
+// (k256/src/arithmetic/mul.rs:342-393, primeorder/src/projective.rs:106-150) because its API serves
+// secret scalars too.  Outputs are canonical (SEC1 bytes / booleans), so for public inputs the device
+// is free to use cheaper arithmetic (north_star: "variable-time windows are allowed
+// only for public-input verification"):
+//   * Jacobian coordinates (x = X/Z^2, y = Y/Z^3, Z = 0 = identity): doubling 2M+5S (a = 0) or 3M+5S
+//     (a = -3), mixed addition 7M+4S, against 6M+2S+3m / 8M+3S+2m_b and 11M+3m / 13M for RCB;
+//   * exceptional cases (P = +-Q, identity operands) are handled by explicit, warp-rarely-taken branches,
+//     so results stay exact for adversarial inputs (Wycheproof "edge case" rows);
+//   * u1*G comes from a precomputed affine table of all v * 2^(gw*w) * G (gw-bit windows, no doublings);
+//   * secp256k1: the per-element table {1..8}Q is brought to ONE common Z without any inversion by
+//     working on the isomorphic curve y^2 = x^3 + 7 Z^6 (the a = 0 doubling does not involve b), so all
+//     66 GLV additions are mixed additions; the true Z is restored with one multiplication at the end.
+// Secret-scalar entry points (ECB200_FLAG_CT) never come here.
+#pragma once
+#include "ec.cuh"
+
+namespace ecb {
+
+template <class C> struct Jac {
+    typedef typename C::F F;
+    typedef typename F::E E;
+    static constexpr int L = C::L;
+    struct J { E X, Y, Z; };
+    struct A { E x, y; };
+
+    ECB_DEV static void set_inf(J& p) { F::set_one(p.X); F::set_one(p.Y); F::set_zero(p.Z); }
+    ECB_DEV static bool is_inf(const J& p) { return F::is_zero(p.Z); }
+    ECB_DEV static void from_affine(J& p, const A& a) { p.X = a.x; p.Y = a.y; F::set_one(p.Z); }
+
+    // ---- doubling
+    ECB_POINT_FN static void dbl(J& r, const J& p) {
+        if constexpr (C::A_IS_ZERO) {
+            // dbl-2009-l: A=X^2 B=Y^2 C=B^2 D=2((X+B)^2-A-C) E=3A F=E^2 X3=F-2D Y3=E(D-X3)-8C Z3=2YZ
+            E a, b, c, d, e, f, t;
+            F::sqr(a, p.X);
+            F::sqr(b, p.Y);
+            F::sqr(c, b);
+            F::add(t, p.X, b); F::sqr(t, t); F::sub(t, t, a); F::sub(t, t, c); F::dbl(d, t);
+            F::dbl(e, a); F::add(e, e, a);
+            F::sqr(f, e);
+            F::mul(t, p.Y, p.Z); F::dbl(r.Z, t);
+            F::dbl(t, d); F::sub(r.X, f, t);
+            F::sub(t, d, r.X); F::mul(t, e, t);
+            F::dbl(c, c); F::dbl(c, c); F::dbl(c, c);
+            F::sub(r.Y, t, c);
+        } else {
+            // dbl-2001-b (a = -3): delta=Z^2 gamma=Y^2 beta=X*gamma alpha=3(X-delta)(X+delta)
+            // X3=alpha^2-8beta Z3=(Y+Z)^2-gamma-delta Y3=alpha(4beta-X3)-8gamma^2
+            E delta, gamma, beta, alpha, t0, t1;
+            F::sqr(delta, p.Z);
+            F::sqr(gamma, p.Y);
+            F::mul(beta, p.X, gamma);
+            F::sub(t0, p.X, delta); F::add(t1, p.X, delta); F::mul(t0, t0, t1);
+            F::dbl(alpha, t0); F::add(alpha, alpha, t0);
+            F::add(t0, p.Y, p.Z); F::sqr(t0, t0); F::sub(t0, t0, gamma); F::sub(r.Z, t0, delta);
+            F::dbl(t0, beta); F::dbl(t0, t0);            // 4 beta
+            F::dbl(t1, t0);                               // 8 beta
+            F::sqr(r.X, alpha); F::sub(r.X, r.X, t1);
+            F::sub(t0, t0, r.X); F::mul(t0, alpha, t0);
+            F::sqr(t1, gamma); F::dbl(t1, t1); F::dbl(t1, t1); F::dbl(t1, t1);
+            F::sub(r.Y, t0, t1);
+        }
+    }
+    // doubling of an affine point (Z = 1): used for the exceptional branch and table starts
+    ECB_DEV static void dbl_affine(J& r, const A& q) {
+        J t;
+        from_affine(t, q);
+        dbl(r, t);
+    }
+
+    // ---- mixed addition r = p + q, q affine and not the identity.  zr (optional) receives Z3 / Z1
+    // (valid only on the generic branch; callers that need it guarantee no exceptional case).
+    ECB_POINT_FN static void madd(J& r, const J& p, const A& q, E* zr) {
+        if (is_inf(p)) { from_affine(r, q); return; }
+        // madd-2007-bl: Z1Z1=Z1^2 U2=X2*Z1Z1 S2=Y2*Z1*Z1Z1 H=U2-X1 HH=H^2 I=4HH J=H*I rr=2(S2-Y1) V=X1*I
+        // X3=rr^2-J-2V Y3=rr(V-X3)-2Y1*J Z3=(Z1+H)^2-Z1Z1-HH
+        E z1z1, u2, s2, h, hh, i, j, rr, v, t;
+        F::sqr(z1z1, p.Z);
+        F::mul(u2, q.x, z1z1);
+        F::mul(s2, q.y, p.Z); F::mul(s2, s2, z1z1);
+        F::sub(h, u2, p.X);
+        F::sub(rr, s2, p.Y);
+        if (F::is_zero(h)) {
+            if (F::is_zero(rr)) dbl_affine(r, q);   // p == q
+            else set_inf(r);                         // p == -q
+            return;
+        }
+        F::dbl(rr, rr);
+        F::sqr(hh, h);
+        F::dbl(i, hh); F::dbl(i, i);
+        F::mul(j, h, i);
+        F::mul(v, p.X, i);
+        F::add(t, p.Z, h); F::sqr(t, t); F::sub(t, t, z1z1); F::sub(t, t, hh);   // Z3 = 2 Z1 H
+        if (zr) F::dbl(*zr, h);
+        E x3, y3;
+        F::sqr(x3, rr); F::sub(x3, x3, j); F::sub(x3, x3, v); F::sub(x3, x3, v);
+        F::sub(y3, v, x3); F::mul(y3, rr, y3);
+        F::mul(j, p.Y, j); F::dbl(j, j);
+        F::sub(y3, y3, j);
+        r.X = x3; r.Y = y3; r.Z = t;
+    }
+
+    // ---- full Jacobian addition r = p + q
+    ECB_POINT_FN static void add(J& r, const J& p, const J& q) {
+        if (is_inf(q)) { r = p; return; }
+        if (is_inf(p)) { r = q; return; }
+        // add-2007-bl
+        E z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t;
+        F::sqr(z1z1, p.Z);
+        F::sqr(z2z2, q.Z);
+        F::mul(u1, p.X, z2z2);
+        F::mul(u2, q.X, z1z1);
+        F::mul(s1, p.Y, q.Z); F::mul(s1, s1, z2z2);
+        F::mul(s2, q.Y, p.Z); F::mul(s2, s2, z1z1);
+        F::sub(h, u2, u1);
+        F::sub(rr, s2, s1);
+        if (F::is_zero(h)) {
+            if (F::is_zero(rr)) dbl(r, p);
+            else set_inf(r);
+            return;
+        }
+        F::dbl(rr, rr);
+        F::dbl(i, h); F::sqr(i, i);
+        F::mul(j, h, i);
+        F::mul(v, u1, i);
+        F::add(t, p.Z, q.Z); F::sqr(t, t); F::sub(t, t, z1z1); F::sub(t, t, z2z2); F::mul(t, t, h);
+        E x3, y3;
+        F::sqr(x3, rr); F::sub(x3, x3, j); F::sub(x3, x3, v); F::sub(x3, x3, v);
+        F::sub(y3, v, x3); F::mul(y3, rr, y3);
+        F::mul(j, s1, j); F::dbl(j, j);
+        F::sub(y3, y3, j);
+        r.X = x3; r.Y = y3; r.Z = t;
+    }
+
+    // Jacobian -> homogeneous projective (x = X'/Z', y = Y'/Z') for the shared normalisation kernel:
+    // (X*Z : Y : Z^3); the identity maps to (0 : 1 : 0).
+    ECB_DEV static void to_proj(typename EC<C>::Proj& o, const J& p) {
+        if (is_inf(p)) { EC<C>::set_identity(o); return; }
+        E zz;
+        F::sqr(zz, p.Z);
+        F::mul(o.X, p.X, p.Z);
+        o.Y = p.Y;
+        F::mul(o.Z, zz, p.Z);
+    }
+
+    // signed radix-16 digit i of a value biased by 0x88..8 (see K256Glv::bias): magnitude 0..8, negate mask
+    ECB_DEV static void digit16(const u32* a, int i, int top, u32& mag, u32& neg) {
+        if (i == top) { mag = a[top >> 3]; neg = 0; return; }
+        int d = (int)((a[i >> 3] >> ((i & 7) * 4)) & 15u) - 8;
+        neg = (u32)(d >> 31);
+        mag = (u32)((d ^ (int)neg) - (int)neg);
+    }
+    ECB_DEV static void cneg_y(A& a, u32 mask) {
+        E ny;
+        F::neg(ny, a.y);
+        F::cmov(a.y, ny, mask);
+    }
+
+    // ---- u1 * G from the big fixed-base table: tab[(w << gw) + v] = v * 2^(gw*w) * G (affine limbs, v >= 1)
+    ECB_DEV static void add_fixed_base(J& acc, const u32* u1, const u32* tab, int gw) {
+        const int nwin = (32 * L + gw - 1) / gw;
+        const u32 vmask = (1u << gw) - 1u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int w = 0; w < nwin; w++) {
+            const int bit = w * gw;
+            u32 v = (u1[bit >> 5] >> (bit & 31)) & vmask;   // gw divides 32
+            if (v) {
+                A g;
+                const u32* e = tab + ((size_t)((size_t)w << gw) + v) * 2 * L;
+                ECB_UNROLL
+                for (int l = 0; l < L; l++) { g.x.v[l] = e[l]; g.y.v[l] = e[L + l]; }
+                madd(acc, acc, g, nullptr);
+            }
+        }
+    }
+
+    // ---- generic (a = -3) variable-base part: acc = k * Q, signed radix-16, Jacobian table {1..8}Q
+    ECB_DEV static void mul_window_signed(J& acc, const A& Q, const u32* k) {
+        J tab[9];
+        set_inf(tab[0]);
+        from_affine(tab[1], Q);
+        dbl(tab[2], tab[1]);
+        madd(tab[3], tab[2], Q, nullptr);
+        dbl(tab[4], tab[2]);
+        madd(tab[5], tab[4], Q, nullptr);
+        dbl(tab[6], tab[3]);
+        madd(tab[7], tab[6], Q, nullptr);
+        dbl(tab[8], tab[4]);
+        u32 kb[L + 1];
+        kb[0] = add_cc(k[0], 0x88888888u);
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) kb[i] = addc_cc(k[i], 0x88888888u);
+        kb[L] = addc(0u, 0u);
+        set_inf(acc);
+        const int top = 8 * L;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int i = top; i >= 0; i--) {
+            if (i != top) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int d = 0; d < 4; d++) dbl(acc, acc);
+            }
+            u32 mag, neg;
+            digit16(kb, i, top, mag, neg);
+            if (mag) {
+                J e = tab[mag];
+                E ny;
+                F::neg(ny, e.Y);
+                F::cmov(e.Y, ny, neg);
+                add(acc, acc, e);
+            }
+        }
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// secp256k1: GLV + shared-Z table on the isomorphic curve
+struct K256Fast {
+    typedef CurveK256 C;
+    typedef Jac<C> JJ;
+    typedef JJ::J J;
+    typedef JJ::A A;
+    typedef FpK256 F;
+    typedef F::E E;
+
+    // acc = (r1 + r2*lambda) * Q with the split s (|r1|, |r2| < 2^128, signs in s.neg*): 128 doublings,
+    // <= 66 mixed additions.  Q must be a valid affine point (not the identity).
+    ECB_DEV static void mul_glv(J& acc, const A& Q, const K256Glv::Split& s) {
+        // 1) multiples 1..8 of Q in Jacobian form, each with zr = Z_j / Z_{j-1}
+        J t[9];
+        E zr[9];
+        JJ::from_affine(t[1], Q);
+        JJ::dbl(t[2], t[1]);                       // Z2 = 2 y1  (Z1 = 1)
+        zr[2] = t[2].Z;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 3; j <= 8; j++) {   // (j-1)Q + Q never hits an exceptional case (the order of Q is a large prime)
+            J prev = t[j - 1], cur;      // copies: no dynamically indexed local elements by reference into a real call
+            E z;
+            JJ::madd(cur, prev, Q, &z);
+            t[j] = cur;
+            zr[j] = z;
+        }
+        // 2) rescale entries 1..7 to Z8: entry j gets (x * zs^2, y * zs^3) with zs = Z8 / Zj = prod_{i>j} zr_i
+        A tab[9];
+        tab[8].x = t[8].X; tab[8].y = t[8].Y;
+        E zs = zr[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 7; j >= 1; j--) {
+            E zs2, zs3;
+            F::sqr(zs2, zs);
+            F::mul(zs3, zs2, zs);
+            F::mul(tab[j].x, t[j].X, zs2);
+            F::mul(tab[j].y, t[j].Y, zs3);
+            if (j > 1) F::mul(zs, zs, zr[j]);
+        }
+        // tab[1..8] are now affine points of the isomorphic curve y^2 = x^3 + 7*Z8^6 (global Z = Z8)
+        E beta;
+        ECB_UNROLL
+        for (int l = 0; l < 8; l++) beta.v[l] = C::beta(l);
+        JJ::set_inf(acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int i = 32; i >= 0; i--) {
+            if (i != 32) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int d = 0; d < 4; d++) JJ::dbl(acc, acc);
+            }
+            u32 mag, neg;
+            K256Glv::digit(s.a1, i, mag, neg);
+            if (mag) {
+                A e = tab[mag];
+                JJ::cneg_y(e, neg ^ s.neg1);
+                JJ::madd(acc, acc, e, nullptr);
+            }
+            K256Glv::digit(s.a2, i, mag, neg);
+            if (mag) {
+                A e = tab[mag];
+                F::mul(e.x, e.x, beta);
+                JJ::cneg_y(e, neg ^ s.neg2);
+                JJ::madd(acc, acc, e, nullptr);
+            }
+        }
+        // 3) back to the real curve: Z *= Z8
+        if (!JJ::is_inf(acc)) F::mul(acc.Z, acc.Z, t[8].Z);
+    }
+};
+
+}  // namespace ecb

@@ -12,6 +12,7 @@
 //   internal affine tables: 2L limbs per entry (x|y).
 #pragma once
 #include "ec.cuh"
+#include "jac.cuh"
 
 namespace ecb {
 
@@ -326,6 +327,171 @@ template <class C> struct Bodies {
             }
             R = acc;
         }
+    }
+
+
+    // ------------------------------------------------------------------ ECDSA verify, fast path (v2)
+    // Two kernels.  (1) prep: everything mod n — range / low-s checks, w = s^-1 by Montgomery's trick over the
+    // PREP_EPT rows a thread owns (one Fermat inversion per thread instead of one per row), u1 = z w,
+    // u2 = r w, and for secp256k1 the GLV split of u2.  Results go to a per-row scratch record.
+    // (2) main: everything mod p — key validation, u2*Q (Jacobian, jac.cuh), u1*G from the big fixed-base
+    // table, inversion-free comparison of x(R) mod n with r.
+    static constexpr int PREP_EPT = 16;
+    static constexpr int PREP_WORDS = C::A_IS_ZERO ? 20 : 2 * L + 4;   // u32 words per row of scratch
+    ECB_DEV static void body_verify_prep(int tid, int nthreads, int n, const u8* z, const u8* rs, u32* scratch) {
+        typename Fn::E pref[PREP_EPT];
+        typename Fn::E acc;
+        Fn::set_one(acc);
+        int cnt = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < PREP_EPT; j++) {
+            int i = tid + j * nthreads;
+            if (i >= n) break;
+            u32 s[L];
+            load_be<L>(s, rs + (size_t)i * 2 * FB + FB);
+            if (!scalar_in_range(s)) { zero_n<L>(s); s[0] = 1; }
+            typename Fn::E sm;
+            Fn::from_limbs(sm, s);
+            pref[j] = acc;
+            Fn::mul(acc, acc, sm);
+            cnt++;
+        }
+        if (cnt == 0) return;
+        typename Fn::E inv;
+        Fn::inv(inv, acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = cnt - 1; j >= 0; j--) {
+            int i = tid + j * nthreads;
+            u32 r[L], s[L], zz[L];
+            load_be<L>(r, rs + (size_t)i * 2 * FB);
+            load_be<L>(s, rs + (size_t)i * 2 * FB + FB);
+            bool valid = scalar_in_range(r) && scalar_in_range(s);
+            if constexpr (C::LOW_S) {   // k256/src/ecdsa.rs:203-205
+                u32 hn[L];
+                ECB_UNROLL
+                for (int l = 0; l < L; l++) hn[l] = C::half_n(l);
+                valid = valid && geq_n<L>(hn, s);
+            }
+            if (!scalar_in_range(s)) { zero_n<L>(s); s[0] = 1; }
+            typename Fn::E sm, wm;
+            Fn::from_limbs(sm, s);
+            Fn::mul(wm, inv, pref[j]);       // s_i^-1 (Montgomery form)
+            Fn::mul(inv, inv, sm);
+            G::load_scalar(zz, z + (size_t)i * FB);
+            u32 u1[L], u2[L];
+            Fn::mul_plain(u1, zz, wm);
+            Fn::mul_plain(u2, r, wm);
+            u32* o = scratch + (size_t)i * PREP_WORDS;
+            ECB_UNROLL
+            for (int l = 0; l < L; l++) o[l] = u1[l];
+            if constexpr (C::A_IS_ZERO) {
+                K256Glv::Split sp;
+                K256Glv::decompose(sp, u2);
+                ECB_UNROLL
+                for (int l = 0; l < 5; l++) { o[8 + l] = sp.a1[l]; o[13 + l] = sp.a2[l]; }
+                o[18] = (valid ? 1u : 0u) | (sp.neg1 & 2u) | (sp.neg2 & 4u);
+                o[19] = 0;
+            } else {
+                ECB_UNROLL
+                for (int l = 0; l < L; l++) o[L + l] = u2[l];
+                o[2 * L] = valid ? 1u : 0u;
+            }
+        }
+    }
+
+    typedef Jac<C> JJ;
+    ECB_DEV static bool finish_verify_jac(const typename JJ::J& R, const u32* r, bool valid) {
+        // accept <=> Z != 0 and (X == r Z^2 or (r + n < p and X == (r + n) Z^2))
+        E re, t, zz;
+        bool okr = F::from_limbs(re, r);
+        F::sqr(zz, R.Z);
+        F::mul(t, re, zz);
+        bool hit = F::eq(t, R.X);
+        u32 pmn[L], nn[L], rn[L];
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) { pmn[i] = C::p_minus_n(i); nn[i] = C::n(i); }
+        bool second = !geq_n<L>(r, pmn);
+        if (second && !hit) {       // rare: only r < p - n (about 2^-128 of the range for these curves) can have a second candidate
+            add_n<L>(rn, r, nn);
+            E rne;
+            F::from_limbs(rne, rn);
+            F::mul(t, rne, zz);
+            hit = F::eq(t, R.X);
+        }
+        return valid && okr && !F::is_zero(R.Z) && hit;
+    }
+    ECB_DEV static void body_verify_main(int tid, int n, const u8* q, const u8* rs, const u32* scratch, const u32* gbig, int gw, u8* ok_out) {
+        if (tid >= n) return;
+        const u32* rec = scratch + (size_t)tid * PREP_WORDS;
+        Aff Qa;
+        bool valid = G::load_affine(Qa, q + (size_t)tid * 2 * FB);
+        if (!valid) G::generator(Qa);
+        typename JJ::A Q;
+        Q.x = Qa.x; Q.y = Qa.y;
+        u32 u1[L], r[L];
+        ECB_UNROLL
+        for (int l = 0; l < L; l++) u1[l] = rec[l];
+        load_be<L>(r, rs + (size_t)tid * 2 * FB);
+        typename JJ::J acc;
+        if constexpr (C::A_IS_ZERO) {
+            K256Glv::Split sp;
+            ECB_UNROLL
+            for (int l = 0; l < 5; l++) { sp.a1[l] = rec[8 + l]; sp.a2[l] = rec[13 + l]; }
+            u32 fl = rec[18];
+            valid = valid && (fl & 1u);
+            sp.neg1 = (u32)0 - ((fl >> 1) & 1u);
+            sp.neg2 = (u32)0 - ((fl >> 2) & 1u);
+            K256Fast::mul_glv(acc, Q, sp);
+        } else {
+            u32 u2[L];
+            ECB_UNROLL
+            for (int l = 0; l < L; l++) u2[l] = rec[L + l];
+            valid = valid && (rec[2 * L] & 1u);
+            JJ::mul_window_signed(acc, Q, u2);
+        }
+        JJ::add_fixed_base(acc, u1, gbig, gw);
+        ok_out[tid] = finish_verify_jac(acc, r, valid) ? 1 : 0;
+    }
+
+    // ------------------------------------------------------------------ variable-base k*P, vartime fast path (v2)
+    // pts: n x 2FB big-endian affine bytes (aff_limbs == nullptr), or internal affine limbs produced by the
+    // normalisation kernel from projective inputs (all-zero entry = identity); output projective limbs
+    ECB_DEV static void body_mul_var_fast(int tid, int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* out, u8* invalid) {
+        if (tid >= n) return;
+        Aff a;
+        bool ok, isinf;
+        if (aff_limbs) {
+            load_aff_limbs(a, aff_limbs + (size_t)tid * 2 * L);
+            isinf = F::is_zero(a.x) && F::is_zero(a.y);
+            ok = isinf || G::on_curve(a);
+        } else {
+            ok = G::load_affine(a, pts + (size_t)tid * 2 * FB);
+            isinf = inf && inf[tid];
+        }
+        u32 kk[L];
+        G::load_scalar(kk, k + (size_t)tid * FB);
+        Proj r;
+        if (!ok || isinf || is_zero_n<L>(kk)) {
+            G::set_identity(r);
+        } else {
+            typename JJ::A Q;
+            Q.x = a.x; Q.y = a.y;
+            typename JJ::J acc;
+            if constexpr (C::A_IS_ZERO) {
+                K256Glv::Split sp;
+                K256Glv::decompose(sp, kk);
+                K256Fast::mul_glv(acc, Q, sp);
+            } else {
+                JJ::mul_window_signed(acc, Q, kk);
+            }
+            JJ::to_proj(r, acc);
+        }
+        store_proj(out + (size_t)tid * 3 * L, r);
+        if (invalid) invalid[tid] = (ok || isinf) ? 0 : 1;
     }
 
     // ------------------------------------------------------------------ fixed-base k*G -> projective

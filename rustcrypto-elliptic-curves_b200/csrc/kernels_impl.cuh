@@ -26,6 +26,15 @@ template <class C> __global__ void __launch_bounds__(BLK) k_normalize(int n, con
 template <class C> __global__ void __launch_bounds__(BLK) k_verify(int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok) {
     Bodies<C>::body_verify(blockIdx.x * BLK + threadIdx.x, n, q, z, rs, gtab, ok);
 }
+template <class C> __global__ void __launch_bounds__(BLK) k_mul_var_fast(int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
+    Bodies<C>::body_mul_var_fast(blockIdx.x * BLK + threadIdx.x, n, pts, aff_limbs, inf, k, proj, invalid);
+}
+template <class C> __global__ void __launch_bounds__(BLK) k_verify_prep(int n, const u8* z, const u8* rs, u32* scratch) {
+    Bodies<C>::body_verify_prep(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, z, rs, scratch);
+}
+template <class C> __global__ void __launch_bounds__(BLK) k_verify_main(int n, const u8* q, const u8* rs, const u32* scratch, const u32* gbig, int gw, u8* ok) {
+    Bodies<C>::body_verify_main(blockIdx.x * BLK + threadIdx.x, n, q, rs, scratch, gbig, gw, ok);
+}
 template <class C> __global__ void __launch_bounds__(BLK) k_proj_to_bytes(int n, const u32* proj, u8* xyz) {
     int tid = blockIdx.x * BLK + threadIdx.x;
     if (tid >= n) return;
@@ -159,10 +168,30 @@ template <class C> struct Launch {
         k_verify<C><<<grid(n), BLK, 0, s>>>(n, q, z, rs, gtab, ok);
         g_launch_count++;
     }
+    static void mul_var_fast(cudaStream_t s, int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
+        if (n <= 0) return;
+        k_mul_var_fast<C><<<grid(n), BLK, 0, s>>>(n, pts, aff_limbs, inf, k, proj, invalid);
+        g_launch_count++;
+    }
+    static void verify_prep(cudaStream_t s, int n, const u8* z, const u8* rs, u32* scratch) {
+        if (n <= 0) return;
+        int ept = (n + 148 * 4 * BLK - 1) / (148 * 4 * BLK);
+        if (ept < 1) ept = 1;
+        if (ept > Bodies<C>::PREP_EPT) ept = Bodies<C>::PREP_EPT;
+        int threads = (n + ept - 1) / ept;
+        k_verify_prep<C><<<grid(threads), BLK, 0, s>>>(n, z, rs, scratch);
+        g_launch_count++;
+    }
+    static void verify_main(cudaStream_t s, int n, const u8* q, const u8* rs, const u32* scratch, const u32* gbig, int gw, u8* ok) {
+        if (n <= 0) return;
+        k_verify_main<C><<<grid(n), BLK, 0, s>>>(n, q, rs, scratch, gbig, gw, ok);
+        g_launch_count++;
+    }
     static const CurveLaunch* table() {
         static const CurveLaunch t = {
             C::ID, C::L, C::FB, C::A_IS_ZERO ? 8 : 15, C::A_IS_ZERO ? 65 : 0, C::A_IS_ZERO ? 8 : 0, C::COMPRESS_DEFAULT,
-            &field_op, &mul_var, &mul_gen, &load_proj, &normalize, &sum, &proj_to_bytes, &verify, SUM_BLOCKS};
+            &field_op, &mul_var, &mul_gen, &load_proj, &normalize, &sum, &proj_to_bytes, &verify,
+            &mul_var_fast, &verify_prep, &verify_main, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
         return &t;
     }
 };

@@ -26,7 +26,13 @@ struct CurveLaunch {
     void (*proj_to_bytes)(cudaStream_t s, int n, const uint32_t* proj, uint8_t* xyz);
     void (*verify)(cudaStream_t s, int n, const uint8_t* q, const uint8_t* z, const uint8_t* rs, const uint32_t* gtab,
                    uint8_t* ok);
-    // launches issued by the last call of each launcher are counted by the callee through this hook
+    // fast public-input path (jac.cuh)
+    void (*mul_var_fast)(cudaStream_t s, int n, const uint8_t* pts, const uint32_t* aff_limbs, const uint8_t* inf,
+                         const uint8_t* k, uint32_t* proj, uint8_t* invalid);
+    void (*verify_prep)(cudaStream_t s, int n, const uint8_t* z, const uint8_t* rs, uint32_t* scratch);
+    void (*verify_main)(cudaStream_t s, int n, const uint8_t* q, const uint8_t* rs, const uint32_t* scratch,
+                        const uint32_t* gbig, int gw, uint8_t* ok);
+    int prep_words;   // u32 words of scratch per row between verify_prep and verify_main
     int sum_blocks;
 };
 

@@ -74,6 +74,39 @@ template <class C> struct Emu {
         return out;
     }
 
+    // big fixed-base table with gw-bit windows: entry (w << gw) + v = v * 2^(gw*w) * G
+    static std::vector<u32> gbig(int gw) {
+        const int nwin = (32 * L + gw - 1) / gw, per = 1 << gw, ne = nwin * per;
+        std::vector<u8> pts(2 * FB * (size_t)ne), ks(FB * (size_t)ne, 0);
+        typename EC<C>::Aff g;
+        EC<C>::generator(g);
+        u32 t[L];
+        for (int e = 0; e < ne; e++) {
+            C::F::to_limbs(t, g.x); store_be<L>(&pts[2 * FB * (size_t)e], t);
+            C::F::to_limbs(t, g.y); store_be<L>(&pts[2 * FB * (size_t)e + FB], t);
+            int w = e / per, v = e % per, bit = w * gw;
+            for (int b = 0; b < gw; b++) if ((v >> b) & 1) { int pos = bit + b; ks[FB * (size_t)e + FB - 1 - pos / 8] |= (u8)(1u << (pos % 8)); }
+        }
+        std::vector<u32> proj(3 * L * (size_t)ne), out(2 * L * (size_t)ne);
+        for (int i = 0; i < ne; i++) B::body_mul_var_fast(i, ne, pts.data(), nullptr, nullptr, ks.data(), proj.data(), nullptr);
+        normalize(ne, proj.data(), NORM_AFF_LIMBS, 0, nullptr, nullptr, out.data(), 0);
+        return out;
+    }
+    static void verify2(int n, const u8* q, const u8* z, const u8* rs, u8* ok, int nthreads) {
+        static std::vector<u32> gt;
+        const int gw = 4;
+        if (gt.empty()) gt = gbig(gw);
+        std::vector<u32> scratch((size_t)n * B::PREP_WORDS);
+        int need = (n + B::PREP_EPT - 1) / B::PREP_EPT;
+        if (nthreads < need) nthreads = need;
+        for (int t = 0; t < nthreads; t++) B::body_verify_prep(t, nthreads, n, z, rs, scratch.data());
+        for (int i = 0; i < n; i++) B::body_verify_main(i, n, q, rs, scratch.data(), gt.data(), gw, ok);
+    }
+    static void mul_var_fast(int n, const u8* pts, const u8* inf, const u8* k, u8* out, int compress, u8* invalid) {
+        std::vector<u32> proj((size_t)3 * L * n);
+        for (int i = 0; i < n; i++) B::body_mul_var_fast(i, n, pts, nullptr, inf, k, proj.data(), invalid);
+        normalize(n, proj.data(), NORM_SEC1, compress, out, nullptr, nullptr, 0);
+    }
     static void field_op(int which, int op, int n, const u8* a, const u8* b, u8* out, u8* ok) {
         for (int i = 0; i < n; i++) B::body_field_op(i, n, which, op, a, b, out, ok);
     }
@@ -131,6 +164,14 @@ int emu_mul_gen(int curve, int ct, int n, const u8* k, u8* out, int compress) {
 }
 int emu_batch_normalize(int curve, int n, const u8* xyz, u8* xy, u8* inf, int nthreads) {
     DISPATCH(curve, batch_normalize(n, xyz, xy, inf, nthreads));
+    return 0;
+}
+int emu_verify2(int curve, int n, const u8* q, const u8* z, const u8* rs, u8* ok, int nthreads) {
+    DISPATCH(curve, verify2(n, q, z, rs, ok, nthreads));
+    return 0;
+}
+int emu_mul_var_fast(int curve, int n, const u8* pts, const u8* inf, const u8* k, u8* out, int compress, u8* invalid) {
+    DISPATCH(curve, mul_var_fast(n, pts, inf, k, out, compress, invalid));
     return 0;
 }
 int emu_verify(int curve, int n, const u8* q, const u8* z, const u8* rs, u8* ok) {

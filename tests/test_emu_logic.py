@@ -107,6 +107,13 @@ def test_mul_var(cname, ct):
         exp = o.batch_mul_var_affine(c, pb, bytes(inf), kb, bool(compress))
         assert bytes(out) == exp
         assert not any(invalid)
+    if not ct:   # Jacobian fast path (affine inputs)
+        stride = 1 + (fb if c.compress else 2 * fb)
+        out = emu_lib.buf(len(ks) * stride)
+        invalid = emu_lib.buf(len(ks))
+        assert lib.emu_mul_var_fast(c.cid, len(ks), pb, bytes(inf), kb, out, int(c.compress), invalid) == 0
+        assert bytes(out) == o.batch_mul_var_affine(c, pb, bytes(inf), kb)
+        assert not any(invalid)
     # projective inputs with random Z, incl. Z = 0
     xyz = bytearray()
     for i, P in enumerate(pts):
@@ -170,13 +177,17 @@ def test_batch_normalize(cname):
 
 
 def run_verify(c, rows):
+    """runs BOTH verify kernels (complete-formula v1 and the Jacobian fast path) and checks they agree"""
     fb = c.fb
     q = b"".join(r[0][0].to_bytes(fb, "big") + r[0][1].to_bytes(fb, "big") for r in rows)
     z = b"".join(r[1] for r in rows)
     rs = b"".join((r[2] % (1 << 8 * fb)).to_bytes(fb, "big") + (r[3] % (1 << 8 * fb)).to_bytes(fb, "big") for r in rows)
     ok = emu_lib.buf(len(rows))
     assert lib.emu_verify(c.cid, len(rows), q, z, rs, ok) == 0
-    return list(ok), o.batch_verify(c, q, z, rs)
+    ok2 = emu_lib.buf(len(rows))
+    assert lib.emu_verify2(c.cid, len(rows), q, z, rs, ok2, 3) == 0
+    assert list(ok) == list(ok2)
+    return list(ok2), o.batch_verify(c, q, z, rs)
 
 
 @pytest.mark.parametrize("cname", ["k256", "p256", "p384"])
@@ -229,3 +240,16 @@ def test_verify_synthetic(cname):
     got, exp = run_verify(c, rows)
     assert got == list(exp)
     assert 0 < sum(got) < len(got)
+
+
+@pytest.mark.parametrize("cname", CUR)
+def test_verify_exceptional_cases(cname):
+    """P + P, P + (-P) and identity accumulators inside the Jacobian fast path, GLV corner scalars."""
+    from tests import crafted
+    c = o.curve(cname)
+    rows = crafted.exceptional_rows(c)
+    if c.fb == 48:
+        rows = rows[::3]
+    got, exp = run_verify(c, rows)
+    assert got == list(exp)
+    assert sum(got) > 5 and sum(got) < len(got)

@@ -330,6 +330,47 @@ def test_verify_synthetic_mask(eng, cname):
     assert sum(got) >= n // 2 and sum(got) < n
 
 
+@pytest.mark.parametrize("cname", CUR)
+def test_verify_exceptional_cases(eng, cname):
+    """Rows crafted so that the Jacobian fast path meets P + P, P + (-P) and identity accumulators (fixed-base
+    part and window loop), plus GLV corner scalars; both verify kernels must give the oracle's answer."""
+    from tests import crafted
+    c = o.curve(cname)
+    rows = crafted.exceptional_rows(c)
+    keys = [r[0] for r in rows]; hs = [r[1] for r in rows]; sigs = [(r[2], r[3]) for r in rows]
+    got = eng.verify_prehash_batch(cname, keys, hs, sigs)
+    exp = [o.verify_prehash(c, Q, h, r, s) for Q, h, (r, s) in zip(keys, hs, sigs)]
+    assert got == exp
+    assert sum(got) > 5 and sum(got) < len(got)
+
+
+def test_verify_kernels_agree(golden):
+    """The complete-formula verify kernel (ECB200_VERIFY_V1=1) and the Jacobian fast path agree on Wycheproof."""
+    import os
+    import ecb200
+    os.environ["ECB200_VERIFY_V1"] = "1"
+    try:
+        e1 = ecb200.Engine(0)
+    finally:
+        del os.environ["ECB200_VERIFY_V1"]
+    e2 = ecb200.Engine(0)
+    for cname in ("k256", "p256"):
+        c = o.curve(cname)
+        blob = golden["wycheproof"][cname]
+        hf = getattr(hashlib, blob["hash"])
+        keys, hs, sigs = [], [], []
+        for wx, wy, msg, sig, flag in blob["rows"]:
+            rs = o.der_parse_strict(bytes.fromhex(sig), c)
+            if rs is None:
+                continue
+            keys.append((int.from_bytes(bytes.fromhex(wx)[-c.fb:], "big"), int.from_bytes(bytes.fromhex(wy)[-c.fb:], "big")))
+            hs.append(hf(bytes.fromhex(msg)).digest())
+            sigs.append(rs)
+        assert e1.verify_prehash_batch(cname, keys, hs, sigs) == e2.verify_prehash_batch(cname, keys, hs, sigs)
+    e1.close()
+    e2.close()
+
+
 def test_large_batch_properties(eng):
     """Size-independent properties at a large size (2^18 here keeps the GPU test tier short; bench.py runs
     the full BASELINE sizes): (a) k*G via fixed-base == via variable-base with P = G; (b) (k1+k2)G ==
