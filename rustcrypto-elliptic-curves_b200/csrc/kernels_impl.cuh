@@ -7,6 +7,9 @@
 namespace ecb {
 
 constexpr int BLK = 128;   // threads per CTA of the arithmetic kernels (register-heavy: 2-4 CTAs per SM)
+#ifndef ECB_FAST_MIN_CTAS
+#define ECB_FAST_MIN_CTAS 4   // resident CTAs per SM the public-input kernels are compiled for (register cap 65536/(128*N))
+#endif
 
 template <class C> __global__ void __launch_bounds__(BLK) k_field_op(int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
     Bodies<C>::body_field_op(blockIdx.x * BLK + threadIdx.x, n, which, op, a, b, out, ok);
@@ -26,13 +29,13 @@ template <class C> __global__ void __launch_bounds__(BLK) k_normalize(int n, con
 template <class C> __global__ void __launch_bounds__(BLK) k_verify(int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok) {
     Bodies<C>::body_verify(blockIdx.x * BLK + threadIdx.x, n, q, z, rs, gtab, ok);
 }
-template <class C> __global__ void __launch_bounds__(BLK) k_mul_var_fast(int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
+template <class C> __global__ void __launch_bounds__(BLK, ECB_FAST_MIN_CTAS) k_mul_var_fast(int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
     Bodies<C>::body_mul_var_fast(blockIdx.x * BLK + threadIdx.x, n, pts, aff_limbs, inf, k, proj, invalid);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_verify_prep(int n, const u8* z, const u8* rs, u32* scratch) {
     Bodies<C>::body_verify_prep(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, z, rs, scratch);
 }
-template <class C> __global__ void __launch_bounds__(BLK) k_verify_main(int n, const u8* q, const u8* rs, const u32* scratch, const u32* gbig, int gw, u8* ok) {
+template <class C> __global__ void __launch_bounds__(BLK, ECB_FAST_MIN_CTAS) k_verify_main(int n, const u8* q, const u8* rs, const u32* scratch, const u32* gbig, int gw, u8* ok) {
     Bodies<C>::body_verify_main(blockIdx.x * BLK + threadIdx.x, n, q, rs, scratch, gbig, gw, ok);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_proj_to_bytes(int n, const u32* proj, u8* xyz) {
