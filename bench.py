@@ -148,6 +148,7 @@ def run_reference(args):
     from tests import port_lib
     wl = importlib_pkg().workloads
     lib = port_lib.load()
+    lib.port_set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     cores = lib.port_threads()
     curve = "k256"
     # bounded sample: sized for roughly 2 s per step on this host
@@ -220,6 +221,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib_pkg()
     wl = pkg.workloads

@@ -33,34 +33,37 @@ template <class C> struct Jac {
     // ---- doubling
     ECB_POINT_FN static void dbl(J& r, const J& p) {
         if constexpr (C::A_IS_ZERO) {
-            // dbl-2009-l: A=X^2 B=Y^2 C=B^2 D=2((X+B)^2-A-C) E=3A F=E^2 X3=F-2D Y3=E(D-X3)-8C Z3=2YZ
-            E a, b, c, d, e, f, t;
+            // a = 0:  A = X^2, B2 = 2Y^2, C4 = B2^2 (= 4Y^4), D = 2*X*B2 (= 4XY^2), E = 3A,
+            //         X3 = E^2 - 2D, Y3 = E(D - X3) - 2*C4, Z3 = 2YZ        (3M + 4S, 10 add-type ops;
+            // the textbook dbl-2009-l form trades one M for an S but needs 14 add-type ops, and on this
+            // machine the ALU pipe, not the multiplier, is the busier one — profiles/)
+            E a, b2, c4, d, e, t;
             F::sqr(a, p.X);
-            F::sqr(b, p.Y);
-            F::sqr(c, b);
-            F::add(t, p.X, b); F::sqr(t, t); F::sub(t, t, a); F::sub(t, t, c); F::dbl(d, t);
+            F::sqr(b2, p.Y); F::dbl(b2, b2);
+            F::sqr(c4, b2);
+            F::mul(d, p.X, b2); F::dbl(d, d);
             F::dbl(e, a); F::add(e, e, a);
-            F::sqr(f, e);
             F::mul(t, p.Y, p.Z); F::dbl(r.Z, t);
-            F::dbl(t, d); F::sub(r.X, f, t);
+            F::sqr(t, e);
+            F::sub(t, t, d); F::sub(r.X, t, d);
             F::sub(t, d, r.X); F::mul(t, e, t);
-            F::dbl(c, c); F::dbl(c, c); F::dbl(c, c);
-            F::sub(r.Y, t, c);
+            F::dbl(c4, c4);
+            F::sub(r.Y, t, c4);
         } else {
-            // dbl-2001-b (a = -3): delta=Z^2 gamma=Y^2 beta=X*gamma alpha=3(X-delta)(X+delta)
-            // X3=alpha^2-8beta Z3=(Y+Z)^2-gamma-delta Y3=alpha(4beta-X3)-8gamma^2
-            E delta, gamma, beta, alpha, t0, t1;
+            // a = -3: delta = Z^2, g2 = 2Y^2, b2 = X*g2 (= 2 beta), alpha = 3(X - delta)(X + delta),
+            //         X3 = alpha^2 - 4*b2, Z3 = 2YZ, Y3 = alpha(2*b2 - X3) - 2*g2^2    (4M + 4S, 12 add-type ops)
+            E delta, g2, b2, alpha, t0, t1;
             F::sqr(delta, p.Z);
-            F::sqr(gamma, p.Y);
-            F::mul(beta, p.X, gamma);
+            F::sqr(g2, p.Y); F::dbl(g2, g2);
+            F::mul(b2, p.X, g2);
             F::sub(t0, p.X, delta); F::add(t1, p.X, delta); F::mul(t0, t0, t1);
             F::dbl(alpha, t0); F::add(alpha, alpha, t0);
-            F::add(t0, p.Y, p.Z); F::sqr(t0, t0); F::sub(t0, t0, gamma); F::sub(r.Z, t0, delta);
-            F::dbl(t0, beta); F::dbl(t0, t0);            // 4 beta
-            F::dbl(t1, t0);                               // 8 beta
-            F::sqr(r.X, alpha); F::sub(r.X, r.X, t1);
-            F::sub(t0, t0, r.X); F::mul(t0, alpha, t0);
-            F::sqr(t1, gamma); F::dbl(t1, t1); F::dbl(t1, t1); F::dbl(t1, t1);
+            F::mul(t0, p.Y, p.Z); F::dbl(r.Z, t0);
+            F::dbl(b2, b2);                               // 4 beta
+            F::dbl(t1, b2);                               // 8 beta
+            F::sqr(t0, alpha); F::sub(r.X, t0, t1);
+            F::sub(t0, b2, r.X); F::mul(t0, alpha, t0);
+            F::sqr(t1, g2); F::dbl(t1, t1);
             F::sub(r.Y, t0, t1);
         }
     }
@@ -71,13 +74,13 @@ template <class C> struct Jac {
         dbl(r, t);
     }
 
-    // ---- mixed addition r = p + q, q affine and not the identity.  zr (optional) receives Z3 / Z1
+    // ---- mixed addition r = p + q, q affine and not the identity.  zr (optional) receives Z3 / Z1 (= H)
     // (valid only on the generic branch; callers that need it guarantee no exceptional case).
     ECB_POINT_FN static void madd(J& r, const J& p, const A& q, E* zr) {
         if (is_inf(p)) { from_affine(r, q); return; }
-        // madd-2007-bl: Z1Z1=Z1^2 U2=X2*Z1Z1 S2=Y2*Z1*Z1Z1 H=U2-X1 HH=H^2 I=4HH J=H*I rr=2(S2-Y1) V=X1*I
-        // X3=rr^2-J-2V Y3=rr(V-X3)-2Y1*J Z3=(Z1+H)^2-Z1Z1-HH
-        E z1z1, u2, s2, h, hh, i, j, rr, v, t;
+        // madd-2004-hmv (8M + 3S, 7 add-type ops): Z1Z1 = Z1^2, U2 = x2*Z1Z1, S2 = y2*Z1*Z1Z1, H = U2 - X1, R = S2 - Y1,
+        // Z3 = Z1*H, HH = H^2, HHH = H*HH, V = X1*HH, X3 = R^2 - HHH - 2V, Y3 = R(V - X3) - Y1*HHH
+        E z1z1, u2, s2, h, rr, hh, hhh, v, t;
         F::sqr(z1z1, p.Z);
         F::mul(u2, q.x, z1z1);
         F::mul(s2, q.y, p.Z); F::mul(s2, s2, z1z1);
@@ -88,19 +91,17 @@ template <class C> struct Jac {
             else set_inf(r);                         // p == -q
             return;
         }
-        F::dbl(rr, rr);
+        if (zr) *zr = h;
         F::sqr(hh, h);
-        F::dbl(i, hh); F::dbl(i, i);
-        F::mul(j, h, i);
-        F::mul(v, p.X, i);
-        F::add(t, p.Z, h); F::sqr(t, t); F::sub(t, t, z1z1); F::sub(t, t, hh);   // Z3 = 2 Z1 H
-        if (zr) F::dbl(*zr, h);
-        E x3, y3;
-        F::sqr(x3, rr); F::sub(x3, x3, j); F::sub(x3, x3, v); F::sub(x3, x3, v);
+        F::mul(hhh, hh, h);
+        F::mul(v, p.X, hh);
+        E x3, y3, z3;
+        F::mul(z3, p.Z, h);
+        F::sqr(x3, rr); F::sub(x3, x3, hhh); F::dbl(t, v); F::sub(x3, x3, t);
         F::sub(y3, v, x3); F::mul(y3, rr, y3);
-        F::mul(j, p.Y, j); F::dbl(j, j);
-        F::sub(y3, y3, j);
-        r.X = x3; r.Y = y3; r.Z = t;
+        F::mul(t, p.Y, hhh);
+        F::sub(y3, y3, t);
+        r.X = x3; r.Y = y3; r.Z = z3;
     }
 
     // ---- full Jacobian addition r = p + q
