@@ -41,8 +41,102 @@ template <class P> struct Mont {
         select_n<L>(r, (carry != 0) || (bw == 0), u, v);
     }
 
+    // Montgomery reduction for the NIST-style primes p = 2^(32L) + sum_k s_k 2^(32 e_k) - 1 (P-256, P-384, SM2):
+    // n0 = 1, so the row multipliers are the running low limbs themselves and Q*p is a handful of
+    // limb-shifted copies of Q = sum_i m_i 2^(32 i).  No multiplier-pipe instruction is issued at all:
+    //   low half:   Q = t_lo + sum_k s_k (Q << 32 e_k)  (mod R), discovered limb by limb;
+    //   high half:  r = t_hi + Q + sum_k s_k (Q >> 32 (L - e_k)) + (carry out of the low half).
+    // ASC_OK primes (every pair of middle exponents sums to >= L: P-256) run the low half as whole carry
+    // chains, one per term in ascending exponent order, and continue each chain into the high half; the
+    // others (P-384, SM2) find Q column by column with a signed two-word accumulator.
+    ECB_DEV static void redc_sparse(u32* r, u32* t) {
+        u32 h[L], top = 0;
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) h[i] = t[L + i];
+        if constexpr (P::ASC_OK) {
+            u32 cs[P::NT];
+            ECB_UNROLL
+            for (int k = 0; k < P::NT; k++) {
+                const int e = P::te(k);
+                if (P::ts(k) > 0) {
+                    t[e] = add_cc(t[e], t[0]);
+                    ECB_UNROLL
+                    for (int i = e + 1; i < L; i++) t[i] = addc_cc(t[i], t[i - e]);
+                    cs[k] = addc(0u, 0u);
+                } else {
+                    t[e] = sub_cc(t[e], t[0]);
+                    ECB_UNROLL
+                    for (int i = e + 1; i < L; i++) t[i] = subc_cc(t[i], t[i - e]);
+                    cs[k] = subc(0u, 0u) & 1u;
+                }
+            }
+            // t[0..L) is Q now; continue every chain through the high half
+            ECB_UNROLL
+            for (int k = 0; k < P::NT; k++) {
+                const int e = P::te(k);
+                if (P::ts(k) > 0) {
+                    add_cc(cs[k], 0xFFFFFFFFu);                      // carry flag := saved carry
+                    ECB_UNROLL
+                    for (int j = 0; j < L; j++) h[j] = addc_cc(h[j], j < e ? t[L - e + j] : 0u);
+                    top = addc(top, 0u);
+                } else {
+                    sub_cc(0u, cs[k]);                               // borrow flag := saved borrow
+                    ECB_UNROLL
+                    for (int j = 0; j < L; j++) h[j] = subc_cc(h[j], j < e ? t[L - e + j] : 0u);
+                    top = subc(top, 0u);
+                }
+            }
+        } else {
+            u32 q[L], alo = 0, ahi = 0;
+            ECB_UNROLL
+            for (int i = 0; i < L; i++) {
+                if (i < P::te(0)) { q[i] = t[i]; continue; }         // no term reaches these limbs
+                alo = add_cc(alo, t[i]);
+                ahi = addc(ahi, 0u);
+                ECB_UNROLL
+                for (int k = 0; k < P::NT; k++) {
+                    if (P::te(k) > i) continue;
+                    if (P::ts(k) > 0) { alo = add_cc(alo, q[i - P::te(k)]); ahi = addc(ahi, 0u); }
+                    else { alo = sub_cc(alo, q[i - P::te(k)]); ahi = subc(ahi, 0u); }
+                }
+                q[i] = alo;
+                alo = ahi;
+                ahi = (u32)((int)ahi >> 31);
+            }
+            ECB_UNROLL
+            for (int i = 0; i < L; i++) t[i] = q[i];
+            ECB_UNROLL
+            for (int k = 0; k < P::NT; k++) {
+                const int e = P::te(k);
+                if (P::ts(k) > 0) {
+                    h[0] = add_cc(h[0], t[L - e]);
+                    ECB_UNROLL
+                    for (int j = 1; j < L; j++) h[j] = addc_cc(h[j], j < e ? t[L - e + j] : 0u);
+                    top = addc(top, 0u);
+                } else {
+                    h[0] = sub_cc(h[0], t[L - e]);
+                    ECB_UNROLL
+                    for (int j = 1; j < L; j++) h[j] = subc_cc(h[j], j < e ? t[L - e + j] : 0u);
+                    top = subc(top, 0u);
+                }
+            }
+            // signed carry out of the low half (alo, sign-extended by ahi)
+            h[0] = add_cc(h[0], alo);
+            ECB_UNROLL
+            for (int j = 1; j < L; j++) h[j] = addc_cc(h[j], ahi);
+            top = addc(top, ahi);
+        }
+        // + Q * 2^(32L)
+        h[0] = add_cc(h[0], t[0]);
+        ECB_UNROLL
+        for (int j = 1; j < L; j++) h[j] = addc_cc(h[j], t[j]);
+        top = addc(top, 0u);
+        final_sub(r, h, top);
+    }
+
     // Montgomery reduction of t[0..2L): r = t * R^-1 mod p   (t < p * R)
     ECB_DEV static void redc(u32* r, u32* t) {
+        if constexpr (P::SPARSE) { redc_sparse(r, t); return; }
         // Row i adds m_i * p at limb i as two aligned-pair carry chains (even j, odd j).  The chain
         // carry-outs (weight i+L and i+L+1) never feed a later m_i, so they are collected in cy[]
         // and added once at the end instead of being rippled to the top in every row.

@@ -253,3 +253,34 @@ def test_verify_exceptional_cases(cname):
     got, exp = run_verify(c, rows)
     assert got == list(exp)
     assert sum(got) > 5 and sum(got) < len(got)
+
+
+@pytest.mark.parametrize("cname", CUR)
+@pytest.mark.parametrize("which", [0, 1])
+def test_field_mul_structured_limbs(cname, which):
+    """Operands built from extreme 32-bit limbs (0, 1, 2^32-1, 2^32-2, 2^31, random): exercises every carry /
+    borrow path of the reductions (special-form fold for k256, shifted-addition Montgomery for the sparse primes)."""
+    c = o.curve(cname)
+    m = c.p if which == 0 else c.n
+    L = c.fb // 4
+    rng = random.Random(99 + which + 7 * c.cid)
+    pool = [0, 1, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 0x7FFFFFFF, 2]
+
+    def val():
+        v = 0
+        for i in range(L):
+            limb = rng.choice(pool) if rng.random() < 0.8 else rng.getrandbits(32)
+            v |= limb << (32 * i)
+        return v % m
+
+    A = [val() for _ in range(3000)]
+    B = [val() for _ in range(3000)]
+    got, ok = field_op(c, which, 2, A, B)
+    assert all(ok)
+    assert got == [a * b % m for a, b in zip(A, B)]
+    got, _ = field_op(c, which, 3, A)
+    assert got == [a * a % m for a in A]
+    got, _ = field_op(c, which, 0, A, B)
+    assert got == [(a + b) % m for a, b in zip(A, B)]
+    got, _ = field_op(c, which, 1, A, B)
+    assert got == [(a - b) % m for a, b in zip(A, B)]
