@@ -107,12 +107,13 @@ __global__ void __launch_bounds__(512, 2) k_mix(u32* sink, u64* cycles, u32 seed
 template <int MIX>
 static void run(int nsm, u32* sink, u64* cyc_d, double clk_mhz, bool last) {
     int grid = nsm * 2, block = 512;
-    k_mix<MIX><<<grid, block>>>(sink, cyc_d, 1);
+    // warm up long enough for the SM clock to reach its boost state (a cold 0.3 ms launch runs at ~1.3 GHz)
+    for (int r = 0; r < 100; r++) k_mix<MIX><<<grid, block>>>(sink, cyc_d, 1);
     CK(cudaDeviceSynchronize());
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0));
-    const int REP = 5;
+    const int REP = 300;   // >= 50 ms per mix: event-timed chip-wide rate at the sustained clock
     for (int r = 0; r < REP; r++) k_mix<MIX><<<grid, block>>>(sink, cyc_d, r + 2);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));

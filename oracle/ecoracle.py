@@ -446,6 +446,149 @@ def sm2_z_hash(distid: bytes, Q: Point) -> bytes:
 
 
 # ----------------------------------------------------------------------------------------------
+# "next" rows of the hot path: point decompression, public-key recovery, BIP340 Schnorr
+# verification, signing.  Third-party bodies (ecdsa 0.16.9 recovery.rs / hazmat.rs, rfc6979 0.4) are restated
+# and anchored on the reference's own vectors (k256/src/ecdsa.rs:278-343, k256/src/schnorr.rs:217-445,
+# */src/test_vectors/ecdsa.rs, p256/src/ecdsa.rs:98-118).
+
+def decompress(c: Curve, x: int, y_is_odd: int) -> Optional[Point]:
+    """DecompressPoint::decompress — k256 affine.rs:184-202, primeorder affine.rs:129-150: x >= p or a
+    non-residue right-hand side -> None; otherwise the root whose parity matches."""
+    if not 0 <= x < c.p:
+        return None
+    y = sqrt_mod(c, (x * x * x + c.a * x + c.b) % c.p)
+    if y is None:
+        return None
+    if (y & 1) != (y_is_odd & 1):
+        y = (c.p - y) % c.p
+    return (x, y)
+
+
+def sign_prehashed(c: Curve, d: int, k: int, z_bytes: bytes) -> Optional[Tuple[int, int, int]]:
+    """hazmat::sign_prehashed (ecdsa 0.16.9) + the k256 wrapper (k256/src/ecdsa.rs:181-198):
+    R = k*G, r = x(R) mod n, s = k^-1 (z + r d); recid = y_odd | x_reduced << 1; k256 normalises s to the low
+    half and flips the parity bit when it does.  None <=> Err (k = 0, r = 0 or s = 0).  d, k in [0, n)."""
+    if not (0 < k < c.n):
+        return None
+    z = reduce_once(c, int.from_bytes(z_bytes, "big"))
+    R = mul_gen(c, k)
+    r = reduce_once(c, R[0])
+    x_reduced = 1 if r != R[0] else 0
+    s = inv_mod(k, c.n) * (z + r * d) % c.n
+    if r == 0 or s == 0:
+        return None
+    y_odd = R[1] & 1
+    if c.low_s and s > c.n >> 1:
+        s = c.n - s
+        y_odd ^= 1
+    return r, s, y_odd | (x_reduced << 1)
+
+
+def rfc6979_k(c: Curve, d: int, z_bytes: bytes, hashname: str = "sha256", ad: bytes = b"") -> int:
+    """rfc6979::generate_k as driven by SignPrimitive::try_sign_prehashed_rfc6979: HMAC-DRBG over
+    int2octets(d) || bits2octets(z) || ad, candidates until 0 < k < n.  Host-side in the reference too."""
+    import hmac
+    hl = hashlib.new(hashname).digest_size
+    x = d.to_bytes(c.fb, "big")
+    h = reduce_once(c, int.from_bytes(z_bytes, "big")).to_bytes(c.fb, "big")
+    V, K = b"\x01" * hl, b"\x00" * hl
+    mac = lambda key, msg: hmac.new(key, msg, hashname).digest()
+    K = mac(K, V + b"\x00" + x + h + ad); V = mac(K, V)
+    K = mac(K, V + b"\x01" + x + h + ad); V = mac(K, V)
+    while True:
+        T = b""
+        while len(T) < c.fb:
+            V = mac(K, V)
+            T += V
+        k = int.from_bytes(T[:c.fb], "big")
+        if 0 < k < c.n:
+            return k
+        K = mac(K, V + b"\x00"); V = mac(K, V)
+
+
+def recover_from_prehash(c: Curve, prehash: bytes, r: int, s: int, recid: int) -> Optional[Point]:
+    """VerifyingKey::recover_from_prehash (ecdsa 0.16.9 recovery.rs; call sites k256/src/ecdsa.rs:300-340).
+    recid bit 0 = y of R is odd, bit 1 = x of R was reduced mod n.  None <=> Err."""
+    if not (1 <= r < c.n and 1 <= s < c.n) or not 0 <= recid <= 3:
+        return None
+    zb = bits2field(c, prehash)
+    if zb is None:
+        return None
+    z = reduce_once(c, int.from_bytes(zb, "big"))
+    x = r
+    if recid & 2:
+        x = r + c.n
+        if x >> (8 * c.fb):          # checked_add overflow
+            return None
+    R = decompress(c, x, recid & 1)  # x >= p fails inside (FieldElement::from_bytes)
+    if R is None:
+        return None
+    r_inv = inv_mod(r, c.n)
+    u1 = (-(r_inv * z)) % c.n
+    u2 = r_inv * s % c.n
+    Q = pt_lincomb(c, [(c.G, u1), (R, u2)])
+    if Q is None:                    # VerifyingKey::from_affine rejects the identity
+        return None
+    if not verify_prehashed(c, Q, zb, r, s):   # "ensure signature verifies with the recovered key"
+        return None
+    return Q
+
+
+def tagged_hash(tag: bytes, *parts: bytes) -> bytes:
+    """BIP340 tagged hash (k256/src/schnorr.rs:180-186)."""
+    th = hashlib.sha256(tag).digest()
+    h = hashlib.sha256(th + th)
+    for p_ in parts:
+        h.update(p_)
+    return h.digest()
+
+
+def schnorr_challenge(r_bytes: bytes, pk_bytes: bytes, msg: bytes) -> bytes:
+    """The 32-byte digest whose reduction is e (k256/src/schnorr/verifying.rs:69-75); hashing stays on the host."""
+    return tagged_hash(b"BIP0340/challenge", r_bytes, pk_bytes, msg)
+
+
+def schnorr_verify_raw(pk_x: bytes, e_bytes: bytes, sig: bytes) -> bool:
+    """BIP340 verification after hashing — k256/src/schnorr/verifying.rs:35-45 (key = lift_x, even y),
+    schnorr.rs:143-160 (signature parsing: r < p, r != 0, s in [1, n-1]), verifying.rs:63-89:
+    R = s*G - e*P; accept <=> R != identity, y(R) even, x(R) == r."""
+    c = K256
+    if len(pk_x) != 32 or len(sig) != 64 or len(e_bytes) != 32:
+        return False
+    P = decompress(c, int.from_bytes(pk_x, "big"), 0)
+    if P is None:
+        return False
+    r, s = int.from_bytes(sig[:32], "big"), int.from_bytes(sig[32:], "big")
+    if not (0 < r < c.p) or not (1 <= s < c.n):
+        return False
+    e = reduce_once(c, int.from_bytes(e_bytes, "big"))
+    R = pt_lincomb(c, [(c.G, s), (P, (c.n - e) % c.n)])
+    return R is not None and (R[1] & 1) == 0 and R[0] == r
+
+
+def schnorr_verify_prehash(pk_x: bytes, msg32: bytes, sig: bytes) -> bool:
+    if len(msg32) != 32 or len(sig) != 64:
+        return False
+    return schnorr_verify_raw(pk_x, schnorr_challenge(sig[:32], pk_x, msg32), sig)
+
+
+def schnorr_sign_prehash(d: int, msg32: bytes, aux: bytes) -> bytes:
+    """BIP340 signing with auxiliary randomness (k256/src/schnorr/signing.rs) — used to replay the signing vectors."""
+    c = K256
+    P = mul_gen(c, d)
+    if P[1] & 1:
+        d = c.n - d
+    t = (d ^ int.from_bytes(tagged_hash(b"BIP0340/aux", aux), "big")).to_bytes(32, "big")
+    pk = P[0].to_bytes(32, "big")
+    k0 = int.from_bytes(tagged_hash(b"BIP0340/nonce", t, pk, msg32), "big") % c.n
+    R = mul_gen(c, k0)
+    k = c.n - k0 if R[1] & 1 else k0
+    rb = R[0].to_bytes(32, "big")
+    e = int.from_bytes(schnorr_challenge(rb, pk, msg32), "big") % c.n
+    return rb + ((k + e * d) % c.n).to_bytes(32, "big")
+
+
+# ----------------------------------------------------------------------------------------------
 # strict DER (ecdsa::der::Signature::from_der as exercised by the Wycheproof runners)
 
 def der_parse_strict(sig: bytes, c: Curve) -> Optional[Tuple[int, int]]:

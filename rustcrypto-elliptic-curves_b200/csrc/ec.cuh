@@ -16,10 +16,12 @@ namespace ecb {
 // kernel keeps the instruction footprint of the window loops small (the bodies are 2-6 k SASS
 // instructions each) and the build time bounded; the ~100 local-memory moves per call are noise next
 // to the ~14 field multiplications inside.
+#ifndef ECB_POINT_FN
 #if defined(__CUDACC__) && !defined(ECB_EMU)
 #define ECB_POINT_FN __device__ __noinline__
 #else
 #define ECB_POINT_FN inline
+#endif
 #endif
 
 template <class C> struct EC {

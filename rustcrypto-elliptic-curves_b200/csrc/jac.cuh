@@ -182,16 +182,15 @@ template <class C> struct Jac {
 
     // ---- generic (a = -3) variable-base part: acc = k * Q, signed radix-16, Jacobian table {1..8}Q
     ECB_DEV static void mul_window_signed(J& acc, const A& Q, const u32* k) {
-        J tab[9];
-        set_inf(tab[0]);
-        from_affine(tab[1], Q);
-        dbl(tab[2], tab[1]);
-        madd(tab[3], tab[2], Q, nullptr);
-        dbl(tab[4], tab[2]);
-        madd(tab[5], tab[4], Q, nullptr);
-        dbl(tab[6], tab[3]);
-        madd(tab[7], tab[6], Q, nullptr);
-        dbl(tab[8], tab[4]);
+        J tab[8];                                  // tab[j-1] = j*Q
+        from_affine(tab[0], Q);
+        dbl(tab[1], tab[0]);
+        madd(tab[2], tab[1], Q, nullptr);
+        dbl(tab[3], tab[1]);
+        madd(tab[4], tab[3], Q, nullptr);
+        dbl(tab[5], tab[2]);
+        madd(tab[6], tab[5], Q, nullptr);
+        dbl(tab[7], tab[3]);
         u32 kb[L + 1];
         kb[0] = add_cc(k[0], 0x88888888u);
         ECB_UNROLL
@@ -212,7 +211,7 @@ template <class C> struct Jac {
             u32 mag, neg;
             digit16(kb, i, top, mag, neg);
             if (mag) {
-                J e = tab[mag];
+                J e = tab[mag - 1];
                 E ny;
                 F::neg(ny, e.Y);
                 F::cmov(e.Y, ny, neg);
@@ -235,38 +234,44 @@ struct K256Fast {
     // acc = (r1 + r2*lambda) * Q with the split s (|r1|, |r2| < 2^128, signs in s.neg*): 128 doublings,
     // <= 66 mixed additions.  Q must be a valid affine point (not the identity).
     ECB_DEV static void mul_glv(J& acc, const A& Q, const K256Glv::Split& s) {
-        // 1) multiples 1..8 of Q in Jacobian form, each with zr = Z_j / Z_{j-1}
-        J t[9];
-        E zr[9];
-        JJ::from_affine(t[1], Q);
-        JJ::dbl(t[2], t[1]);                       // Z2 = 2 y1  (Z1 = 1)
-        zr[2] = t[2].Z;
+        // 1) multiples 1..8 of Q in Jacobian form; only (X_j, Y_j) and zr_j = Z_j / Z_{j-1} are kept
+        //    (tab[j-1], zr[j-2]) - 736 bytes of local memory per thread instead of the 1.7 KB of full J entries
+        A tab[8];
+        E zr[7];
+        J cur;
+        tab[0] = Q;
+        {
+            J one;
+            JJ::from_affine(one, Q);
+            JJ::dbl(cur, one);                      // Z2 = 2 y1  (Z1 = 1)
+        }
+        tab[1].x = cur.X; tab[1].y = cur.Y; zr[0] = cur.Z;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
         for (int j = 3; j <= 8; j++) {   // (j-1)Q + Q never hits an exceptional case (the order of Q is a large prime)
-            J prev = t[j - 1], cur;      // copies: no dynamically indexed local elements by reference into a real call
+            J prev = cur;
             E z;
             JJ::madd(cur, prev, Q, &z);
-            t[j] = cur;
-            zr[j] = z;
+            tab[j - 1].x = cur.X; tab[j - 1].y = cur.Y;
+            zr[j - 2] = z;
         }
+        const E z8 = cur.Z;
         // 2) rescale entries 1..7 to Z8: entry j gets (x * zs^2, y * zs^3) with zs = Z8 / Zj = prod_{i>j} zr_i
-        A tab[9];
-        tab[8].x = t[8].X; tab[8].y = t[8].Y;
-        E zs = zr[8];
+        E zs = zr[6];
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
         for (int j = 7; j >= 1; j--) {
-            E zs2, zs3;
+            E zs2, zs3, x = tab[j - 1].x, y = tab[j - 1].y;
             F::sqr(zs2, zs);
             F::mul(zs3, zs2, zs);
-            F::mul(tab[j].x, t[j].X, zs2);
-            F::mul(tab[j].y, t[j].Y, zs3);
-            if (j > 1) F::mul(zs, zs, zr[j]);
+            F::mul(x, x, zs2);
+            F::mul(y, y, zs3);
+            tab[j - 1].x = x; tab[j - 1].y = y;
+            if (j > 1) { E f = zr[j - 2]; F::mul(zs, zs, f); }
         }
-        // tab[1..8] are now affine points of the isomorphic curve y^2 = x^3 + 7*Z8^6 (global Z = Z8)
+        // tab[0..7] = {1..8}Q are now affine points of the isomorphic curve y^2 = x^3 + 7*Z8^6 (global Z = Z8)
         E beta;
         ECB_UNROLL
         for (int l = 0; l < 8; l++) beta.v[l] = C::beta(l);
@@ -284,20 +289,20 @@ struct K256Fast {
             u32 mag, neg;
             K256Glv::digit(s.a1, i, mag, neg);
             if (mag) {
-                A e = tab[mag];
+                A e = tab[mag - 1];
                 JJ::cneg_y(e, neg ^ s.neg1);
                 JJ::madd(acc, acc, e, nullptr);
             }
             K256Glv::digit(s.a2, i, mag, neg);
             if (mag) {
-                A e = tab[mag];
+                A e = tab[mag - 1];
                 F::mul(e.x, e.x, beta);
                 JJ::cneg_y(e, neg ^ s.neg2);
                 JJ::madd(acc, acc, e, nullptr);
             }
         }
         // 3) back to the real curve: Z *= Z8
-        if (!JJ::is_inf(acc)) F::mul(acc.Z, acc.Z, t[8].Z);
+        if (!JJ::is_inf(acc)) F::mul(acc.Z, acc.Z, z8);
     }
 };
 

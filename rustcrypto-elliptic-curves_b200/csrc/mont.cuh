@@ -189,13 +189,28 @@ template <class P> struct Mont {
         u32 c = add_n<L>(v, a.v, b.v);
         final_sub(r.v, v, c);
     }
+    // p(i) & m for an all-ones / zero mask m; the sparse primes only have limbs 0, 1, 2^32-2, 2^32-1
+    ECB_DEV static u32 masked_p(int i, u32 m) {
+        return P::p(i) == 0u ? 0u : P::p(i) == 0xFFFFFFFFu ? m : P::p(i) == 1u ? (m >> 31) : P::p(i) == 0xFFFFFFFEu ? (m << 1) : (P::p(i) & m);
+    }
     ECB_DEV static void sub(E& r, const E& a, const E& b) {
-        u32 v[L], u[L];
-        u32 bw = sub_n<L>(v, a.v, b.v);
-        u[0] = add_cc(v[0], P::p(0));
+        u32 v[L];
+        v[0] = sub_cc(a.v[0], b.v[0]);
         ECB_UNROLL
-        for (int i = 1; i < L; i++) u[i] = addc_cc(v[i], P::p(i));
-        select_n<L>(r.v, bw != 0, u, v);
+        for (int i = 1; i < L; i++) v[i] = subc_cc(a.v[i], b.v[i]);
+        const u32 m = subc(0u, 0u);                 // 0xFFFFFFFF on borrow, else 0
+        if constexpr (P::SPARSE) {
+            // + p on borrow with mask-derived operands: no select pass
+            r.v[0] = add_cc(v[0], masked_p(0, m));
+            ECB_UNROLL
+            for (int i = 1; i < L; i++) r.v[i] = addc_cc(v[i], masked_p(i, m));
+        } else {
+            u32 u[L];
+            u[0] = add_cc(v[0], P::p(0));
+            ECB_UNROLL
+            for (int i = 1; i < L; i++) u[i] = addc_cc(v[i], P::p(i));
+            select_n<L>(r.v, m != 0, u, v);
+        }
     }
     ECB_DEV static void neg(E& r, const E& a) {
         E z;

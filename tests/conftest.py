@@ -21,4 +21,4 @@ def load_golden(name):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {n: load_golden(n) for n in ("group", "field", "ecdsa", "wycheproof", "misc")}
+    return {n: load_golden(n) for n in ("group", "field", "ecdsa", "wycheproof", "misc", "next")}

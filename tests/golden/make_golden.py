@@ -107,6 +107,35 @@ def blobby_rows(path):
     return rows
 
 
+def keccak256(data: bytes) -> bytes:
+    """Keccak-256 (original padding 0x01, as sha3::Keccak256) — only to turn the reference's Ethereum-style
+    vectors into prehashes; hashing is outside the hot path."""
+    RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B, 0x0000000080000001,
+          0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088, 0x0000000080008009, 0x000000008000000A,
+          0x000000008000808B, 0x800000000000008B, 0x8000000000008089, 0x8000000000008003, 0x8000000000008002, 0x8000000000000080,
+          0x000000000000800A, 0x800000008000000A, 0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008]
+    ROT = [[0, 36, 3, 41, 18], [1, 44, 10, 45, 2], [62, 6, 43, 15, 61], [28, 55, 25, 21, 56], [27, 20, 39, 8, 14]]
+    M = (1 << 64) - 1
+    rol = lambda v, n: ((v << n) | (v >> (64 - n))) & M if n else v
+    rate = 136
+    msg = bytearray(data) + b"\x01" + b"\x00" * ((-len(data) - 2) % rate) + b"\x80" if (len(data) + 1) % rate else bytearray(data) + b"\x81"
+    A = [[0] * 5 for _ in range(5)]
+    for off in range(0, len(msg), rate):
+        for i in range(rate // 8):
+            A[i % 5][i // 5] ^= int.from_bytes(msg[off + 8 * i:off + 8 * i + 8], "little")
+        for rc in RC:
+            C = [A[x][0] ^ A[x][1] ^ A[x][2] ^ A[x][3] ^ A[x][4] for x in range(5)]
+            D = [C[(x - 1) % 5] ^ rol(C[(x + 1) % 5], 1) for x in range(5)]
+            A = [[A[x][y] ^ D[x] for y in range(5)] for x in range(5)]
+            B = [[0] * 5 for _ in range(5)]
+            for x in range(5):
+                for y in range(5):
+                    B[y][(2 * x + 3 * y) % 5] = rol(A[x][y], ROT[x][y])
+            A = [[B[x][y] ^ ((~B[(x + 1) % 5][y]) & B[(x + 2) % 5][y]) for y in range(5)] for x in range(5)]
+            A[0][0] ^= rc
+    return b"".join(A[i % 5][i // 5].to_bytes(8, "little") for i in range(4))
+
+
 def main():
     group = {c: group_vectors(c) for c in ("k256", "p256", "p384")}
     field = {c: field_vectors(c) for c in ("k256", "p256")}
@@ -165,6 +194,49 @@ def main():
     # k256 bench fixed scalars: k256/benches/scalar.rs:14-35, ecdsa.rs:13-37
     misc["k256_bench_scalars"] = {"source": "k256/benches/scalar.rs,ecdsa.rs",
                                   "hexes": hexes(read("k256/benches/scalar.rs")) + hexes(read("k256/benches/ecdsa.rs"))}
+
+    # ---- "next" rows: BIP340 vectors, public-key recovery vectors
+    t = read("k256/src/schnorr.rs")
+    tt = t[t.index("const BIP340_SIGN_VECTORS"):t.index("fn bip340_sign_vectors")]
+    sign = []
+    for blk in tt.split("SignVector {")[1:]:
+        idx = int(re.search(r"index:\s*(\d+)", blk).group(1))
+        sk, pk, aux, msg, sig = hexes(blk)
+        sign.append({"index": idx, "secret_key": sk, "public_key": pk, "aux_rand": aux, "message": msg, "signature": sig})
+    tt = t[t.index("const BIP340_VERIFY_VECTORS"):t.index("fn bip340_verify_vectors")]
+    ver = []
+    for blk in tt.split("VerifyVector {")[1:]:
+        idx = int(re.search(r"index:\s*(\d+)", blk).group(1))
+        pk, msg, sig = hexes(blk)
+        ver.append({"index": idx, "public_key": pk, "message": msg, "signature": sig,
+                    "valid": re.search(r"valid:\s*(true|false)", blk).group(1) == "true"})
+    t = read("k256/src/ecdsa.rs")
+    tt = t[t.index("const RECOVERY_TEST_VECTORS"):t.index("fn public_key_recovery")]
+    rec = []
+    for blk in tt.split("RecoveryTestVector {")[1:]:
+        pk, sig = hexes(blk)
+        msg = re.search(r'msg:\s*b"([^"]*)"', blk).group(1)
+        yo, xr = re.search(r"RecoveryId::new\((true|false),\s*(true|false)\)", blk).groups()
+        rec.append({"pk": pk, "msg": msg, "hash": "sha256", "sig": sig, "recid": (yo == "true") | ((xr == "true") << 1)})
+    # module-doc example (k256/src/ecdsa.rs:113-140): Keccak256 prehash, recovery id 1
+    doc = t[t.index("### Recovering a [`VerifyingKey`] from a signature"):t.index("assert_eq!(recovered_key, expected_key)")]
+    dh = hexes(re.sub(r"(?m)^//!", "", doc))
+    rec.append({"pk": dh[1], "msg": "example message", "hash": "keccak256", "sig": dh[0], "recid": 1})
+    tt = t[t.index("fn ethereum_end_to_end_example"):t.index("mod wycheproof")]
+    eh = hexes(tt)
+    eth = {"source": "k256/src/ecdsa.rs:310-340", "d": eh[0], "msg": eh[1], "sig": eh[2], "recid": 0, "hash": "keccak256",
+           "prehash": keccak256(bytes.fromhex(eh[1])).hex()}
+    for r_ in rec:
+        m_ = r_["msg"].encode()
+        r_["prehash"] = (keccak256(m_) if r_["hash"] == "keccak256" else __import__("hashlib").sha256(m_).digest()).hex()
+    nxt = {"bip340_sign": {"source": "k256/src/schnorr.rs:217-289", "vectors": sign},
+           "bip340_verify": {"source": "k256/src/schnorr.rs:308-449", "vectors": ver},
+           "k256_recovery": {"source": "k256/src/ecdsa.rs:113-140,278-310", "vectors": rec},
+           "k256_ethereum_sign_recover": eth}
+    with open(os.path.join(OUT, "next.json"), "w") as f:
+        json.dump(nxt, f, indent=0, separators=(",", ":"))
+        f.write("\n")
+    print("next: bip340 sign", len(sign), "verify", len(ver), "recovery", len(rec))
 
     for name, obj in (("group", group), ("field", field), ("ecdsa", ecdsa), ("wycheproof", wyche), ("misc", misc)):
         with open(os.path.join(OUT, name + ".json"), "w") as f:

@@ -179,3 +179,88 @@ def test_batch_normalize_identity_slots():
     P = o.mul_gen(c, 5)
     pts = [(P[0] * 7 % c.p, P[1] * 7 % c.p, 7), (0, 1, 0), (c.gx * 3 % c.p, c.gy * 3 % c.p, 3)]
     assert o.batch_normalize(c, pts) == [P, None, c.G]
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" rows: signing, recovery, BIP340
+
+@pytest.mark.parametrize("cname", ["k256", "p256", "p384"])
+def test_ecdsa_signing_vectors(golden, cname):
+    # the FIPS / RFC vectors carry d and k: sign_prehashed must reproduce (r, s) (ecdsa_core new_signing_test!)
+    c = o.curve(cname)
+    for v in golden["ecdsa"][cname]["vectors"]:
+        d, k, z = H(v["d"]), H(v["k"]), bytes.fromhex(v["m"])
+        zb = o.bits2field(c, z)
+        r, s, recid = o.sign_prehashed(c, d, k, zb)
+        if c.low_s and H(v["s"]) > c.n >> 1:
+            assert (r, c.n - s) == (H(v["r"]), H(v["s"]))
+        else:
+            assert (r, s) == (H(v["r"]), H(v["s"]))
+        assert o.mul_gen(c, d) == (H(v["q_x"]), H(v["q_y"]))
+        assert o.recover_from_prehash(c, z, r, s, recid) == (H(v["q_x"]), H(v["q_y"]))
+        assert o.recover_from_prehash(c, z, r, s, recid ^ 1) != (H(v["q_x"]), H(v["q_y"]))
+
+
+def test_p256_rfc6979_signing(golden):
+    m = golden["misc"]["p256_rfc6979"]
+    d = H(m["d"])
+    for msg, sig in m["sigs"]:
+        z = hashlib.sha256(msg.encode()).digest()
+        k = o.rfc6979_k(o.P256, d, z)
+        r, s, _ = o.sign_prehashed(o.P256, d, k, z)
+        assert "%064x%064x" % (r, s) == sig
+
+
+def test_k256_recovery_vectors(golden):
+    c = o.K256
+    for v in golden["next"]["k256_recovery"]["vectors"]:
+        r, s = H(v["sig"][:64]), H(v["sig"][64:])
+        Q = o.recover_from_prehash(c, bytes.fromhex(v["prehash"]), r, s, v["recid"])
+        assert Q is not None and o.sec1_encode(c, Q, True).hex() == v["pk"]
+        assert o.recover_from_prehash(c, bytes.fromhex(v["prehash"]), r, s, v["recid"] ^ 1) != Q
+    # high-s signatures are rejected by the final verify step (k256/src/ecdsa.rs:203-205)
+    v = golden["next"]["k256_recovery"]["vectors"][0]
+    r, s = H(v["sig"][:64]), H(v["sig"][64:])
+    assert o.recover_from_prehash(c, bytes.fromhex(v["prehash"]), r, c.n - s, v["recid"] ^ 1) is None
+    # recid bit 1 with r + n >= p cannot decompress
+    assert o.recover_from_prehash(c, bytes.fromhex(v["prehash"]), r, s, v["recid"] | 2) is None
+
+
+def test_k256_ethereum_end_to_end(golden):
+    c = o.K256
+    e = golden["next"]["k256_ethereum_sign_recover"]
+    d, z = H(e["d"]), bytes.fromhex(e["prehash"])
+    k = o.rfc6979_k(c, d, z)
+    r, s, recid = o.sign_prehashed(c, d, k, z)
+    assert "%064x%064x" % (r, s) == e["sig"] and recid == e["recid"]
+    assert o.recover_from_prehash(c, z, r, s, recid) == o.mul_gen(c, d)
+
+
+def test_bip340_vectors(golden):
+    for v in golden["next"]["bip340_sign"]["vectors"]:
+        d = H(v["secret_key"])
+        P = o.mul_gen(o.K256, d)
+        assert "%064X" % P[0] == v["public_key"].upper()
+        sig = o.schnorr_sign_prehash(d, bytes.fromhex(v["message"]), bytes.fromhex(v["aux_rand"]))
+        assert sig.hex() == v["signature"].lower(), v["index"]
+        assert o.schnorr_verify_prehash(bytes.fromhex(v["public_key"]), bytes.fromhex(v["message"]), sig)
+    seen = set()
+    for v in golden["next"]["bip340_verify"]["vectors"]:
+        got = o.schnorr_verify_prehash(bytes.fromhex(v["public_key"]), bytes.fromhex(v["message"]), bytes.fromhex(v["signature"]))
+        assert got == v["valid"], v["index"]
+        seen.add(v["index"])
+    assert seen == set(range(4, 15))
+
+
+@pytest.mark.parametrize("cname", ["k256", "p256", "p384", "sm2"])
+def test_decompress_roundtrip(cname):
+    import random
+    c = o.curve(cname)
+    rng = random.Random(3)
+    for _ in range(10):
+        P = o.mul_gen(c, rng.randrange(1, c.n))
+        assert o.decompress(c, P[0], P[1] & 1) == P
+        assert o.decompress(c, P[0], (P[1] & 1) ^ 1) == (P[0], c.p - P[1])
+    assert o.decompress(c, c.p, 0) is None
+    bad = next(x for x in range(1, 50) if o.sqrt_mod(c, (x ** 3 + c.a * x + c.b) % c.p) is None)
+    assert o.decompress(c, bad, 0) is None
