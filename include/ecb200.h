@@ -132,6 +132,73 @@ int ecb200_batch_normalize_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8
 int ecb200_ecdsa_verify_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_q, const uint8_t* d_z,
                             const uint8_t* d_rs, uint8_t* d_ok, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Callers and data formats either side of the path.  Same conventions;
+ * every entry point has a `_dev` twin taking device pointers and a stream.
+ */
+
+/* decode modes of ecb200_decode_points */
+#define ECB200_DECODE_SEC1 0u    /* tag 02/03 + x, tag 04 + x + y, all-zero slot = identity */
+#define ECB200_DECODE_COMPACT 1u /* x only, even root (DecompactPoint; BIP340 x-only keys) */
+
+/* xy[i] = the affine point encoded in slot i; status[i] = 1 point, 2 identity, 0 invalid (xy zeroed unless 1).
+ * Replaces `AffinePoint::from_encoded_point` / `DecompressPoint::decompress` / `DecompactPoint::decompact`
+ * (k256/src/arithmetic/affine.rs:184-211,241-270; primeorder/src/affine.rs:129-195) incl. the square root
+ * (k256 field.rs:220-255, p256 field.rs:385-411, p384 field.rs:95-117).  enc: n slots of `stride` bytes
+ * (stride >= 1+FB for compressed-only input, >= 1+2FB if tag 04 may occur; FB for ECB200_DECODE_COMPACT). */
+int ecb200_decode_points(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* enc, size_t stride, uint32_t mode,
+                         uint8_t* xy, uint8_t* status);
+
+/* ecb200_ecdsa_verify with SEC1-encoded public keys (`VerifyingKey::from_sec1_bytes` + `verify_prehash`):
+ * keys are decoded (decompressed) on the device; an undecodable or identity key gives ok = 0. */
+int ecb200_ecdsa_verify_sec1(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* keys, size_t key_stride,
+                             const uint8_t* z, const uint8_t* rs, uint8_t* ok);
+
+/* keys[i] = SEC1 slot of the public key recovered from (z, r||s, recid); ok[i] = 0 where recovery fails.
+ * Replaces `VerifyingKey::recover_from_prehash` (ecdsa 0.16.9 recovery.rs; call sites and vectors
+ * k256/src/ecdsa.rs:113-140,278-343).  recid: one byte per row, bit 0 = y(R) odd, bit 1 = x(R) was reduced.
+ * Failure cases as in the reference: r, s out of range, r + n overflow / >= p, no square root, identity key,
+ * and (k256) a high-s signature, which the closing `verify_prehash` of the reference rejects. */
+int ecb200_ecdsa_recover(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* z, const uint8_t* rs,
+                         const uint8_t* recid, uint8_t* keys, uint8_t* ok, uint32_t flags);
+
+/* BIP340 Schnorr verification over secp256k1 after hashing.  Replaces the arithmetic of
+ * `schnorr::VerifyingKey::verify_prehash` (k256/src/schnorr/verifying.rs:63-89) plus key / signature parsing
+ * (verifying.rs:35-45, schnorr.rs:143-160).  pk: n x 32 x-only keys; e: n x 32 challenge digests
+ * tagged_hash("BIP0340/challenge", r || pk || msg) (hashing stays with the caller, like the ECDSA prehash;
+ * reduced mod n on the device); sig: n x 64 r||s.  ok = 1 iff lift_x(pk) exists, 0 < r < p, 1 <= s < n and
+ * R = s*G - e*P is finite with even y and x(R) = r. */
+int ecb200_schnorr_verify(ecb200_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* e, const uint8_t* sig,
+                          uint8_t* ok);
+
+/* SM2DSA verification after hashing.  Replaces `sm2::dsa::VerifyingKey::verify_prehash`
+ * (sm2/src/dsa/verifying.rs:130-168): q: n x 64 keys x||y; e: n x 32 digests SM3(Z_A || M); rs: n x 64.
+ * t = r + s (t = 0 rejected), (x1, y1) = s*G + t*P, accept iff r == e + x1 (mod n). */
+int ecb200_sm2dsa_verify(ecb200_ctx* ctx, size_t n, const uint8_t* q, const uint8_t* e, const uint8_t* rs,
+                         uint8_t* ok);
+
+/* ECDSA signing with caller-supplied nonces (RFC 6979 derivation is HMAC work and stays on the host).
+ * Replaces `SignPrimitive::try_sign_prehashed` (ecdsa 0.16.9 hazmat::sign_prehashed; k256/src/ecdsa.rs:181-198
+ * adds low-s normalisation and the parity flip of the recovery id).  d, k: n x FB secret scalars; z: n x FB
+ * prehash after bits2field; rs: n x 2FB; recid: n bytes; ok[i] = 0 (outputs zeroed) when d or k is 0 or >= n, or
+ * r or s is 0.  Constant-time discipline: fixed-base multiplication with full table scans, complete formulas,
+ * masked selections; no branch or address depends on d or k. */
+int ecb200_ecdsa_sign(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d, const uint8_t* k, const uint8_t* z,
+                      uint8_t* rs, uint8_t* recid, uint8_t* ok);
+
+int ecb200_decode_points_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_enc, size_t stride,
+                             uint32_t mode, uint8_t* d_xy, uint8_t* d_status, void* stream);
+int ecb200_ecdsa_verify_sec1_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_keys, size_t key_stride,
+                                 const uint8_t* d_z, const uint8_t* d_rs, uint8_t* d_ok, void* stream);
+int ecb200_ecdsa_recover_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_z, const uint8_t* d_rs,
+                             const uint8_t* d_recid, uint8_t* d_keys, uint8_t* d_ok, uint32_t flags, void* stream);
+int ecb200_schnorr_verify_dev(ecb200_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* d_e,
+                              const uint8_t* d_sig, uint8_t* d_ok, void* stream);
+int ecb200_sm2dsa_verify_dev(ecb200_ctx* ctx, size_t n, const uint8_t* d_q, const uint8_t* d_e, const uint8_t* d_rs,
+                             uint8_t* d_ok, void* stream);
+int ecb200_ecdsa_sign_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_d, const uint8_t* d_k,
+                          const uint8_t* d_z, uint8_t* d_rs, uint8_t* d_recid, uint8_t* d_ok, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,12 @@ if the CUDA library is missing or no B200 is visible, construction raises.
     LinearCombinationExt::lincomb_ext       (mul.rs:313-340)     Engine.lincomb(curve, points, ks)
     VerifyingKey::verify_prehash            (ecdsa.rs:200-209)   Engine.verify_prehash_batch(curve, keys, prehashes, sigs)
     FieldElement / Scalar ops (test hook)   (field_8x32_risc0.rs) Engine.field_op(curve, which, op, a, b)
+    AffinePoint::from_encoded_point / decompress (affine.rs:184-270) Engine.decode_points(curve, enc, stride, mode)
+    VerifyingKey::from_sec1_bytes + verify_prehash               Engine.ecdsa_verify_sec1(curve, keys, stride, z, rs)
+    VerifyingKey::recover_from_prehash      (ecdsa.rs:278-343)   Engine.ecdsa_recover(curve, z, rs, recid)
+    schnorr::VerifyingKey::verify_prehash   (schnorr/verifying.rs:63-89) Engine.schnorr_verify(pk, e, sig)
+    sm2::dsa::VerifyingKey::verify_prehash  (sm2 dsa/verifying.rs:130-168) Engine.sm2dsa_verify(q, e, rs)
+    SignPrimitive::try_sign_prehashed       (ecdsa.rs:181-198)   Engine.ecdsa_sign(curve, d, k, z)
 """
 from __future__ import annotations
 
@@ -37,7 +43,11 @@ ABI_SYMBOLS = [
     "ecb200_version", "ecb200_launch_count", "ecb200_sync", "ecb200_mul_gen", "ecb200_mul_var",
     "ecb200_batch_normalize", "ecb200_lincomb", "ecb200_ecdsa_verify", "ecb200_field_op", "ecb200_mul_gen_dev",
     "ecb200_mul_var_dev", "ecb200_batch_normalize_dev", "ecb200_ecdsa_verify_dev",
+    "ecb200_decode_points", "ecb200_ecdsa_verify_sec1", "ecb200_ecdsa_recover", "ecb200_schnorr_verify", "ecb200_sm2dsa_verify",
+    "ecb200_ecdsa_sign", "ecb200_decode_points_dev", "ecb200_ecdsa_verify_sec1_dev", "ecb200_ecdsa_recover_dev",
+    "ecb200_schnorr_verify_dev", "ecb200_sm2dsa_verify_dev", "ecb200_ecdsa_sign_dev",
 ]
+DECODE_SEC1, DECODE_COMPACT = 0, 1
 
 
 class Ecb200Error(RuntimeError):
@@ -80,6 +90,18 @@ def load_library() -> ctypes.CDLL:
     lib.ecb200_mul_var_dev.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, u8p, u32, vp]
     lib.ecb200_batch_normalize_dev.argtypes = [vp, ci, sz, u8p, u8p, u8p, vp]
     lib.ecb200_ecdsa_verify_dev.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, vp]
+    lib.ecb200_decode_points.argtypes = [vp, ci, sz, u8p, sz, u32, u8p, u8p]
+    lib.ecb200_ecdsa_verify_sec1.argtypes = [vp, ci, sz, u8p, sz, u8p, u8p, u8p]
+    lib.ecb200_ecdsa_recover.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, u8p, u32]
+    lib.ecb200_schnorr_verify.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
+    lib.ecb200_sm2dsa_verify.argtypes = [vp, sz, u8p, u8p, u8p, u8p]
+    lib.ecb200_ecdsa_sign.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, u8p, u8p]
+    lib.ecb200_decode_points_dev.argtypes = [vp, ci, sz, u8p, sz, u32, u8p, u8p, vp]
+    lib.ecb200_ecdsa_verify_sec1_dev.argtypes = [vp, ci, sz, u8p, sz, u8p, u8p, u8p, vp]
+    lib.ecb200_ecdsa_recover_dev.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, u8p, u32, vp]
+    lib.ecb200_schnorr_verify_dev.argtypes = [vp, sz, u8p, u8p, u8p, u8p, vp]
+    lib.ecb200_sm2dsa_verify_dev.argtypes = [vp, sz, u8p, u8p, u8p, u8p, vp]
+    lib.ecb200_ecdsa_sign_dev.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, u8p, u8p, vp]
     _lib = lib
     return lib
 
@@ -256,6 +278,78 @@ class Engine:
         self._check(self.lib.ecb200_field_op(self.h, cid, which, op, n, pa, pb, po, pk), "field_op")
         return bytes(out), bytes(ok)
 
+    # ------------------------------------------------------------------ SURVEY §8f rows (host buffers)
+    def decode_points(self, curve, enc: bytes, stride: int, mode: int = DECODE_SEC1) -> Tuple[bytes, bytes]:
+        """from_encoded_point / decompress / decompact over n fixed-stride slots -> (x||y bytes, status bytes 1/2/0)."""
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = _nbytes(enc) // stride
+        xy, st = bytearray(n * 2 * fb), bytearray(n)
+        pe, a = _as_buf(enc)
+        px, b = _as_buf(xy)
+        ps, c = _as_buf(st)
+        self._check(self.lib.ecb200_decode_points(self.h, cid, n, pe, stride, mode, px, ps), "decode_points")
+        return bytes(xy), bytes(st)
+
+    def ecdsa_verify_sec1(self, curve, keys: bytes, key_stride: int, z: bytes, rs: bytes) -> bytes:
+        """verify_prehash with SEC1-encoded keys (VerifyingKey::from_sec1_bytes), keys decoded on the device."""
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = _nbytes(z) // fb
+        ok = bytearray(n)
+        pk, a = _as_buf(keys)
+        pz, b = _as_buf(z)
+        pr, c = _as_buf(rs)
+        po, d = _as_buf(ok)
+        self._check(self.lib.ecb200_ecdsa_verify_sec1(self.h, cid, n, pk, key_stride, pz, pr, po), "ecdsa_verify_sec1")
+        return bytes(ok)
+
+    def ecdsa_recover(self, curve, z: bytes, rs: bytes, recid: bytes, flags: int = 0) -> Tuple[bytes, bytes]:
+        """VerifyingKey::recover_from_prehash over a batch -> (SEC1 key slots, ok bytes)."""
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = _nbytes(recid)
+        keys, ok = bytearray(n * slot_bytes(cid, flags)), bytearray(n)
+        pz, a = _as_buf(z)
+        pr, b = _as_buf(rs)
+        pi, c = _as_buf(recid)
+        pk, d = _as_buf(keys)
+        po, e = _as_buf(ok)
+        self._check(self.lib.ecb200_ecdsa_recover(self.h, cid, n, pz, pr, pi, pk, po, flags), "ecdsa_recover")
+        return bytes(keys), bytes(ok)
+
+    def schnorr_verify(self, pk: bytes, e: bytes, sig: bytes) -> bytes:
+        """BIP340 verification after hashing: pk n x 32, e n x 32 challenge digests, sig n x 64."""
+        n = _nbytes(pk) // 32
+        ok = bytearray(n)
+        pp, a = _as_buf(pk)
+        pe, b = _as_buf(e)
+        ps, c = _as_buf(sig)
+        po, d = _as_buf(ok)
+        self._check(self.lib.ecb200_schnorr_verify(self.h, n, pp, pe, ps, po), "schnorr_verify")
+        return bytes(ok)
+
+    def sm2dsa_verify(self, q: bytes, e: bytes, rs: bytes) -> bytes:
+        n = _nbytes(e) // 32
+        ok = bytearray(n)
+        pq, a = _as_buf(q)
+        pe, b = _as_buf(e)
+        pr, c = _as_buf(rs)
+        po, d = _as_buf(ok)
+        self._check(self.lib.ecb200_sm2dsa_verify(self.h, n, pq, pe, pr, po), "sm2dsa_verify")
+        return bytes(ok)
+
+    def ecdsa_sign(self, curve, d: bytes, k: bytes, z: bytes) -> Tuple[bytes, bytes, bytes]:
+        """try_sign_prehashed with caller-supplied nonces -> (r||s, recovery ids, ok)."""
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = _nbytes(z) // fb
+        rs, rid, ok = bytearray(n * 2 * fb), bytearray(n), bytearray(n)
+        pd, a = _as_buf(d)
+        pk, b = _as_buf(k)
+        pz, c = _as_buf(z)
+        pr, e = _as_buf(rs)
+        pi, f = _as_buf(rid)
+        po, g = _as_buf(ok)
+        self._check(self.lib.ecb200_ecdsa_sign(self.h, cid, n, pd, pk, pz, pr, pi, po), "ecdsa_sign")
+        return bytes(rs), bytes(rid), bytes(ok)
+
     # ------------------------------------------------------------------ device-pointer API (torch uint8 CUDA tensors)
     @staticmethod
     def _ptr(t):
@@ -279,6 +373,34 @@ class Engine:
         self._check(self.lib.ecb200_ecdsa_verify_dev(self.h, curve_id(curve), n, self._ptr(d_q), self._ptr(d_z), self._ptr(d_rs),
                                                      self._ptr(d_ok), ctypes.c_void_p(stream) if stream else None),
                     "ecdsa_verify_dev")
+
+
+    def ecdsa_verify_sec1_dev(self, curve, n, d_keys, key_stride, d_z, d_rs, d_ok, stream=None):
+        self._check(self.lib.ecb200_ecdsa_verify_sec1_dev(self.h, curve_id(curve), n, self._ptr(d_keys), key_stride, self._ptr(d_z),
+                                                          self._ptr(d_rs), self._ptr(d_ok), ctypes.c_void_p(stream) if stream else None),
+                    "ecdsa_verify_sec1_dev")
+
+    def ecdsa_recover_dev(self, curve, n, d_z, d_rs, d_recid, d_keys, d_ok, flags=0, stream=None):
+        self._check(self.lib.ecb200_ecdsa_recover_dev(self.h, curve_id(curve), n, self._ptr(d_z), self._ptr(d_rs), self._ptr(d_recid),
+                                                      self._ptr(d_keys), self._ptr(d_ok), flags, ctypes.c_void_p(stream) if stream else None),
+                    "ecdsa_recover_dev")
+
+    def schnorr_verify_dev(self, n, d_pk, d_e, d_sig, d_ok, stream=None):
+        self._check(self.lib.ecb200_schnorr_verify_dev(self.h, n, self._ptr(d_pk), self._ptr(d_e), self._ptr(d_sig), self._ptr(d_ok),
+                                                       ctypes.c_void_p(stream) if stream else None), "schnorr_verify_dev")
+
+    def sm2dsa_verify_dev(self, n, d_q, d_e, d_rs, d_ok, stream=None):
+        self._check(self.lib.ecb200_sm2dsa_verify_dev(self.h, n, self._ptr(d_q), self._ptr(d_e), self._ptr(d_rs), self._ptr(d_ok),
+                                                      ctypes.c_void_p(stream) if stream else None), "sm2dsa_verify_dev")
+
+    def ecdsa_sign_dev(self, curve, n, d_d, d_k, d_z, d_rs, d_recid, d_ok, stream=None):
+        self._check(self.lib.ecb200_ecdsa_sign_dev(self.h, curve_id(curve), n, self._ptr(d_d), self._ptr(d_k), self._ptr(d_z), self._ptr(d_rs),
+                                                   self._ptr(d_recid), self._ptr(d_ok), ctypes.c_void_p(stream) if stream else None),
+                    "ecdsa_sign_dev")
+
+    def decode_points_dev(self, curve, n, d_enc, stride, mode, d_xy, d_status, stream=None):
+        self._check(self.lib.ecb200_decode_points_dev(self.h, curve_id(curve), n, self._ptr(d_enc), stride, mode, self._ptr(d_xy),
+                                                      self._ptr(d_status), ctypes.c_void_p(stream) if stream else None), "decode_points_dev")
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:

@@ -75,10 +75,11 @@ struct ecb200_ctx {
     int gw = 16;                             // window width of gbig (ECB200_GW = 4, 8 or 16)
     bool verify_v1 = false;                  // ECB200_VERIFY_V1=1: complete-formula verify kernel (A/B comparisons)
     DevBuf prep, aff;                        // verify_prep scratch; affine limbs of normalised projective inputs
+    DevBuf kxy, kst;                         // decoded keys (x||y) and their status bytes; also xy / identity flags of the Schnorr epilogue
     DevBuf proj;                             // projective scratch (n x 3L limbs) — shared by all entry points
     DevBuf partial, one_point;
-    DevBuf d_in[NSLOT][4], d_out[NSLOT][2];  // staging for host-pointer entry points
-    PinBuf h_in[NSLOT][4], h_out[NSLOT][2];
+    DevBuf d_in[NSLOT][4], d_out[NSLOT][3];  // staging for host-pointer entry points
+    PinBuf h_in[NSLOT][4], h_out[NSLOT][3];
     std::string err;
     uint64_t launches_base = 0;
 };
@@ -284,16 +285,74 @@ int batch_normalize_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const u
     CU(c, cudaGetLastError());
     return 0;
 }
-int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q, const uint8_t* d_z, const uint8_t* d_rs, uint8_t* d_ok, cudaStream_t s) {
-    if (c->verify_v1) {
+enum { VM_ECDSA = 0, VM_SM2DSA = 1, VM_SCHNORR = 2, VM_RECOVER = 3, DEC_SEC1 = 0, DEC_COMPACT = 1, FIN_SCHNORR = 0, FIN_RECOVER = 1 };   // = kernels.cuh
+
+int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q, const uint8_t* d_z, const uint8_t* d_rs, uint8_t* d_ok, cudaStream_t s,
+                int mode = VM_ECDSA) {
+    if (c->verify_v1 && mode == VM_ECDSA) {
         cl->verify(s, (int)n, d_q, d_z, d_rs, c->gtab[cl->id], d_ok);
     } else {
         int r = ensure_gbig(c, cl);
         if (r) return r;
         CU(c, c->prep.reserve(n * (size_t)cl->prep_words * 4));
-        cl->verify_prep(s, (int)n, d_z, d_rs, (uint32_t*)c->prep.p);
-        cl->verify_main(s, (int)n, d_q, d_rs, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok);
+        cl->verify_prep(s, (int)n, mode, d_z, d_rs, (uint32_t*)c->prep.p);
+        cl->verify_main(s, (int)n, mode, d_q, d_rs, d_z, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, nullptr);
     }
+    CU(c, cudaGetLastError());
+    return 0;
+}
+// SEC1 / compact decoding into x||y + status (f1)
+int decode_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_enc, size_t stride, int mode, uint8_t* d_xy, uint8_t* d_status, cudaStream_t s) {
+    cl->decode(s, (int)n, mode, d_enc, (int)stride, d_xy, d_status);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+// ECDSA verification with SEC1-encoded keys: decode on the device, then the ordinary pipeline (an undecodable key
+// becomes x||y = 0, which is off every supported curve, so the row is rejected by the key check of the main kernel)
+int verify_sec1_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_keys, size_t stride, const uint8_t* d_z, const uint8_t* d_rs,
+                     uint8_t* d_ok, cudaStream_t s) {
+    CU(c, c->kxy.reserve(n * 2 * (size_t)cl->FB));
+    CU(c, c->kst.reserve(n));
+    cl->decode(s, (int)n, DEC_SEC1, d_keys, (int)stride, (uint8_t*)c->kxy.p, (uint8_t*)c->kst.p);
+    return verify_core(c, cl, n, (const uint8_t*)c->kxy.p, d_z, d_rs, d_ok, s);
+}
+// BIP340: prep (mod n) -> main (lift_x, s*G - e*P) -> normalise -> byte-level epilogue (R finite, y even, x == r)
+int schnorr_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_pk, const uint8_t* d_e, const uint8_t* d_sig, uint8_t* d_ok, cudaStream_t s) {
+    int r = ensure_gbig(c, cl);
+    if (r) return r;
+    CU(c, c->prep.reserve(n * (size_t)cl->prep_words * 4));
+    CU(c, c->proj.reserve(n * 3 * (size_t)cl->L * 4));
+    CU(c, c->kxy.reserve(n * 2 * (size_t)cl->FB));
+    CU(c, c->kst.reserve(n));
+    cl->verify_prep(s, (int)n, VM_SCHNORR, d_e, d_sig, (uint32_t*)c->prep.p);
+    cl->verify_main(s, (int)n, VM_SCHNORR, d_pk, d_sig, d_e, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, (uint32_t*)c->proj.p);
+    cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 1 /*NORM_XY_BYTES*/, 0, (uint8_t*)c->kxy.p, (uint8_t*)c->kst.p, nullptr);
+    cl->finish(s, (int)n, FIN_SCHNORR, (const uint8_t*)c->kxy.p, 0, (const uint8_t*)c->kst.p, d_sig, d_ok);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+// public-key recovery: prep (r^-1) -> main (decompress R, u1*G + u2*R) -> normalise to SEC1 -> ok &= key != identity
+int recover_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_z, const uint8_t* d_rs, const uint8_t* d_recid, uint8_t* d_keys,
+                 uint8_t* d_ok, uint32_t flags, cudaStream_t s) {
+    int r = ensure_gbig(c, cl);
+    if (r) return r;
+    CU(c, c->prep.reserve(n * (size_t)cl->prep_words * 4));
+    CU(c, c->proj.reserve(n * 3 * (size_t)cl->L * 4));
+    cl->verify_prep(s, (int)n, VM_RECOVER, d_z, d_rs, (uint32_t*)c->prep.p);
+    cl->verify_main(s, (int)n, VM_RECOVER, nullptr, d_rs, d_z, d_recid, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, (uint32_t*)c->proj.p);
+    cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 0, resolve_compress(cl, flags) ? 1 : 0, d_keys, nullptr, nullptr);
+    cl->finish(s, (int)n, FIN_RECOVER, d_keys, (int)slot_bytes(cl, flags), nullptr, nullptr, d_ok);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+// signing: constant-time fixed-base k*G -> normalise -> (r, s, recid)
+int sign_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_d, const uint8_t* d_k, const uint8_t* d_z, uint8_t* d_rs, uint8_t* d_recid,
+              uint8_t* d_ok, cudaStream_t s) {
+    CU(c, c->proj.reserve(n * 3 * (size_t)cl->L * 4));
+    CU(c, c->aff.reserve(n * 2 * (size_t)cl->L * 4));
+    cl->mul_gen(s, true, (int)n, d_k, c->gentab[cl->id], (uint32_t*)c->proj.p);
+    cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, (uint32_t*)c->aff.p);
+    cl->sign_finish(s, (int)n, d_d, d_k, d_z, (const uint32_t*)c->aff.p, d_rs, d_recid, d_ok);
     CU(c, cudaGetLastError());
     return 0;
 }
@@ -330,9 +389,9 @@ int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, co
             CU(c, cudaEventRecord(c->ev_in[slot], c->copy_in));
             CU(c, cudaStreamWaitEvent(c->stream, c->ev_in[slot], 0));
             const uint8_t* di[4];
-            uint8_t* dout_[2];
+            uint8_t* dout_[3];
             for (int k = 0; k < 4; k++) di[k] = (k < n_in && in[k] && in_sz[k]) ? (const uint8_t*)c->d_in[slot][k].p : nullptr;
-            for (int k = 0; k < 2; k++) dout_[k] = (k < n_out && out[k] && out_sz[k]) ? (uint8_t*)c->d_out[slot][k].p : nullptr;
+            for (int k = 0; k < 3; k++) dout_[k] = (k < n_out && out[k] && out_sz[k]) ? (uint8_t*)c->d_out[slot][k].p : nullptr;
             int r = enqueue(cnt, di, dout_, c->stream);
             if (r) return r;
             CU(c, cudaEventRecord(c->ev_done[slot], c->stream));
@@ -413,12 +472,14 @@ void ecb200_destroy(ecb200_ctx* c) {
     }
     c->prep.release();
     c->aff.release();
+    c->kxy.release();
+    c->kst.release();
     c->proj.release();
     c->partial.release();
     c->one_point.release();
     for (int s = 0; s < NSLOT; s++) {
         for (int k = 0; k < 4; k++) { c->d_in[s][k].release(); c->h_in[s][k].release(); }
-        for (int k = 0; k < 2; k++) { c->d_out[s][k].release(); c->h_out[s][k].release(); }
+        for (int k = 0; k < 3; k++) { c->d_out[s][k].release(); c->h_out[s][k].release(); }
         if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]);
         if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]);
         if (c->ev_out[s]) cudaEventDestroy(c->ev_out[s]);
@@ -577,6 +638,130 @@ int ecb200_lincomb(ecb200_ctx* c, int curve, size_t n_terms, const uint8_t* pts,
     CU(c, cudaMemcpyAsync(out_point, d_bytes, out_bytes, cudaMemcpyDeviceToHost, s));
     CU(c, cudaStreamSynchronize(s));
     return 0;
+}
+
+
+// ---- SEC1 decoding, verification with encoded keys, recovery, BIP340, SM2DSA, signing
+int ecb200_decode_points_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_enc, size_t stride, uint32_t mode, uint8_t* d_xy, uint8_t* d_status,
+                             void* stream) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || mode > 1 || (n && (!d_enc || !d_xy || !d_status)) || stride < (size_t)cl->FB + (mode == DEC_SEC1 ? 1 : 0))
+        return fail(c, ECB200_ERR_ARG, "decode_points_dev: bad argument");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return decode_core(c, cl, n, d_enc, stride, (int)mode, d_xy, d_status, pick(c, stream));
+}
+int ecb200_decode_points(ecb200_ctx* c, int curve, size_t n, const uint8_t* enc, size_t stride, uint32_t mode, uint8_t* xy, uint8_t* status) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || mode > 1 || (n && (!enc || !xy || !status)) || stride < (size_t)cl->FB + (mode == DEC_SEC1 ? 1 : 0))
+        return fail(c, ECB200_ERR_ARG, "decode_points: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[1] = {enc};
+    size_t in_sz[1] = {stride};
+    uint8_t* o[2] = {xy, status};
+    size_t o_sz[2] = {(size_t)cl->FB * 2, 1};
+    return run_pipeline(c, n, 1, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return decode_core(c, cl, cnt, di[0], stride, (int)mode, dout[0], dout[1], s);
+    });
+}
+int ecb200_ecdsa_verify_sec1_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_keys, size_t key_stride, const uint8_t* d_z, const uint8_t* d_rs,
+                                 uint8_t* d_ok, void* stream) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!d_keys || !d_z || !d_rs || !d_ok)) || key_stride < (size_t)cl->FB + 1) return fail(c, ECB200_ERR_ARG, "ecdsa_verify_sec1_dev: bad argument");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return verify_sec1_core(c, cl, n, d_keys, key_stride, d_z, d_rs, d_ok, pick(c, stream));
+}
+int ecb200_ecdsa_verify_sec1(ecb200_ctx* c, int curve, size_t n, const uint8_t* keys, size_t key_stride, const uint8_t* z, const uint8_t* rs, uint8_t* ok) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!keys || !z || !rs || !ok)) || key_stride < (size_t)cl->FB + 1) return fail(c, ECB200_ERR_ARG, "ecdsa_verify_sec1: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[3] = {keys, z, rs};
+    size_t in_sz[3] = {key_stride, (size_t)cl->FB, (size_t)cl->FB * 2};
+    uint8_t* o[1] = {ok};
+    size_t o_sz[1] = {1};
+    return run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return verify_sec1_core(c, cl, cnt, di[0], key_stride, di[1], di[2], dout[0], s);
+    });
+}
+int ecb200_ecdsa_recover_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_z, const uint8_t* d_rs, const uint8_t* d_recid, uint8_t* d_keys,
+                             uint8_t* d_ok, uint32_t flags, void* stream) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!d_z || !d_rs || !d_recid || !d_keys || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_recover_dev: bad argument");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return recover_core(c, cl, n, d_z, d_rs, d_recid, d_keys, d_ok, flags, pick(c, stream));
+}
+int ecb200_ecdsa_recover(ecb200_ctx* c, int curve, size_t n, const uint8_t* z, const uint8_t* rs, const uint8_t* recid, uint8_t* keys, uint8_t* ok,
+                         uint32_t flags) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!z || !rs || !recid || !keys || !ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_recover: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[3] = {z, rs, recid};
+    size_t in_sz[3] = {(size_t)cl->FB, (size_t)cl->FB * 2, 1};
+    uint8_t* o[2] = {keys, ok};
+    size_t o_sz[2] = {slot_bytes(cl, flags), 1};
+    return run_pipeline(c, n, 3, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return recover_core(c, cl, cnt, di[0], di[1], di[2], dout[0], dout[1], flags, s);
+    });
+}
+int ecb200_schnorr_verify_dev(ecb200_ctx* c, size_t n, const uint8_t* d_pk, const uint8_t* d_e, const uint8_t* d_sig, uint8_t* d_ok, void* stream) {
+    const CurveLaunch* cl = curve_of(c, ECB200_K256);
+    if (!cl || (n && (!d_pk || !d_e || !d_sig || !d_ok))) return fail(c, ECB200_ERR_ARG, "schnorr_verify_dev: bad argument");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return schnorr_core(c, cl, n, d_pk, d_e, d_sig, d_ok, pick(c, stream));
+}
+int ecb200_schnorr_verify(ecb200_ctx* c, size_t n, const uint8_t* pk, const uint8_t* e, const uint8_t* sig, uint8_t* ok) {
+    const CurveLaunch* cl = curve_of(c, ECB200_K256);
+    if (!cl || (n && (!pk || !e || !sig || !ok))) return fail(c, ECB200_ERR_ARG, "schnorr_verify: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[3] = {pk, e, sig};
+    size_t in_sz[3] = {32, 32, 64};
+    uint8_t* o[1] = {ok};
+    size_t o_sz[1] = {1};
+    return run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return schnorr_core(c, cl, cnt, di[0], di[1], di[2], dout[0], s);
+    });
+}
+int ecb200_sm2dsa_verify_dev(ecb200_ctx* c, size_t n, const uint8_t* d_q, const uint8_t* d_e, const uint8_t* d_rs, uint8_t* d_ok, void* stream) {
+    const CurveLaunch* cl = curve_of(c, ECB200_SM2);
+    if (!cl || (n && (!d_q || !d_e || !d_rs || !d_ok))) return fail(c, ECB200_ERR_ARG, "sm2dsa_verify_dev: bad argument");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return verify_core(c, cl, n, d_q, d_e, d_rs, d_ok, pick(c, stream), VM_SM2DSA);
+}
+int ecb200_sm2dsa_verify(ecb200_ctx* c, size_t n, const uint8_t* q, const uint8_t* e, const uint8_t* rs, uint8_t* ok) {
+    const CurveLaunch* cl = curve_of(c, ECB200_SM2);
+    if (!cl || (n && (!q || !e || !rs || !ok))) return fail(c, ECB200_ERR_ARG, "sm2dsa_verify: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[3] = {q, e, rs};
+    size_t in_sz[3] = {64, 32, 64};
+    uint8_t* o[1] = {ok};
+    size_t o_sz[1] = {1};
+    return run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return verify_core(c, cl, cnt, di[0], di[1], di[2], dout[0], s, VM_SM2DSA);
+    });
+}
+int ecb200_ecdsa_sign_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_d, const uint8_t* d_k, const uint8_t* d_z, uint8_t* d_rs, uint8_t* d_recid,
+                          uint8_t* d_ok, void* stream) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!d_d || !d_k || !d_z || !d_rs || !d_recid || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_sign_dev: bad argument");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return sign_core(c, cl, n, d_d, d_k, d_z, d_rs, d_recid, d_ok, pick(c, stream));
+}
+int ecb200_ecdsa_sign(ecb200_ctx* c, int curve, size_t n, const uint8_t* d, const uint8_t* k, const uint8_t* z, uint8_t* rs, uint8_t* recid, uint8_t* ok) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!d || !k || !z || !rs || !recid || !ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_sign: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[3] = {d, k, z};
+    size_t in_sz[3] = {(size_t)cl->FB, (size_t)cl->FB, (size_t)cl->FB};
+    uint8_t* o[3] = {rs, recid, ok};
+    size_t o_sz[3] = {(size_t)cl->FB * 2, 1, 1};
+    return run_pipeline(c, n, 3, in, in_sz, 3, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return sign_core(c, cl, cnt, di[0], di[1], di[2], dout[0], dout[1], dout[2], s);
+    });
 }
 
 }  // extern "C"

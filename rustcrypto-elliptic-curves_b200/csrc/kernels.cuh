@@ -25,6 +25,16 @@ enum : u32 {
 
 enum : int { NORM_SEC1 = 0, NORM_XY_BYTES = 1, NORM_AFF_LIMBS = 2 };
 
+// what the two-term public-input pipeline (prep -> main -> optional finish) computes
+enum : int {
+    VM_ECDSA = 0,     // u1 = z/s, u2 = r/s, Q from x||y;      accept <=> x(R) mod n == r
+    VM_SM2DSA = 1,    // u1 = s,   u2 = r+s, Q from x||y;      accept <=> (e + x(R)) mod n == r      (sm2/src/dsa/verifying.rs:130-168)
+    VM_SCHNORR = 2,   // u1 = s,   u2 = -e,  Q = lift_x(pk);   R goes to the normalise + finish kernels (k256/src/schnorr/verifying.rs:63-89)
+    VM_RECOVER = 3,   // u1 = -z/r, u2 = s/r, Q = decompress(r [+ n], recid); result point = the public key (ecdsa 0.16.9 recovery.rs)
+};
+enum : int { DEC_SEC1 = 0, DEC_COMPACT = 1 };
+enum : int { FIN_SCHNORR = 0, FIN_RECOVER = 1 };
+
 template <class C> struct Bodies {
     typedef EC<C> G;
     typedef typename G::Proj Proj;
@@ -338,10 +348,16 @@ template <class C> struct Bodies {
     // table, inversion-free comparison of x(R) mod n with r.
     static constexpr int PREP_EPT = 16;
     static constexpr int PREP_WORDS = C::A_IS_ZERO ? 20 : 2 * L + 4;   // u32 words per row of scratch
-    ECB_DEV static void body_verify_prep(int tid, int nthreads, int n, const u8* z, const u8* rs, u32* scratch) {
+    // value inverted by Montgomery's trick in the prep kernel: s for ECDSA, r for recovery (1 when out of range)
+    ECB_DEV static void prep_invertible(u32* v, int mode, const u8* rs_row) {
+        load_be<L>(v, rs_row + (mode == VM_RECOVER ? 0 : FB));
+        if (!scalar_in_range(v)) { zero_n<L>(v); v[0] = 1; }
+    }
+    ECB_DEV static void body_verify_prep(int tid, int nthreads, int n, int mode, const u8* z, const u8* rs, u32* scratch) {
         typename Fn::E pref[PREP_EPT];
-        typename Fn::E acc;
+        typename Fn::E acc, inv;
         Fn::set_one(acc);
+        const bool need_inv = (mode == VM_ECDSA || mode == VM_RECOVER);
         int cnt = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -349,18 +365,18 @@ template <class C> struct Bodies {
         for (int j = 0; j < PREP_EPT; j++) {
             int i = tid + j * nthreads;
             if (i >= n) break;
-            u32 s[L];
-            load_be<L>(s, rs + (size_t)i * 2 * FB + FB);
-            if (!scalar_in_range(s)) { zero_n<L>(s); s[0] = 1; }
-            typename Fn::E sm;
-            Fn::from_limbs(sm, s);
-            pref[j] = acc;
-            Fn::mul(acc, acc, sm);
+            if (need_inv) {
+                u32 s[L];
+                prep_invertible(s, mode, rs + (size_t)i * 2 * FB);
+                typename Fn::E sm;
+                Fn::from_limbs(sm, s);
+                pref[j] = acc;
+                Fn::mul(acc, acc, sm);
+            }
             cnt++;
         }
         if (cnt == 0) return;
-        typename Fn::E inv;
-        Fn::inv(inv, acc);
+        if (need_inv) Fn::inv(inv, acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -369,22 +385,56 @@ template <class C> struct Bodies {
             u32 r[L], s[L], zz[L];
             load_be<L>(r, rs + (size_t)i * 2 * FB);
             load_be<L>(s, rs + (size_t)i * 2 * FB + FB);
-            bool valid = scalar_in_range(r) && scalar_in_range(s);
-            if constexpr (C::LOW_S) {   // k256/src/ecdsa.rs:203-205
+            G::load_scalar(zz, z + (size_t)i * FB);
+            bool valid = scalar_in_range(s);
+            if (mode == VM_SCHNORR) {   // r is a field element: 0 < r < p (k256/src/schnorr.rs:143-160)
+                u32 pp[L];
+                ECB_UNROLL
+                for (int l = 0; l < L; l++) pp[l] = C::p(l);
+                valid = valid && !is_zero_n<L>(r) && !geq_n<L>(r, pp);
+            } else {
+                valid = valid && scalar_in_range(r);
+            }
+            if (C::LOW_S && (mode == VM_ECDSA || mode == VM_RECOVER)) {   // k256/src/ecdsa.rs:203-205 (recovery ends with a verify)
                 u32 hn[L];
                 ECB_UNROLL
                 for (int l = 0; l < L; l++) hn[l] = C::half_n(l);
                 valid = valid && geq_n<L>(hn, s);
             }
-            if (!scalar_in_range(s)) { zero_n<L>(s); s[0] = 1; }
-            typename Fn::E sm, wm;
-            Fn::from_limbs(sm, s);
-            Fn::mul(wm, inv, pref[j]);       // s_i^-1 (Montgomery form)
-            Fn::mul(inv, inv, sm);
-            G::load_scalar(zz, z + (size_t)i * FB);
             u32 u1[L], u2[L];
-            Fn::mul_plain(u1, zz, wm);
-            Fn::mul_plain(u2, r, wm);
+            if (need_inv) {
+                u32 d[L];
+                prep_invertible(d, mode, rs + (size_t)i * 2 * FB);
+                typename Fn::E dm, wm;
+                Fn::from_limbs(dm, d);
+                Fn::mul(wm, inv, pref[j]);       // d_i^-1 (Montgomery form)
+                Fn::mul(inv, inv, dm);
+                if (mode == VM_ECDSA) {
+                    Fn::mul_plain(u1, zz, wm);
+                    Fn::mul_plain(u2, r, wm);
+                } else {                          // recovery: u1 = -(z / r), u2 = s / r
+                    typename Fn::E t, nt;
+                    Fn::mul_plain(t.v, zz, wm);
+                    Fn::neg(nt, t);
+                    copy_n<L>(u1, nt.v);
+                    Fn::mul_plain(u2, s, wm);
+                }
+            } else if (mode == VM_SM2DSA) {       // t = r + s (mod n), t = 0 is rejected
+                typename Fn::E a, b, t;
+                copy_n<L>(a.v, r); copy_n<L>(b.v, s);
+                if (!valid) { Fn::set_zero(a); Fn::set_zero(b); }
+                Fn::add(t, a, b);
+                valid = valid && !Fn::is_zero(t);
+                copy_n<L>(u1, b.v);
+                copy_n<L>(u2, t.v);
+            } else {                              // Schnorr: R = s*G - e*P
+                typename Fn::E e, ne;
+                copy_n<L>(e.v, zz);
+                Fn::neg(ne, e);
+                copy_n<L>(u1, s);
+                if (!valid) zero_n<L>(u1);
+                copy_n<L>(u2, ne.v);
+            }
             u32* o = scratch + (size_t)i * PREP_WORDS;
             ECB_UNROLL
             for (int l = 0; l < L; l++) o[l] = u1[l];
@@ -404,8 +454,11 @@ template <class C> struct Bodies {
     }
 
     typedef Jac<C> JJ;
-    ECB_DEV static bool finish_verify_jac(const typename JJ::J& R, const u32* r, bool valid) {
-        // accept <=> Z != 0 and (X == r Z^2 or (r + n < p and X == (r + n) Z^2))
+    // accept <=> x(R) mod n == t for a target t < n, without leaving Jacobian coordinates:
+    // Z != 0 and (X == t Z^2 or (t + n < p and X == (t + n) Z^2)).  id_x0: the identity counts as x = 0
+    // (SM2DSA reads AffinePoint::IDENTITY.x; ECDSA can never accept it because r >= 1).
+    ECB_DEV static bool finish_verify_jac(const typename JJ::J& R, const u32* r, bool valid, bool id_x0 = false) {
+        if (F::is_zero(R.Z)) return valid && id_x0 && is_zero_n<L>(r);
         E re, t, zz;
         bool okr = F::from_limbs(re, r);
         F::sqr(zz, R.Z);
@@ -422,20 +475,63 @@ template <class C> struct Bodies {
             F::mul(t, rne, zz);
             hit = F::eq(t, R.X);
         }
-        return valid && okr && !F::is_zero(R.Z) && hit;
+        return valid && okr && hit;
     }
-    ECB_DEV static void body_verify_main(int tid, int n, const u8* q, const u8* rs, const u32* scratch, const u32* gbig, int gw, u8* ok_out) {
+    // DecompressPoint::decompress (k256 affine.rs:184-202, primeorder affine.rs:129-150): x limbs (plain) -> point
+    ECB_DEV static bool decompress(typename JJ::A& Q, const u32* x, u32 y_is_odd) {
+        E alpha, beta, t;
+        bool ok = F::from_limbs(Q.x, x);          // rejects x >= p
+        F::sqr(t, Q.x);
+        F::mul(alpha, t, Q.x);
+        if constexpr (!C::A_IS_ZERO) {
+            F::dbl(t, Q.x); F::add(t, t, Q.x);
+            F::sub(alpha, alpha, t);
+        }
+        G::const_b(t);
+        F::add(alpha, alpha, t);
+        F::sqrt_candidate(beta, alpha);
+        F::sqr(t, beta);
+        ok = ok && F::eq(t, alpha);
+        E nb;
+        F::neg(nb, beta);
+        u32 odd = F::is_odd(beta) ? 1u : 0u;
+        F::select(Q.y, odd == (y_is_odd & 1u), beta, nb);
+        return ok;
+    }
+    // q: x||y (ECDSA / SM2DSA), x only (Schnorr); aux: recovery ids (VM_RECOVER), zin: e bytes (VM_SM2DSA target).
+    // VM_SCHNORR / VM_RECOVER write the result point to proj_out (identity for rejected rows) and the validity so far to ok_out.
+    ECB_DEV static void body_verify_main(int tid, int n, int mode, const u8* q, const u8* rs, const u8* zin, const u8* aux,
+                                         const u32* scratch, const u32* gbig, int gw, u8* ok_out, u32* proj_out) {
         if (tid >= n) return;
         const u32* rec = scratch + (size_t)tid * PREP_WORDS;
-        Aff Qa;
-        bool valid = G::load_affine(Qa, q + (size_t)tid * 2 * FB);
-        if (!valid) G::generator(Qa);
         typename JJ::A Q;
-        Q.x = Qa.x; Q.y = Qa.y;
-        u32 u1[L], r[L];
+        bool valid;
+        u32 r[L];
+        load_be<L>(r, rs + (size_t)tid * 2 * FB);
+        if (mode == VM_SCHNORR) {
+            u32 x[L];
+            load_be<L>(x, q + (size_t)tid * FB);
+            valid = decompress(Q, x, 0u);             // lift_x: the even root (k256/src/schnorr/verifying.rs:35-45)
+        } else if (mode == VM_RECOVER) {
+            const u32 id = aux[tid];
+            u32 x[L], nn[L];
+            valid = id < 4u;
+            copy_n<L>(x, r);
+            if (id & 2u) {                            // x(R) was reduced: restore r + n, reject on overflow (>= p fails in decompress)
+                ECB_UNROLL
+                for (int i = 0; i < L; i++) nn[i] = C::n(i);
+                valid = (add_n<L>(x, r, nn) == 0) && valid;
+            }
+            valid = decompress(Q, x, id & 1u) && valid;
+        } else {
+            Aff Qa;
+            valid = G::load_affine(Qa, q + (size_t)tid * 2 * FB);
+            Q.x = Qa.x; Q.y = Qa.y;
+        }
+        if (!valid) { Aff g; G::generator(g); Q.x = g.x; Q.y = g.y; }
+        u32 u1[L];
         ECB_UNROLL
         for (int l = 0; l < L; l++) u1[l] = rec[l];
-        load_be<L>(r, rs + (size_t)tid * 2 * FB);
         typename JJ::J acc;
         if constexpr (C::A_IS_ZERO) {
             K256Glv::Split sp;
@@ -454,7 +550,169 @@ template <class C> struct Bodies {
             JJ::mul_window_signed(acc, Q, u2);
         }
         JJ::add_fixed_base(acc, u1, gbig, gw);
-        ok_out[tid] = finish_verify_jac(acc, r, valid) ? 1 : 0;
+        if (mode == VM_ECDSA) {
+            ok_out[tid] = finish_verify_jac(acc, r, valid) ? 1 : 0;
+        } else if (mode == VM_SM2DSA) {
+            // target = (r - e) mod n
+            u32 e[L];
+            G::load_scalar(e, zin + (size_t)tid * FB);
+            typename Fn::E a, b, t;
+            copy_n<L>(a.v, r); copy_n<L>(b.v, e);
+            if (!valid) Fn::set_zero(a);              // r may be out of range on rejected rows
+            Fn::sub(t, a, b);
+            ok_out[tid] = finish_verify_jac(acc, t.v, valid, true) ? 1 : 0;
+        } else {
+            Proj o;
+            if (valid) JJ::to_proj(o, acc); else G::set_identity(o);
+            store_proj(proj_out + (size_t)tid * 3 * L, o);
+            ok_out[tid] = valid ? 1 : 0;
+        }
+    }
+
+    // ------------------------------------------------------------------ SEC1 decoding
+    // FromEncodedPoint (k256 affine.rs:241-270, primeorder affine.rs:164-195).  enc: n slots of `stride` bytes.
+    // DEC_SEC1: tag 02/03 + x (stride >= 1+FB), tag 04 + x + y (stride >= 1+2FB), all-zero slot = identity;
+    // DEC_COMPACT: x only, even root (DecompactPoint, BIP340 keys).  status: 1 point, 2 identity, 0 invalid; xy zeroed unless 1.
+    ECB_DEV static void body_decode(int tid, int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
+        if (tid >= n) return;
+        const u8* e = enc + (size_t)tid * stride;
+        u8* o = xy + (size_t)tid * 2 * FB;
+        typename JJ::A Q;
+        u32 st = 0;
+        u32 x[L];
+        if (mode == DEC_COMPACT) {
+            load_be<L>(x, e);
+            st = decompress(Q, x, 0u) ? 1u : 0u;
+        } else {
+            const u32 tag = e[0];
+            if ((tag == 2u || tag == 3u) && stride >= 1 + FB) {
+                load_be<L>(x, e + 1);
+                st = decompress(Q, x, tag & 1u) ? 1u : 0u;
+            } else if (tag == 4u && stride >= 1 + 2 * FB) {
+                Aff a;
+                st = G::load_affine(a, e + 1) ? 1u : 0u;
+                Q.x = a.x; Q.y = a.y;
+            } else if (tag == 0u) {
+                u32 any = 0;
+                for (int b = 1; b < stride; b++) any |= e[b];
+                st = any ? 0u : 2u;
+            }
+        }
+        if (st == 1u) {
+            u32 t[L];
+            F::to_limbs(t, Q.x); store_be<L>(o, t);
+            F::to_limbs(t, Q.y); store_be<L>(o + FB, t);
+        } else {
+            for (int b = 0; b < 2 * FB; b++) o[b] = 0;
+        }
+        status[tid] = (u8)st;
+    }
+
+    // ------------------------------------------------------------------ byte-level epilogues after normalisation
+    // FIN_SCHNORR: ok &= !identity && y even && x == r           (a: x||y bytes, inf: identity flags, rs: r||s)
+    // FIN_RECOVER: ok &= recovered key != identity                (a: SEC1 slots of `stride` bytes)
+    ECB_DEV static void body_finish(int tid, int n, int kind, const u8* a, int stride, const u8* inf, const u8* rs, u8* ok) {
+        if (tid >= n) return;
+        u32 v = ok[tid];
+        if (kind == FIN_SCHNORR) {
+            const u8* xy = a + (size_t)tid * 2 * FB;
+            const u8* r = rs + (size_t)tid * 2 * FB;
+            u32 diff = 0;
+            for (int b = 0; b < FB; b++) diff |= (u32)(xy[b] ^ r[b]);
+            v = v && !inf[tid] && !(xy[2 * FB - 1] & 1u) && diff == 0;
+        } else {
+            v = v && a[(size_t)tid * stride] != 0;
+        }
+        ok[tid] = v ? 1 : 0;
+    }
+
+    // ------------------------------------------------------------------ ECDSA signing epilogue
+    // hazmat::sign_prehashed (ecdsa 0.16.9) + k256 try_sign_prehashed (k256/src/ecdsa.rs:181-198).  R = k*G arrives as
+    // affine limbs from the constant-time fixed-base kernel + normalisation; here r = x(R) mod n,
+    // s = k^-1 (z + r d), recid = y_odd | x_reduced << 1, low-s normalisation for k256.  k^-1 comes from Montgomery's trick
+    // over the rows of a thread.  Secret-dependent values (d, k, k^-1, the point) never steer a branch or an address:
+    // selections are masks, the inversion exponent is public.  ok = 0 (and zeroed outputs) when d or k is 0 or >= n, or r or s is 0.
+    ECB_DEV static bool load_secret_scalar(u32* v, const u8* bytes) {   // plain limbs; false (and v = 1) unless 1 <= v < n
+        load_be<L>(v, bytes);
+        bool ok = scalar_in_range(v);
+        u32 one[L];
+        zero_n<L>(one); one[0] = 1;
+        select_n<L>(v, ok, v, one);
+        return ok;
+    }
+    ECB_DEV static void body_sign_finish(int tid, int nthreads, int n, const u8* d, const u8* k, const u8* z, const u32* aff,
+                                         u8* rs_out, u8* recid_out, u8* ok_out) {
+        typename Fn::E pref[PREP_EPT];
+        typename Fn::E acc, inv;
+        Fn::set_one(acc);
+        int cnt = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < PREP_EPT; j++) {
+            int i = tid + j * nthreads;
+            if (i >= n) break;
+            u32 kk[L];
+            load_secret_scalar(kk, k + (size_t)i * FB);
+            typename Fn::E km;
+            Fn::from_limbs(km, kk);
+            pref[j] = acc;
+            Fn::mul(acc, acc, km);
+            cnt++;
+        }
+        if (cnt == 0) return;
+        Fn::inv(inv, acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = cnt - 1; j >= 0; j--) {
+            int i = tid + j * nthreads;
+            u32 kk[L], dd[L], zz[L];
+            bool ok = load_secret_scalar(kk, k + (size_t)i * FB);
+            ok = load_secret_scalar(dd, d + (size_t)i * FB) && ok;
+            G::load_scalar(zz, z + (size_t)i * FB);
+            typename Fn::E km, kinv;
+            Fn::from_limbs(km, kk);
+            Fn::mul(kinv, inv, pref[j]);            // k_i^-1 (Montgomery form)
+            Fn::mul(inv, inv, km);
+            // r = x(R) mod n, recovery bits
+            Aff R;
+            load_aff_limbs(R, aff + (size_t)i * 2 * L);
+            u32 x[L], y[L], xr[L], nn[L];
+            F::to_limbs(x, R.x);
+            F::to_limbs(y, R.y);
+            ECB_UNROLL
+            for (int l = 0; l < L; l++) nn[l] = C::n(l);
+            u32 bw = sub_n<L>(xr, x, nn);
+            u32 rr[L];
+            select_n<L>(rr, bw == 0, xr, x);
+            u32 recid = (y[0] & 1u) | ((bw == 0) ? 2u : 0u);
+            // s = k^-1 (z + r d)
+            typename Fn::E rm, dm, t, zm, sm;
+            Fn::from_limbs(rm, rr);                  // Montgomery form of r
+            Fn::mul_plain(t.v, dd, rm);              // r*d, plain
+            copy_n<L>(zm.v, zz);
+            Fn::add(t, t, zm);
+            Fn::mul_plain(sm.v, t.v, kinv);          // plain s
+            ok = ok && !is_zero_n<L>(rr) && !Fn::is_zero(sm);
+            if constexpr (C::LOW_S) {                // normalize_s + parity flip (k256/src/ecdsa.rs:192-196)
+                u32 hn[L];
+                ECB_UNROLL
+                for (int l = 0; l < L; l++) hn[l] = C::half_n(l);
+                bool high = !geq_n<L>(hn, sm.v);
+                typename Fn::E ns;
+                Fn::neg(ns, sm);
+                Fn::select(sm, high, ns, sm);
+                recid ^= high ? 1u : 0u;
+            }
+            const u32 m = ok ? 0xFFFFFFFFu : 0u;
+            ECB_UNROLL
+            for (int l = 0; l < L; l++) { rr[l] &= m; sm.v[l] &= m; }
+            store_be<L>(rs_out + (size_t)i * 2 * FB, rr);
+            store_be<L>(rs_out + (size_t)i * 2 * FB + FB, sm.v);
+            recid_out[i] = (u8)(recid & m);
+            ok_out[i] = (u8)(m & 1u);
+        }
     }
 
     // ------------------------------------------------------------------ variable-base k*P, vartime fast path (v2)

@@ -32,11 +32,21 @@ template <class C> __global__ void __launch_bounds__(BLK) k_verify(int n, const 
 template <class C> __global__ void __launch_bounds__(BLK, ECB_FAST_MIN_CTAS) k_mul_var_fast(int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
     Bodies<C>::body_mul_var_fast(blockIdx.x * BLK + threadIdx.x, n, pts, aff_limbs, inf, k, proj, invalid);
 }
-template <class C> __global__ void __launch_bounds__(BLK) k_verify_prep(int n, const u8* z, const u8* rs, u32* scratch) {
-    Bodies<C>::body_verify_prep(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, z, rs, scratch);
+template <class C> __global__ void __launch_bounds__(BLK) k_verify_prep(int n, int mode, const u8* z, const u8* rs, u32* scratch) {
+    Bodies<C>::body_verify_prep(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, mode, z, rs, scratch);
 }
-template <class C> __global__ void __launch_bounds__(BLK, ECB_FAST_MIN_CTAS) k_verify_main(int n, const u8* q, const u8* rs, const u32* scratch, const u32* gbig, int gw, u8* ok) {
-    Bodies<C>::body_verify_main(blockIdx.x * BLK + threadIdx.x, n, q, rs, scratch, gbig, gw, ok);
+// MODE is a template parameter: the ECDSA instance carries no decompression / projective-output code
+template <class C, int MODE> __global__ void __launch_bounds__(BLK, ECB_FAST_MIN_CTAS) k_verify_main(int n, const u8* q, const u8* rs, const u8* z, const u8* aux, const u32* scratch, const u32* gbig, int gw, u8* ok, u32* proj_out) {
+    Bodies<C>::body_verify_main(blockIdx.x * BLK + threadIdx.x, n, MODE, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+}
+template <class C> __global__ void __launch_bounds__(BLK) k_decode(int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
+    Bodies<C>::body_decode(blockIdx.x * BLK + threadIdx.x, n, mode, enc, stride, xy, status);
+}
+template <class C> __global__ void __launch_bounds__(BLK) k_finish(int n, int kind, const u8* a, int stride, const u8* inf, const u8* rs, u8* ok) {
+    Bodies<C>::body_finish(blockIdx.x * BLK + threadIdx.x, n, kind, a, stride, inf, rs, ok);
+}
+template <class C> __global__ void __launch_bounds__(BLK) k_sign_finish(int n, const u8* d, const u8* k, const u8* z, const u32* aff, u8* rs_out, u8* recid_out, u8* ok_out) {
+    Bodies<C>::body_sign_finish(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, d, k, z, aff, rs_out, recid_out, ok_out);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_proj_to_bytes(int n, const u32* proj, u8* xyz) {
     int tid = blockIdx.x * BLK + threadIdx.x;
@@ -176,25 +186,50 @@ template <class C> struct Launch {
         k_mul_var_fast<C><<<grid(n), BLK, 0, s>>>(n, pts, aff_limbs, inf, k, proj, invalid);
         g_launch_count++;
     }
-    static void verify_prep(cudaStream_t s, int n, const u8* z, const u8* rs, u32* scratch) {
-        if (n <= 0) return;
+    static int ept_threads(int n) {   // threads for the Montgomery-trick kernels: as few rows per thread as keeps ~4 CTAs per SM busy
         int ept = (n + 148 * 4 * BLK - 1) / (148 * 4 * BLK);
         if (ept < 1) ept = 1;
         if (ept > Bodies<C>::PREP_EPT) ept = Bodies<C>::PREP_EPT;
-        int threads = (n + ept - 1) / ept;
-        k_verify_prep<C><<<grid(threads), BLK, 0, s>>>(n, z, rs, scratch);
+        return (n + ept - 1) / ept;
+    }
+    static void verify_prep(cudaStream_t s, int n, int mode, const u8* z, const u8* rs, u32* scratch) {
+        if (n <= 0) return;
+        k_verify_prep<C><<<grid(ept_threads(n)), BLK, 0, s>>>(n, mode, z, rs, scratch);
         g_launch_count++;
     }
-    static void verify_main(cudaStream_t s, int n, const u8* q, const u8* rs, const u32* scratch, const u32* gbig, int gw, u8* ok) {
+    static void verify_main(cudaStream_t s, int n, int mode, const u8* q, const u8* rs, const u8* z, const u8* aux, const u32* scratch,
+                            const u32* gbig, int gw, u8* ok, u32* proj_out) {
         if (n <= 0) return;
-        k_verify_main<C><<<grid(n), BLK, 0, s>>>(n, q, rs, scratch, gbig, gw, ok);
+        // Schnorr exists for secp256k1 only, SM2DSA for SM2 only (abi.cu rejects other combinations before launching)
+        if (mode == VM_ECDSA) k_verify_main<C, VM_ECDSA><<<grid(n), BLK, 0, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+        else if (mode == VM_RECOVER) k_verify_main<C, VM_RECOVER><<<grid(n), BLK, 0, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+        else if (mode == VM_SCHNORR) {
+            if constexpr (C::A_IS_ZERO) k_verify_main<C, VM_SCHNORR><<<grid(n), BLK, 0, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+        } else if (mode == VM_SM2DSA) {
+            if constexpr (C::ID == 3) k_verify_main<C, VM_SM2DSA><<<grid(n), BLK, 0, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+        }
+        g_launch_count++;
+    }
+    static void decode(cudaStream_t s, int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
+        if (n <= 0) return;
+        k_decode<C><<<grid(n), BLK, 0, s>>>(n, mode, enc, stride, xy, status);
+        g_launch_count++;
+    }
+    static void finish(cudaStream_t s, int n, int kind, const u8* a, int stride, const u8* inf, const u8* rs, u8* ok) {
+        if (n <= 0) return;
+        k_finish<C><<<grid(n), BLK, 0, s>>>(n, kind, a, stride, inf, rs, ok);
+        g_launch_count++;
+    }
+    static void sign_finish(cudaStream_t s, int n, const u8* d, const u8* k, const u8* z, const u32* aff, u8* rs_out, u8* recid_out, u8* ok_out) {
+        if (n <= 0) return;
+        k_sign_finish<C><<<grid(ept_threads(n)), BLK, 0, s>>>(n, d, k, z, aff, rs_out, recid_out, ok_out);
         g_launch_count++;
     }
     static const CurveLaunch* table() {
         static const CurveLaunch t = {
             C::ID, C::L, C::FB, C::A_IS_ZERO ? 8 : 15, C::A_IS_ZERO ? 65 : 0, C::A_IS_ZERO ? 8 : 0, C::COMPRESS_DEFAULT,
             &field_op, &mul_var, &mul_gen, &load_proj, &normalize, &sum, &proj_to_bytes, &verify,
-            &mul_var_fast, &verify_prep, &verify_main, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
+            &mul_var_fast, &verify_prep, &verify_main, &decode, &finish, &sign_finish, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
         return &t;
     }
 };

@@ -29,9 +29,14 @@ struct CurveLaunch {
     // fast public-input path (jac.cuh)
     void (*mul_var_fast)(cudaStream_t s, int n, const uint8_t* pts, const uint32_t* aff_limbs, const uint8_t* inf,
                          const uint8_t* k, uint32_t* proj, uint8_t* invalid);
-    void (*verify_prep)(cudaStream_t s, int n, const uint8_t* z, const uint8_t* rs, uint32_t* scratch);
-    void (*verify_main)(cudaStream_t s, int n, const uint8_t* q, const uint8_t* rs, const uint32_t* scratch,
-                        const uint32_t* gbig, int gw, uint8_t* ok);
+    // mode = VM_* (kernels.cuh): ECDSA verify, SM2DSA verify, BIP340 Schnorr verify, ECDSA public-key recovery
+    void (*verify_prep)(cudaStream_t s, int n, int mode, const uint8_t* z, const uint8_t* rs, uint32_t* scratch);
+    void (*verify_main)(cudaStream_t s, int n, int mode, const uint8_t* q, const uint8_t* rs, const uint8_t* z, const uint8_t* aux,
+                        const uint32_t* scratch, const uint32_t* gbig, int gw, uint8_t* ok, uint32_t* proj_out);
+    void (*decode)(cudaStream_t s, int n, int mode, const uint8_t* enc, int stride, uint8_t* xy, uint8_t* status);
+    void (*finish)(cudaStream_t s, int n, int kind, const uint8_t* a, int stride, const uint8_t* inf, const uint8_t* rs, uint8_t* ok);
+    void (*sign_finish)(cudaStream_t s, int n, const uint8_t* d, const uint8_t* k, const uint8_t* z, const uint32_t* aff,
+                        uint8_t* rs_out, uint8_t* recid_out, uint8_t* ok_out);
     int prep_words;   // u32 words of scratch per row between verify_prep and verify_main
     int sum_blocks;
 };

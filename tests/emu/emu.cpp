@@ -92,15 +92,45 @@ template <class C> struct Emu {
         normalize(ne, proj.data(), NORM_AFF_LIMBS, 0, nullptr, nullptr, out.data(), 0);
         return out;
     }
-    static void verify2(int n, const u8* q, const u8* z, const u8* rs, u8* ok, int nthreads) {
+    static const std::vector<u32>& gbig4() {
         static std::vector<u32> gt;
+        if (gt.empty()) gt = gbig(4);
+        return gt;
+    }
+    // the two-term pipeline in every mode (VM_*): prep -> main [-> normalise -> finish]
+    static void verify_mode(int mode, int n, const u8* q, const u8* z, const u8* rs, const u8* aux, u8* ok, u8* out, int compress, int nthreads) {
         const int gw = 4;
-        if (gt.empty()) gt = gbig(gw);
-        std::vector<u32> scratch((size_t)n * B::PREP_WORDS);
+        const std::vector<u32>& gt = gbig4();
+        std::vector<u32> scratch((size_t)n * B::PREP_WORDS), proj((size_t)3 * L * n);
         int need = (n + B::PREP_EPT - 1) / B::PREP_EPT;
         if (nthreads < need) nthreads = need;
-        for (int t = 0; t < nthreads; t++) B::body_verify_prep(t, nthreads, n, z, rs, scratch.data());
-        for (int i = 0; i < n; i++) B::body_verify_main(i, n, q, rs, scratch.data(), gt.data(), gw, ok);
+        for (int t = 0; t < nthreads; t++) B::body_verify_prep(t, nthreads, n, mode, z, rs, scratch.data());
+        for (int i = 0; i < n; i++) B::body_verify_main(i, n, mode, q, rs, z, aux, scratch.data(), gt.data(), gw, ok, proj.data());
+        if (mode == VM_SCHNORR) {
+            std::vector<u8> xy((size_t)2 * FB * n), inf(n);
+            normalize(n, proj.data(), NORM_XY_BYTES, 0, xy.data(), inf.data(), nullptr, 0);
+            for (int i = 0; i < n; i++) B::body_finish(i, n, FIN_SCHNORR, xy.data(), 0, inf.data(), rs, ok);
+        } else if (mode == VM_RECOVER) {
+            normalize(n, proj.data(), NORM_SEC1, compress, out, nullptr, nullptr, 0);
+            const int stride = compress ? 1 + FB : 1 + 2 * FB;
+            for (int i = 0; i < n; i++) B::body_finish(i, n, FIN_RECOVER, out, stride, nullptr, nullptr, ok);
+        }
+    }
+    static void verify2(int n, const u8* q, const u8* z, const u8* rs, u8* ok, int nthreads) {
+        verify_mode(VM_ECDSA, n, q, z, rs, nullptr, ok, nullptr, 0, nthreads);
+    }
+    static void decode(int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
+        for (int i = 0; i < n; i++) B::body_decode(i, n, mode, enc, stride, xy, status);
+    }
+    static void sign(int n, const u8* d, const u8* k, const u8* z, u8* rs, u8* recid, u8* ok, int nthreads) {
+        static std::vector<u32> tab;
+        if (C::A_IS_ZERO && tab.empty()) tab = gentab();
+        std::vector<u32> proj((size_t)3 * L * n), aff((size_t)2 * L * n);
+        for (int i = 0; i < n; i++) B::template body_mul_gen<true>(i, n, k, tab.data(), proj.data());
+        normalize(n, proj.data(), NORM_AFF_LIMBS, 0, nullptr, nullptr, aff.data(), 0);
+        int need = (n + B::PREP_EPT - 1) / B::PREP_EPT;
+        if (nthreads < need) nthreads = need;
+        for (int t = 0; t < nthreads; t++) B::body_sign_finish(t, nthreads, n, d, k, z, aff.data(), rs, recid, ok);
     }
     static void mul_var_fast(int n, const u8* pts, const u8* inf, const u8* k, u8* out, int compress, u8* invalid) {
         std::vector<u32> proj((size_t)3 * L * n);
@@ -172,6 +202,20 @@ int emu_verify2(int curve, int n, const u8* q, const u8* z, const u8* rs, u8* ok
 }
 int emu_mul_var_fast(int curve, int n, const u8* pts, const u8* inf, const u8* k, u8* out, int compress, u8* invalid) {
     DISPATCH(curve, mul_var_fast(n, pts, inf, k, out, compress, invalid));
+    return 0;
+}
+int emu_verify_mode(int curve, int mode, int n, const u8* q, const u8* z, const u8* rs, const u8* aux, u8* ok, u8* out, int compress, int nthreads) {
+    if (mode == VM_SCHNORR && curve != 0) return -1;
+    if (mode == VM_SM2DSA && curve != 3) return -1;
+    DISPATCH(curve, verify_mode(mode, n, q, z, rs, aux, ok, out, compress, nthreads));
+    return 0;
+}
+int emu_decode(int curve, int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
+    DISPATCH(curve, decode(n, mode, enc, stride, xy, status));
+    return 0;
+}
+int emu_sign(int curve, int n, const u8* d, const u8* k, const u8* z, u8* rs, u8* recid, u8* ok, int nthreads) {
+    DISPATCH(curve, sign(n, d, k, z, rs, recid, ok, nthreads));
     return 0;
 }
 int emu_verify(int curve, int n, const u8* q, const u8* z, const u8* rs, u8* ok) {

@@ -284,3 +284,66 @@ def test_field_mul_structured_limbs(cname, which):
     assert got == [(a + b) % m for a, b in zip(A, B)]
     got, _ = field_op(c, which, 1, A, B)
     assert got == [(a - b) % m for a, b in zip(A, B)]
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY §8f rows on the host emulation (logic only; parity is asserted on the B200)
+from tests import nextrows  # noqa: E402
+
+VM_ECDSA, VM_SM2DSA, VM_SCHNORR, VM_RECOVER = 0, 1, 2, 3
+
+
+@pytest.mark.parametrize("cname", CUR)
+def test_decode_points(cname):
+    c = o.curve(cname)
+    slots, stride, st, xy = nextrows.decode_cases(c, n_random=4 if c.fb == 48 else 8)
+    n = len(st)
+    got_xy, got_st = emu_lib.buf(n * 2 * c.fb), emu_lib.buf(n)
+    assert lib.emu_decode(c.cid, n, 0, slots, stride, got_xy, got_st) == 0
+    assert bytes(got_st) == st and bytes(got_xy) == xy
+    enc, st, xy = nextrows.compact_cases(c, n_random=3)
+    n = len(st)
+    got_xy, got_st = emu_lib.buf(n * 2 * c.fb), emu_lib.buf(n)
+    assert lib.emu_decode(c.cid, n, 1, enc, c.fb, got_xy, got_st) == 0
+    assert bytes(got_st) == st and bytes(got_xy) == xy
+
+
+@pytest.mark.parametrize("cname", ["k256", "p256"])
+def test_recover(cname, golden):
+    c = o.curve(cname)
+    zb, rsb, ids, exp_keys, exp_ok = nextrows.recover_cases(c, golden, n_random=5)
+    n = len(ids)
+    stride = len(exp_keys) // n
+    ok, keys = emu_lib.buf(n), emu_lib.buf(n * stride)
+    assert lib.emu_verify_mode(c.cid, VM_RECOVER, n, None, zb, rsb, ids, ok, keys, int(c.compress), 3) == 0
+    assert bytes(ok) == exp_ok
+    assert bytes(keys) == exp_keys
+    assert 0 < sum(exp_ok) < n
+
+
+def test_schnorr(golden):
+    pkb, eb, sb, exp = nextrows.schnorr_cases(golden, n_random=4)
+    n = len(exp)
+    ok = emu_lib.buf(n)
+    assert lib.emu_verify_mode(0, VM_SCHNORR, n, pkb, eb, sb, None, ok, None, 0, 2) == 0
+    assert bytes(ok) == exp
+    assert 0 < sum(exp) < n
+
+
+def test_sm2dsa(golden):
+    qb, eb, rsb, exp = nextrows.sm2dsa_cases(golden, n_random=5)
+    n = len(exp)
+    ok = emu_lib.buf(n)
+    assert lib.emu_verify_mode(3, VM_SM2DSA, n, qb, eb, rsb, None, ok, None, 0, 2) == 0
+    assert bytes(ok) == exp
+    assert 0 < sum(exp) < n
+
+
+@pytest.mark.parametrize("cname", ["k256", "p256"])
+def test_sign(cname, golden):
+    c = o.curve(cname)
+    db, kb, zb, rs, rid, okx = nextrows.sign_cases(c, golden, n_random=4)
+    n = len(okx)
+    g_rs, g_rid, g_ok = emu_lib.buf(n * 2 * c.fb), emu_lib.buf(n), emu_lib.buf(n)
+    assert lib.emu_sign(c.cid, n, db, kb, zb, g_rs, g_rid, g_ok, 2) == 0
+    assert bytes(g_ok) == okx and bytes(g_rs) == rs and bytes(g_rid) == rid
