@@ -46,6 +46,7 @@ ABI_SYMBOLS = [
     "ecb200_decode_points", "ecb200_ecdsa_verify_sec1", "ecb200_ecdsa_recover", "ecb200_schnorr_verify", "ecb200_sm2dsa_verify",
     "ecb200_ecdsa_sign", "ecb200_decode_points_dev", "ecb200_ecdsa_verify_sec1_dev", "ecb200_ecdsa_recover_dev",
     "ecb200_schnorr_verify_dev", "ecb200_sm2dsa_verify_dev", "ecb200_ecdsa_sign_dev",
+    "ecb200_kernel_timing", "ecb200_kernel_timing_read",
 ]
 DECODE_SEC1, DECODE_COMPACT = 0, 1
 
@@ -80,6 +81,8 @@ def load_library() -> ctypes.CDLL:
     lib.ecb200_launch_count.argtypes = [vp]
     lib.ecb200_launch_count.restype = ctypes.c_uint64
     lib.ecb200_sync.argtypes = [vp]
+    lib.ecb200_kernel_timing.argtypes = [vp, ci]
+    lib.ecb200_kernel_timing_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
     lib.ecb200_mul_gen.argtypes = [vp, ci, sz, u8p, u8p, u32]
     lib.ecb200_mul_var.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, u8p, u32]
     lib.ecb200_batch_normalize.argtypes = [vp, ci, sz, u8p, u8p, u8p]
@@ -183,6 +186,15 @@ class Engine:
 
     def sync(self):
         self._check(self.lib.ecb200_sync(self.h), "sync")
+
+    def kernel_timing(self, enable: bool):
+        self._check(self.lib.ecb200_kernel_timing(self.h, 1 if enable else 0), "kernel_timing")
+
+    def kernel_timing_read(self) -> Tuple[float, int]:
+        """(summed ms, launches) of the dominant kernel since the last read (CUDA events on its launch stream)."""
+        ms, cnt = ctypes.c_double(), ctypes.c_uint64()
+        self._check(self.lib.ecb200_kernel_timing_read(self.h, ctypes.byref(ms), ctypes.byref(cnt)), "kernel_timing_read")
+        return float(ms.value), int(cnt.value)
 
     # ------------------------------------------------------------------ host-buffer API (bytes in, bytes out)
     def mul_by_generator_batch(self, curve, ks: bytes, flags: int = 0) -> bytes:

@@ -82,6 +82,9 @@ struct ecb200_ctx {
     PinBuf h_in[NSLOT][4], h_out[NSLOT][3];
     std::string err;
     uint64_t launches_base = 0;
+    // optional per-launch timing of the dominant kernel (verify_main) with CUDA events on its own stream
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
 };
 
 namespace {
@@ -296,7 +299,17 @@ int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d
         if (r) return r;
         CU(c, c->prep.reserve(n * (size_t)cl->prep_words * 4));
         cl->verify_prep(s, (int)n, mode, d_z, d_rs, (uint32_t*)c->prep.p);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (c->timing) {
+            CU(c, cudaEventCreate(&e0));
+            CU(c, cudaEventCreate(&e1));
+            CU(c, cudaEventRecord(e0, s));
+        }
         cl->verify_main(s, (int)n, mode, d_q, d_rs, d_z, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, nullptr);
+        if (c->timing) {
+            CU(c, cudaEventRecord(e1, s));
+            c->timed.emplace_back(e0, e1);
+        }
     }
     CU(c, cudaGetLastError());
     return 0;
@@ -496,6 +509,29 @@ int ecb200_sync(ecb200_ctx* c) {
     if (!c) return ECB200_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ecb200_kernel_timing(ecb200_ctx* c, int enable) {
+    if (!c) return ECB200_ERR_ARG;
+    c->timing = enable != 0;
+    return 0;
+}
+int ecb200_kernel_timing_read(ecb200_ctx* c, double* total_ms, uint64_t* launches) {
+    if (!c || !total_ms || !launches) return ECB200_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    double sum = 0;
+    for (auto& pr : c->timed) {
+        CU(c, cudaEventSynchronize(pr.second));
+        float ms = 0;
+        CU(c, cudaEventElapsedTime(&ms, pr.first, pr.second));
+        sum += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    *total_ms = sum;
+    *launches = c->timed.size();
+    c->timed.clear();
     return 0;
 }
 
