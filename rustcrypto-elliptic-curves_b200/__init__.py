@@ -243,17 +243,19 @@ class Engine:
         self._check(self.lib.ecb200_lincomb(self.h, cid, n, pp, pk, po, flags, FLAG_PROJ if out_proj else 0), "lincomb")
         return bytes(out)
 
-    def ecdsa_verify(self, curve, q: bytes, z: bytes, rs: bytes) -> bytes:
-        """ok bytes for n x (Q = x||y, z = bits2field(prehash), r||s)."""
+    def ecdsa_verify(self, curve, q: bytes, z: bytes, rs: bytes, out=None) -> bytes:
+        """ok bytes for n x (Q = x||y, z = bits2field(prehash), r||s).  Buffers may be bytes or numpy uint8 arrays;
+        page-locked arrays (e.g. views of torch pinned tensors) are DMA'd directly, pageable ones are staged.
+        out: optional n-byte numpy array that receives the result (returned as is)."""
         cid, fb = curve_id(curve), field_bytes(curve)
         n = _nbytes(z) // fb
-        ok = bytearray(n)
+        ok = out if out is not None else bytearray(n)
         pq, a = _as_buf(q)
         pz, b = _as_buf(z)
         pr, c = _as_buf(rs)
         po, d = _as_buf(ok)
         self._check(self.lib.ecb200_ecdsa_verify(self.h, cid, n, pq, pz, pr, po), "ecdsa_verify")
-        return bytes(ok)
+        return ok if out is not None else bytes(ok)
 
     def verify_prehash_batch(self, curve, keys: Sequence[Tuple[int, int]], prehashes: Sequence[bytes],
                              sigs: Sequence[Tuple[int, int]]) -> List[bool]:

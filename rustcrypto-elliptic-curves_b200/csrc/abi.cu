@@ -378,26 +378,47 @@ template <class Fn>
 int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, const size_t* in_sz, int n_out, uint8_t* const* out,
                  const size_t* out_sz, Fn&& enqueue) {
     if (n == 0) return 0;
-    size_t nchunks = (n + CHUNK - 1) / CHUNK;
+    // piece 0 is a quarter of the others, so the first (unoverlapped) H2D is short
+    const size_t FIRST = CHUNK / 4;
+    auto piece = [&](size_t ch, size_t& off, size_t& cnt) {
+        off = ch == 0 ? 0 : FIRST + (ch - 1) * CHUNK;
+        cnt = std::min(ch == 0 ? FIRST : CHUNK, n - off);
+    };
+    size_t nchunks = n <= FIRST ? 1 : 1 + (n - FIRST + CHUNK - 1) / CHUNK;
     const size_t cap = std::min(n, CHUNK);   // staging capacity in elements
+    // caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister) are copied from / to directly;
+    // pageable ones go through the context's pinned staging buffers
+    bool in_pinned[4] = {}, out_pinned[3] = {};
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    for (int k = 0; k < n_in; k++) in_pinned[k] = in[k] && in_sz[k] && is_pinned(in[k]);
+    for (int k = 0; k < n_out; k++) out_pinned[k] = out[k] && out_sz[k] && is_pinned(out[k]);
     for (size_t ch = 0; ch < nchunks + 1; ch++) {
         if (ch < nchunks) {
             int slot = (int)(ch % NSLOT);
-            size_t off = ch * CHUNK, cnt = std::min(CHUNK, n - off);
+            size_t off, cnt;
+            piece(ch, off, cnt);
             // slot reuse: its previous D2H must have drained (host copy-out below waits on it) — ensured
             // because chunk ch-NSLOT was fully retired in an earlier iteration.
             for (int k = 0; k < n_in; k++) {
                 if (!in[k] || !in_sz[k]) continue;
                 size_t bytes = cnt * in_sz[k];
                 CU(c, c->d_in[slot][k].reserve(cap * in_sz[k]));
-                CU(c, c->h_in[slot][k].reserve(cap * in_sz[k]));
-                memcpy(c->h_in[slot][k].p, in[k] + off * in_sz[k], bytes);
-                CU(c, cudaMemcpyAsync(c->d_in[slot][k].p, c->h_in[slot][k].p, bytes, cudaMemcpyHostToDevice, c->copy_in));
+                const void* src = in[k] + off * in_sz[k];
+                if (!in_pinned[k]) {
+                    CU(c, c->h_in[slot][k].reserve(cap * in_sz[k]));
+                    memcpy(c->h_in[slot][k].p, src, bytes);
+                    src = c->h_in[slot][k].p;
+                }
+                CU(c, cudaMemcpyAsync(c->d_in[slot][k].p, src, bytes, cudaMemcpyHostToDevice, c->copy_in));
             }
             for (int k = 0; k < n_out; k++) {
                 if (!out[k] || !out_sz[k]) continue;
                 CU(c, c->d_out[slot][k].reserve(cap * out_sz[k]));
-                CU(c, c->h_out[slot][k].reserve(cap * out_sz[k]));
+                if (!out_pinned[k]) CU(c, c->h_out[slot][k].reserve(cap * out_sz[k]));
             }
             CU(c, cudaEventRecord(c->ev_in[slot], c->copy_in));
             CU(c, cudaStreamWaitEvent(c->stream, c->ev_in[slot], 0));
@@ -411,17 +432,19 @@ int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, co
             CU(c, cudaStreamWaitEvent(c->copy_out, c->ev_done[slot], 0));
             for (int k = 0; k < n_out; k++) {
                 if (!out[k] || !out_sz[k]) continue;
-                CU(c, cudaMemcpyAsync(c->h_out[slot][k].p, c->d_out[slot][k].p, cnt * out_sz[k], cudaMemcpyDeviceToHost, c->copy_out));
+                void* dst = out_pinned[k] ? (void*)(out[k] + off * out_sz[k]) : c->h_out[slot][k].p;
+                CU(c, cudaMemcpyAsync(dst, c->d_out[slot][k].p, cnt * out_sz[k], cudaMemcpyDeviceToHost, c->copy_out));
             }
             CU(c, cudaEventRecord(c->ev_out[slot], c->copy_out));
         }
         if (ch >= 1) {   // retire chunk ch-1: wait for its D2H and copy out of pinned memory
             size_t pc = ch - 1;
             int slot = (int)(pc % NSLOT);
-            size_t off = pc * CHUNK, cnt = std::min(CHUNK, n - off);
+            size_t off, cnt;
+            piece(pc, off, cnt);
             CU(c, cudaEventSynchronize(c->ev_out[slot]));
             for (int k = 0; k < n_out; k++) {
-                if (!out[k] || !out_sz[k]) continue;
+                if (!out[k] || !out_sz[k] || out_pinned[k]) continue;
                 memcpy(out[k] + off * out_sz[k], c->h_out[slot][k].p, cnt * out_sz[k]);
             }
         }

@@ -394,3 +394,44 @@ def test_large_batch_properties(eng):
     rev = ks[::-1].copy().tobytes()
     ar = eng.mul_by_generator_batch("k256", rev, 0)
     assert np.array_equal(np.frombuffer(ar, np.uint8).reshape(n, 33)[::-1], np.frombuffer(a, np.uint8).reshape(n, 33))
+
+
+def test_pinned_host_buffers(eng):
+    """Host entry points DMA directly from / to page-locked caller buffers and stage pageable ones: same bytes."""
+    import torch
+    c = o.K256
+    rng = random.Random(5)
+    rows = make_sigs(c, rng, 300)
+    for i in range(0, 300, 7):
+        rows[i][3] ^= 2
+    q = np.frombuffer(b"".join(be(r[0], 32) for r in rows), np.uint8).copy()
+    z = np.frombuffer(b"".join(r[1] for r in rows), np.uint8).copy()
+    rs = np.frombuffer(b"".join(be((r[2], r[3]), 32) for r in rows), np.uint8).copy()
+    ref = eng.ecdsa_verify("k256", q.tobytes(), z.tobytes(), rs.tobytes())
+    pq, pz, prs = (torch.from_numpy(a).pin_memory() for a in (q, z, rs))
+    out = torch.zeros(300, dtype=torch.uint8).pin_memory()
+    got = eng.ecdsa_verify("k256", pq.numpy(), pz.numpy(), prs.numpy(), out=out.numpy())
+    assert bytes(got) == ref and 0 < sum(ref) < 300
+    # mixed: pinned inputs, pageable output
+    assert eng.ecdsa_verify("k256", pq.numpy(), z, prs.numpy()) == ref
+
+
+@pytest.mark.parametrize("n", [(1 << 18) - 1, (1 << 18) + 1, (1 << 18) + (1 << 20) + 5, (1 << 18) + 2 * (1 << 20)])
+def test_pipeline_chunk_boundaries(eng, n):
+    """Host pipeline pieces (2^18 then 2^20 rows): a periodic input must give the same periodic output at every
+    position, whatever piece a row falls into."""
+    c = o.K256
+    per = 1009
+    rng = random.Random(n)
+    A = [rng.randrange(c.p) for _ in range(per)]
+    B = [rng.randrange(c.p) for _ in range(per)]
+    a = np.frombuffer(be(A, 32), np.uint8).reshape(per, 32)
+    b = np.frombuffer(be(B, 32), np.uint8).reshape(per, 32)
+    reps = (n + per - 1) // per
+    aa = np.tile(a, (reps, 1))[:n].copy()
+    bb = np.tile(b, (reps, 1))[:n].copy()
+    out, ok = eng.field_op("k256", 0, 2, aa, bb)
+    got = np.frombuffer(out, np.uint8).reshape(n, 32)
+    exp = np.frombuffer(be([x * y % c.p for x, y in zip(A, B)], 32), np.uint8).reshape(per, 32)
+    assert np.array_equal(got, np.tile(exp, (reps, 1))[:n])
+    assert ok == b"\x01" * n
