@@ -149,8 +149,6 @@ const char* GY[4] = {
     "4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5",
     "3617DE4A96262C6F5D9E98BF9292DC29F8F41DBD289A147CE9DA3113B5F0B8C00A60B1CE1D7E819D7A431D7C90EA0E5F",
     "BC3736A2F4F6779C59BDCEE36B692153D0A9877CC62A474002DF32E52139F0A0"};
-// 2^256 mod n for secp256k1 (the scalar of window 64 of the fixed-base table)
-const char* K256_2_256_MOD_N = "000000000000000000000000000000014551231950B75FC4402DA1732FC9BEBF";
 
 void hex_to(uint8_t* dst, const char* hex, int nbytes) {
     for (int i = 0; i < nbytes; i++) {
@@ -173,11 +171,9 @@ int build_tables(ecb200_ctx* c) {
             int r = build_table(c, cl, sc, cl->ngtab, &c->gtab[id], gxy);
             if (r) return r;
         }
-        if (cl->gen_windows) {   // (j+1) * 16^i * G, i < 65, j < 8
+        if (cl->gen_windows) {   // (j+1) * 16^i * G, i < 8L + 1, j < 8
             const int ne = cl->gen_windows * cl->gen_entries;
             std::vector<uint8_t> sc((size_t)ne * FB, 0);
-            uint8_t top[32];
-            hex_to(top, K256_2_256_MOD_N, 32);
             for (int e = 0; e < ne; e++) {
                 int i = e / cl->gen_entries, j = e % cl->gen_entries;
                 uint8_t* s = &sc[(size_t)e * FB];
@@ -189,10 +185,11 @@ int build_tables(ecb200_ctx* c) {
                     s[FB - 1 - byte] |= (uint8_t)w;
                     if (byte + 1 < FB) s[FB - 2 - byte] |= (uint8_t)(w >> 8);
                 } else {
-                    // (j+1) * (2^256 mod n): small multiple of a 129-bit value, no reduction needed
+                    // (j+1) * (2^(8FB) mod n): a small multiple of a value far below n (129 bits for k256, < 2^225
+                    // for P-256 / SM2, < 2^191 for P-384), so no reduction is needed
                     unsigned carry = 0;
                     for (int b = FB - 1; b >= 0; b--) {
-                        unsigned t = (unsigned)top[b] * v + carry;
+                        unsigned t = (unsigned)cl->r_mod_n[b] * v + carry;
                         s[b] = (uint8_t)t;
                         carry = t >> 8;
                     }

@@ -753,65 +753,58 @@ template <class C> struct Bodies {
     }
 
     // ------------------------------------------------------------------ fixed-base k*G -> projective
-    // k256: 65 signed radix-16 digits, table tab[i][j] = (j+1) * 16^i * G affine (65 x 8 entries),
-    // 65 mixed additions and no doublings (the reference spaces 33 tables by 2^8 and pays 4 doublings,
-    // k256/src/arithmetic/mul.rs:397-439).  Other curves: G*k through the generic multiplication,
-    // as primeorder/src/projective.rs:422-431 does.
+    // 8*L + 1 signed radix-16 digits, table tab[i][j] = (j+1) * 16^i * G affine (GEN_WINDOWS x 8 entries), one complete
+    // mixed addition per digit and no doublings (the reference spaces 33 tables by 2^8 and pays 4 doublings for k256,
+    // k256/src/arithmetic/mul.rs:397-439, and runs the generic window multiplication for the primeorder curves,
+    // primeorder/src/projective.rs:422-431; the result point is the same).
+    static constexpr int GEN_WINDOWS = 8 * L + 1;
     template <bool CT> ECB_DEV static void body_mul_gen(int tid, int n, const u8* k, const u32* tab, u32* out) {
         if (tid >= n) return;
         u32 kk[L];
         G::load_scalar(kk, k + (size_t)tid * FB);
         Proj r;
-        if constexpr (C::A_IS_ZERO) {
-            u32 kb[L + 1];
-            kb[0] = add_cc(kk[0], 0x88888888u);
-            ECB_UNROLL
-            for (int i = 1; i < L; i++) kb[i] = addc_cc(kk[i], 0x88888888u);
-            kb[L] = addc(0u, 0u);
-            G::set_identity(r);
+        u32 kb[L + 1];
+        kb[0] = add_cc(kk[0], 0x88888888u);
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) kb[i] = addc_cc(kk[i], 0x88888888u);
+        kb[L] = addc(0u, 0u);
+        G::set_identity(r);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-            for (int i = 0; i < 65; i++) {
-                u32 mag, neg;
-                if (i == 64) { mag = kb[8]; neg = 0; }
-                else {
-                    int d = (int)((kb[i >> 3] >> ((i & 7) * 4)) & 15u) - 8;
-                    neg = (u32)(d >> 31);
-                    mag = (u32)((d ^ (int)neg) - (int)neg);
+        for (int i = 0; i < GEN_WINDOWS; i++) {
+            u32 mag, neg;
+            if (i == 8 * L) { mag = kb[L]; neg = 0; }
+            else {
+                int d = (int)((kb[i >> 3] >> ((i & 7) * 4)) & 15u) - 8;
+                neg = (u32)(d >> 31);
+                mag = (u32)((d ^ (int)neg) - (int)neg);
+            }
+            const u32* win = tab + (size_t)i * 8 * 2 * L;
+            Aff g;
+            if constexpr (CT) {
+                F::set_zero(g.x); F::set_zero(g.y);
+                for (u32 j = 1; j <= 8; j++) {
+                    Aff c;
+                    load_aff_limbs(c, win + (size_t)(j - 1) * 2 * L);
+                    u32 m = (u32)0 - (u32)(j == mag);
+                    F::cmov(g.x, c.x, m); F::cmov(g.y, c.y, m);
                 }
-                const u32* win = tab + (size_t)i * 8 * 2 * L;
-                Aff g;
-                if constexpr (CT) {
-                    F::set_zero(g.x); F::set_zero(g.y);
-                    for (u32 j = 1; j <= 8; j++) {
-                        Aff c;
-                        load_aff_limbs(c, win + (size_t)(j - 1) * 2 * L);
-                        u32 m = (u32)0 - (u32)(j == mag);
-                        F::cmov(g.x, c.x, m); F::cmov(g.y, c.y, m);
-                    }
+                E ny;
+                F::neg(ny, g.y);
+                F::cmov(g.y, ny, neg);
+                Proj sum;
+                G::add_mixed(sum, r, g);
+                G::cmov(r, sum, (u32)0 - (u32)(mag != 0));
+            } else {
+                if (mag) {
+                    load_aff_limbs(g, win + (size_t)(mag - 1) * 2 * L);
                     E ny;
                     F::neg(ny, g.y);
                     F::cmov(g.y, ny, neg);
-                    Proj sum;
-                    G::add_mixed(sum, r, g);
-                    G::cmov(r, sum, (u32)0 - (u32)(mag != 0));
-                } else {
-                    if (mag) {
-                        load_aff_limbs(g, win + (size_t)(mag - 1) * 2 * L);
-                        E ny;
-                        F::neg(ny, g.y);
-                        F::cmov(g.y, ny, neg);
-                        G::add_mixed(r, r, g);
-                    }
+                    G::add_mixed(r, r, g);
                 }
             }
-        } else {
-            Aff g;
-            G::generator(g);
-            Proj pg;
-            G::from_affine(pg, g);
-            VarMul<C, CT>::run(r, pg, kk);
         }
         store_proj(out + (size_t)tid * 3 * L, r);
     }

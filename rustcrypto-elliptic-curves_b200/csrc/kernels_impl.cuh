@@ -84,7 +84,7 @@ template <class C> __global__ void __launch_bounds__(BLK) k_sum(int n, const u32
 }
 
 // ---------------------------------------------------------------------------------------------
-// secp256k1 fixed-base kernel with the 65x8 affine table staged in shared memory by one TMA bulk
+// fixed-base kernel with the (8L+1) x 8 affine table staged in shared memory by one TMA bulk
 // copy per CTA (cp.async.bulk global -> shared, completion on an mbarrier; UBLKCP in SASS).
 __device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 
@@ -126,20 +126,15 @@ template <class C> struct Launch {
     }
     static void mul_gen(cudaStream_t s, bool ct, int n, const u8* k, const u32* tab, u32* proj) {
         if (n <= 0) return;
-        if constexpr (C::A_IS_ZERO) {
-            const u32 bytes = 65u * 8u * 2u * C::L * 4u;
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaFuncSetAttribute(k_mul_gen_smem<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-                cudaFuncSetAttribute(k_mul_gen_smem<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-                attr_set = true;
-            }
-            if (ct) k_mul_gen_smem<C, true><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
-            else k_mul_gen_smem<C, false><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
-        } else {
-            if (ct) k_mul_gen<C, true><<<grid(n), BLK, 0, s>>>(n, k, tab, proj);
-            else k_mul_gen<C, false><<<grid(n), BLK, 0, s>>>(n, k, tab, proj);
+        const u32 bytes = (u32)Bodies<C>::GEN_WINDOWS * 8u * 2u * C::L * 4u;   // 33 KB (L = 8), 74.5 KB (L = 12)
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_mul_gen_smem<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            cudaFuncSetAttribute(k_mul_gen_smem<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            attr_set = true;
         }
+        if (ct) k_mul_gen_smem<C, true><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
+        else k_mul_gen_smem<C, false><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
         g_launch_count++;
     }
     static void load_proj(cudaStream_t s, int n, const u8* xyz, u32* proj, u8* invalid) {
@@ -226,10 +221,19 @@ template <class C> struct Launch {
         g_launch_count++;
     }
     static const CurveLaunch* table() {
-        static const CurveLaunch t = {
-            C::ID, C::L, C::FB, C::A_IS_ZERO ? 8 : 15, C::A_IS_ZERO ? 65 : 0, C::A_IS_ZERO ? 8 : 0, C::COMPRESS_DEFAULT,
+        static CurveLaunch t = {
+            C::ID, C::L, C::FB, C::A_IS_ZERO ? 8 : 15, Bodies<C>::GEN_WINDOWS, 8, C::COMPRESS_DEFAULT, {0},
             &field_op, &mul_var, &mul_gen, &load_proj, &normalize, &sum, &proj_to_bytes, &verify,
             &mul_var_fast, &verify_prep, &verify_main, &decode, &finish, &sign_finish, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
+        static bool init = false;
+        if (!init) {   // R mod n (the Montgomery "one" of the scalar field) as big-endian bytes
+            for (int i = 0; i < C::L; i++) {
+                const u32 w = C::Fn::Params::one(i);
+                t.r_mod_n[C::FB - 4 * i - 1] = (u8)w; t.r_mod_n[C::FB - 4 * i - 2] = (u8)(w >> 8);
+                t.r_mod_n[C::FB - 4 * i - 3] = (u8)(w >> 16); t.r_mod_n[C::FB - 4 * i - 4] = (u8)(w >> 24);
+            }
+            init = true;
+        }
         return &t;
     }
 };

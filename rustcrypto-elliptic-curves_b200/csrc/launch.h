@@ -11,8 +11,9 @@ struct CurveLaunch {
     int L;        // 32-bit limbs per field element
     int FB;       // field bytes
     int ngtab;    // entries of the small affine generator table used by verify (8 or 15)
-    int gen_windows, gen_entries;   // fixed-base table shape (k256: 65 x 8; others 0)
+    int gen_windows, gen_entries;   // fixed-base table shape: (8L + 1) windows x 8 entries
     bool compress_default;
+    uint8_t r_mod_n[48];            // 2^(32L) mod n, big-endian FB bytes: the scalar of the top fixed-base window
 
     void (*field_op)(cudaStream_t s, int n, int which, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* ok);
     void (*mul_var)(cudaStream_t s, bool ct, int n, uint32_t flags, const uint8_t* pts, const uint8_t* inf,

@@ -39,9 +39,9 @@ template <class C> struct Emu {
         normalize(ng, proj.data(), NORM_AFF_LIMBS, 0, nullptr, nullptr, out.data(), 0);
         return out;
     }
-    // k256 fixed-base table: (j+1) * 16^i * G, i < 65, j < 8
+    // fixed-base table: (j+1) * 16^i * G, i < 8L + 1, j < 8
     static std::vector<u32> gentab() {
-        const int ne = 65 * 8;
+        const int NW = B::GEN_WINDOWS, ne = NW * 8;
         std::vector<u8> pts(2 * FB * ne), ks(FB * ne, 0);
         typename EC<C>::Aff g;
         EC<C>::generator(g);
@@ -50,8 +50,6 @@ template <class C> struct Emu {
             C::F::to_limbs(t, g.x); store_be<L>(&pts[2 * FB * e], t);
             C::F::to_limbs(t, g.y); store_be<L>(&pts[2 * FB * e + FB], t);
             int i = e / 8, j = e % 8;
-            // (j+1) << 4i as big-endian bytes; i = 64 would overflow 256 bits -> reduce is wrong, so use mod n arithmetic:
-            // 16^64 = 2^256 = (2^256 - n) mod n handled by load_scalar's single subtraction.
             int bit = 4 * i;
             unsigned v = (unsigned)(j + 1);
             if (bit < 8 * FB) {
@@ -60,9 +58,9 @@ template <class C> struct Emu {
                 ks[FB * e + FB - 1 - byte] |= (u8)w;
                 if (byte + 1 < FB) ks[FB * e + FB - 2 - byte] |= (u8)(w >> 8);
             } else {
-                // (j+1) * (2^256 mod n), j+1 <= 8: computed with the scalar field
+                // (j+1) * (2^(8FB) mod n), j+1 <= 8: computed with the scalar field
                 typename C::Fn::E a, acc;
-                for (int l = 0; l < L; l++) a.v[l] = C::Fn::Params::one(l);   // R mod n = 2^256 mod n (plain value)
+                for (int l = 0; l < L; l++) a.v[l] = C::Fn::Params::one(l);   // R mod n (plain value)
                 acc = a;
                 for (unsigned m = 1; m < v; m++) C::Fn::add(acc, acc, a);
                 store_be<L>(&ks[FB * e], acc.v);
@@ -124,7 +122,7 @@ template <class C> struct Emu {
     }
     static void sign(int n, const u8* d, const u8* k, const u8* z, u8* rs, u8* recid, u8* ok, int nthreads) {
         static std::vector<u32> tab;
-        if (C::A_IS_ZERO && tab.empty()) tab = gentab();
+        if (tab.empty()) tab = gentab();
         std::vector<u32> proj((size_t)3 * L * n), aff((size_t)2 * L * n);
         for (int i = 0; i < n; i++) B::template body_mul_gen<true>(i, n, k, tab.data(), proj.data());
         normalize(n, proj.data(), NORM_AFF_LIMBS, 0, nullptr, nullptr, aff.data(), 0);
@@ -150,7 +148,7 @@ template <class C> struct Emu {
     }
     static void mul_gen(int ct, int n, const u8* k, u8* out, int compress) {
         static std::vector<u32> tab;
-        if (C::A_IS_ZERO && tab.empty()) tab = gentab();
+        if (tab.empty()) tab = gentab();
         std::vector<u32> proj((size_t)3 * L * n);
         for (int i = 0; i < n; i++) {
             if (ct) B::template body_mul_gen<true>(i, n, k, tab.data(), proj.data());

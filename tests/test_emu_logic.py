@@ -134,12 +134,13 @@ def test_mul_var(cname, ct):
     assert list(invalid) == [1] and bytes(out) == bytes(stride)
 
 
-@pytest.mark.parametrize("cname", ["k256", "p256"])
+@pytest.mark.parametrize("cname", CUR)
 @pytest.mark.parametrize("ct", [0, 1])
 def test_mul_gen(cname, ct, golden):
     c = o.curve(cname)
     rng = random.Random(3)
-    ks = scalars_edge(c, rng, 12) + [int(k, 16) for k, _, _ in golden["group"][cname]["mul"]]
+    ks = scalars_edge(c, rng, 12) + [int(k, 16) for k, _, _ in golden["group"].get(cname, {"mul": []})["mul"]]
+    ks += [(1 << (8 * c.fb)) - 1, (1 << (8 * c.fb)) - 2, c.n - 8, int("8" * (2 * c.fb), 16), int("7" * (2 * c.fb), 16) % c.n]   # top-window carry
     fb = c.fb
     kb = b"".join((k % (1 << (8 * fb))).to_bytes(fb, "big") for k in ks)
     stride = 1 + (fb if c.compress else 2 * fb)
