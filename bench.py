@@ -350,8 +350,24 @@ def cpu_baseline(q, z, rs, exp):
     lib.port_verify(0, n, qb, zb, rb, ok)
     dt = time.time() - t
     agree = bytes(ok) == exp[:n].tobytes()
-    return {"value": round(n / dt, 1), "unit": "verifies/s", "cores": lib.port_threads(), "kind": "port",
-            "sample": f"first {n} rows of the same batch, one pass ({dt:.1f} s)", "matches_gpu_mask": bool(agree)}
+    out = {"value": round(n / dt, 1), "unit": "verifies/s", "cores": lib.port_threads(), "kind": "port",
+           "sample": f"first {n} rows of the same batch, one pass ({dt:.1f} s)", "matches_gpu_mask": bool(agree)}
+    try:   # second CPU figure: OpenSSL libcrypto (ECDSA_do_verify + low-s rule) on the same cores
+        from oracle import libcrypto_ref as lc
+        m = 1 << 13
+        t = time.time()
+        lc.verify_batch("k256", q[:m].tobytes(), z[:m].tobytes(), rs[:m].tobytes())
+        rate = m / max(time.time() - t, 1e-6)
+        m = int(min(q.shape[0], max(m, rate * 5.0)))
+        t = time.time()
+        okl = lc.verify_batch("k256", q[:m].tobytes(), z[:m].tobytes(), rs[:m].tobytes())
+        dt2 = time.time() - t
+        out["openssl"] = {"value": round(m / dt2, 1), "unit": "verifies/s", "cores": lc.threads_used(), "version": lc.lib().OpenSSL_version(0).decode()
+                          if hasattr(lc.lib(), "OpenSSL_version") else "libcrypto", "sample": f"first {m} rows ({dt2:.1f} s), oracle/osslref.c (OpenMP)" if lc.driver() else f"first {m} rows ({dt2:.1f} s), ctypes + thread pool",
+                          "matches_gpu_mask": bool(okl == exp[:m].tobytes())}
+    except Exception as e:   # libcrypto missing on the box: the port figure stands alone
+        out["openssl"] = {"unavailable": str(e)[:120]}
+    return out
 
 
 def other_configs(pkg, eng, dev, ts):
