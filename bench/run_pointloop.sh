@@ -13,5 +13,5 @@ build pi_fn "$INL" "$NOI" ""
 build pi_fi "$INL" "$INL" ""
 build pn_fi "$NOI" "$INL" ""
 if [ "$1" = run ]; then
-  for v in pn_fn pi_fn pi_fi pn_fi; do echo "== $v"; ./pointloop_$v 64; done
+  for v in ${2:-pn_fn pi_fn pi_fi pn_fi}; do echo "== $v"; ./pointloop_$v 64; done
 fi

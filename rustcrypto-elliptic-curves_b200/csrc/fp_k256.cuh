@@ -101,20 +101,18 @@ struct FpK256 {
     // point kernels stay inside the instruction cache (ncu showed "no instruction" as the top stall
     // of the fully inlined build, profiles/).  ptxas passes the 8-limb structs in registers: no
     // local-memory traffic at the call.
-    ECB_FIELD_FN static E mul_fn(E a, E b) {
-        E r;
+    ECB_DEV static void mul_body(E& r, const E& a, const E& b) {
         u32 t[16];
         mul_wide<8>(t, a.v, b.v);
         reduce512(r.v, t);
-        return r;
     }
-    ECB_FIELD_FN static E sqr_fn(E a) {
-        E r;
+    ECB_DEV static void sqr_body(E& r, const E& a) {
         u32 t[16];
         sqr_wide<8>(t, a.v);
         reduce512(r.v, t);
-        return r;
     }
+    ECB_FIELD_FN static E mul_fn(E a, E b) { E r; mul_body(r, a, b); return r; }
+    ECB_FIELD_FN static E sqr_fn(E a) { E r; sqr_body(r, a); return r; }
     ECB_DEV static void mul(E& r, const E& a, const E& b) { r = mul_fn(a, b); }
     ECB_DEV static void sqr(E& r, const E& a) { r = sqr_fn(a); }
     ECB_DEV static void add(E& r, const E& a, const E& b) {

@@ -168,20 +168,18 @@ template <class P> struct Mont {
     }
 
     // real functions with register arguments (see fp_k256.cuh for why)
-    ECB_FIELD_FN static E mul_fn(E a, E b) {
-        E r;
+    ECB_DEV static void mul_body(E& r, const E& a, const E& b) {
         u32 t[2 * L];
         mul_wide<L>(t, a.v, b.v);
         redc(r.v, t);
-        return r;
     }
-    ECB_FIELD_FN static E sqr_fn(E a) {
-        E r;
+    ECB_DEV static void sqr_body(E& r, const E& a) {
         u32 t[2 * L];
         sqr_wide<L>(t, a.v);
         redc(r.v, t);
-        return r;
     }
+    ECB_FIELD_FN static E mul_fn(E a, E b) { E r; mul_body(r, a, b); return r; }
+    ECB_FIELD_FN static E sqr_fn(E a) { E r; sqr_body(r, a); return r; }
     ECB_DEV static void mul(E& r, const E& a, const E& b) { r = mul_fn(a, b); }
     ECB_DEV static void sqr(E& r, const E& a) { r = sqr_fn(a); }
     ECB_DEV static void add(E& r, const E& a, const E& b) {

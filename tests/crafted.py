@@ -34,3 +34,49 @@ def exceptional_rows(c):
         if row is not None:
             rows.append(row)
     return rows
+
+
+def reduced_x_points(c, count=3):
+    """Curve points whose affine x lies in [n, p): x mod n = x - n is tiny, so r = x - n takes the verifier's second
+    candidate (r + n < p) and the recovery id's x-reduced bit.  Exists because p - n ~ 2^(bits/2) for these curves."""
+    out, t = [], 0
+    while len(out) < count:
+        t += 1
+        P = o.decompress(c, c.n + t, t & 1)
+        if P is not None:
+            out.append(P)
+    return out
+
+
+def reduced_x_rows(c):
+    """Valid (Q, z, r, s) rows whose R = u1*G + u2*Q has x(R) >= n (no discrete log needed: Q = (R - u1*G)/u2),
+    plus twins with r replaced by x(R) - n + 1 (must be rejected)."""
+    import random
+    rng = random.Random(123 + c.cid)
+    rows = []
+    for R in reduced_x_points(c):
+        u1, u2 = rng.randrange(1, c.n), rng.randrange(1, c.n)
+        T = o.pt_add(c, R, o.pt_neg(c, o.mul_gen(c, u1)))
+        Q = o.pt_mul(c, pow(u2, -1, c.n), T)
+        r = R[0] - c.n
+        s = r * pow(u2, -1, c.n) % c.n
+        z = u1 * s % c.n
+        if c.low_s and s > c.n >> 1:
+            s = c.n - s                       # (u1, u2) -> (-u1, -u2): R -> -R, same x, still valid for the same z
+        rows.append((Q, z.to_bytes(c.fb, "big"), r, s))
+        rows.append((Q, z.to_bytes(c.fb, "big"), r + 1, s))
+    return rows
+
+
+def reduced_x_recover_rows(c):
+    """(z, r, s, recid) with the x-reduced bit set and a recoverable key: R has x(R) = r + n < p."""
+    import random
+    rng = random.Random(321 + c.cid)
+    rows = []
+    for R in reduced_x_points(c):
+        r = R[0] - c.n
+        s = rng.randrange(1, (c.n >> 1) + 1)
+        z = rng.randrange(1 << (8 * c.fb)).to_bytes(c.fb, "big")
+        rows.append((z, r, s, 2 | (R[1] & 1)))
+        rows.append((z, r, s, R[1] & 1))      # same r without the bit: decompress(r) — a different point or none
+    return rows

@@ -86,6 +86,8 @@ def recover_cases(c, golden=None, n_random=10, seed=9):
             rows.append((z, r, c.n - s, recid ^ 1))    # high-s twin: rejected on k256, fine elsewhere
         if i % 5 == 0:
             rows.append((z, 0, s, recid)); rows.append((z, r, 0, recid)); rows.append((z, c.n, s, recid)); rows.append((z, r, s, 4))
+    from tests import crafted
+    rows += crafted.reduced_x_recover_rows(c)          # x-reduced bit set AND recoverable (x(R) = r + n < p)
     # r whose restored x overflows / exceeds p, and an r with no point
     rows.append((bytes(c.fb), c.n - 1, 1, 2))
     rows.append((bytes(c.fb), non_residue_x(c), 1, 0))

@@ -251,6 +251,7 @@ def test_verify_exceptional_cases(cname):
     rows = crafted.exceptional_rows(c)
     if c.fb == 48:
         rows = rows[::3]
+    rows += crafted.reduced_x_rows(c)          # x(R) >= n: the second candidate r + n of the inversion-free comparison
     got, exp = run_verify(c, rows)
     assert got == list(exp)
     assert sum(got) > 5 and sum(got) < len(got)

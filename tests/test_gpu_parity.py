@@ -336,7 +336,7 @@ def test_verify_exceptional_cases(eng, cname):
     part and window loop), plus GLV corner scalars; both verify kernels must give the oracle's answer."""
     from tests import crafted
     c = o.curve(cname)
-    rows = crafted.exceptional_rows(c)
+    rows = crafted.exceptional_rows(c) + crafted.reduced_x_rows(c)
     keys = [r[0] for r in rows]; hs = [r[1] for r in rows]; sigs = [(r[2], r[3]) for r in rows]
     got = eng.verify_prehash_batch(cname, keys, hs, sigs)
     exp = [o.verify_prehash(c, Q, h, r, s) for Q, h, (r, s) in zip(keys, hs, sigs)]
