@@ -120,6 +120,16 @@ template <int L> ECB_DEV void cmov_n(u32* r, const u32* a, u32 mask) {
 // r[0..2L) = a * b.  Even/odd-column schoolbook: products whose weight i+j is even accumulate in
 // e[], odd-weight products in o[] (o[k] has weight k+1), so every IMAD.WIDE lands on an aligned
 // register pair and two carry chains run independently; r = e + (o << 32) at the end.
+// A row chain can only carry out of its top pair when an earlier row already accumulated there: the e chain after
+// even rows i >= 2, the o chain after odd rows.  The other carry-outs are provably zero (the top pair is fresh: one
+// product plus at most a captured carry cannot reach 2^64) and are not captured at all - each capture costs a SEL, an
+// IMAD.X and a zeroing IMAD.MOV, two of them on the multiplier pipe.  (Checked by simulation with all-ones operands,
+// which maximise every partial sum; the host emulation asserts it on every call.)
+#if defined(ECB_EMU)
+#define ECB_ASSERT_NO_CARRY() do { if (ecb_cf_ != 0) __builtin_trap(); } while (0)
+#else
+#define ECB_ASSERT_NO_CARRY() do { } while (0)
+#endif
 template <int L> ECB_DEV void mul_wide(u32* r, const u32* a, const u32* b) {
     static_assert(L % 2 == 0, "even limb counts only");
     u32 e[2 * L], o[2 * L];
@@ -134,13 +144,13 @@ template <int L> ECB_DEV void mul_wide(u32* r, const u32* a, const u32* b) {
                 e[i + j] = (j == 0) ? madlo_cc(a[j], bi, e[i + j]) : madloc_cc(a[j], bi, e[i + j]);
                 e[i + j + 1] = madhic_cc(a[j], bi, e[i + j + 1]);
             }
-            if (i + L < 2 * L) e[i + L] = addc(e[i + L], 0);
+            if (i >= 2) e[i + L] = addc(e[i + L], 0); else ECB_ASSERT_NO_CARRY();
             ECB_UNROLL
             for (int j = 1; j < L; j += 2) {
                 o[i + j - 1] = (j == 1) ? madlo_cc(a[j], bi, o[i + j - 1]) : madloc_cc(a[j], bi, o[i + j - 1]);
                 o[i + j] = madhic_cc(a[j], bi, o[i + j]);
             }
-            if (i + L < 2 * L) o[i + L] = addc(o[i + L], 0);
+            ECB_ASSERT_NO_CARRY();
         } else {
             ECB_UNROLL
             for (int j = 0; j < L; j += 2) {
@@ -153,7 +163,7 @@ template <int L> ECB_DEV void mul_wide(u32* r, const u32* a, const u32* b) {
                 e[i + j] = (j == 1) ? madlo_cc(a[j], bi, e[i + j]) : madloc_cc(a[j], bi, e[i + j]);
                 e[i + j + 1] = madhic_cc(a[j], bi, e[i + j + 1]);
             }
-            if (i + L + 1 < 2 * L) e[i + L + 1] = addc(e[i + L + 1], 0);
+            ECB_ASSERT_NO_CARRY();
         }
     }
     r[0] = e[0];
@@ -184,7 +194,8 @@ template <int L> ECB_DEV void sqr_wide(u32* r, const u32* a) {
             }
             // carry out goes to the next o limb above the last pair touched
             const int last = i + 1 + 2 * ((L - 1 - (i + 1)) / 2);   // last j used
-            if (i + last + 1 < 2 * L) o[i + last + 1] = addc(o[i + last + 1], 0);
+            if ((i & 1) && i <= L - 3) o[i + last + 1] = addc(o[i + last + 1], 0);   // other rows end on a fresh pair
+            else ECB_ASSERT_NO_CARRY();
         }
         // j = i+2, i+4, ... : weight even -> e[i+j], e[i+j+1]
         if (i + 2 < L) {
@@ -196,7 +207,8 @@ template <int L> ECB_DEV void sqr_wide(u32* r, const u32* a) {
                 first = false;
             }
             const int last = i + 2 + 2 * ((L - 1 - (i + 2)) / 2);
-            if (i + last + 2 < 2 * L) e[i + last + 2] = addc(e[i + last + 2], 0);
+            if (!(i & 1) && i >= 2 && i <= L - 4) e[i + last + 2] = addc(e[i + last + 2], 0);
+            else ECB_ASSERT_NO_CARRY();
         }
     }
     // t = e + (o << 32)
