@@ -12,6 +12,8 @@ build pn_fn "$NOI" "$NOI" ""
 build pi_fn "$INL" "$NOI" ""
 build pi_fi "$INL" "$INL" ""
 build pn_fi "$NOI" "$INL" ""
+# field functions that store their result through a pointer (operands still by value)
+[ -x pointloop_pn_fo ] || $NV -DECB_POINT_FN="$NOI" -DECB_FIELD_OUT_PTR -o pointloop_pn_fo pointloop.cu
 if [ "$1" = run ]; then
-  for v in ${2:-pn_fn pi_fn pi_fi pn_fi}; do echo "== $v"; ./pointloop_$v 64; done
+  for v in ${2:-pn_fn pi_fn pi_fi pn_fi pn_fo}; do echo "== $v"; ./pointloop_$v 64; done
 fi

@@ -10,6 +10,9 @@ constexpr int BLK = 128;   // threads per CTA of the arithmetic kernels (registe
 #ifndef ECB_FAST_MIN_CTAS
 #define ECB_FAST_MIN_CTAS 4   // resident CTAs per SM the public-input kernels are compiled for (register cap 65536/(128*N))
 #endif
+// (3 CTAs per SM / 168 registers for the 12-limb curve removes its 52 bytes of spills but was slower on the B200:
+// P-384 P*k 5.66 -> 5.23 M/s, so every curve keeps 4)
+template <class C> constexpr int fast_min_ctas() { return ECB_FAST_MIN_CTAS; }
 
 template <class C> __global__ void __launch_bounds__(BLK) k_field_op(int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
     Bodies<C>::body_field_op(blockIdx.x * BLK + threadIdx.x, n, which, op, a, b, out, ok);
@@ -29,14 +32,14 @@ template <class C> __global__ void __launch_bounds__(BLK) k_normalize(int n, con
 template <class C> __global__ void __launch_bounds__(BLK) k_verify(int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok) {
     Bodies<C>::body_verify(blockIdx.x * BLK + threadIdx.x, n, q, z, rs, gtab, ok);
 }
-template <class C> __global__ void __launch_bounds__(BLK, ECB_FAST_MIN_CTAS) k_mul_var_fast(int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
+template <class C> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_mul_var_fast(int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
     Bodies<C>::body_mul_var_fast(blockIdx.x * BLK + threadIdx.x, n, pts, aff_limbs, inf, k, proj, invalid);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_verify_prep(int n, int mode, const u8* z, const u8* rs, u32* scratch) {
     Bodies<C>::body_verify_prep(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, mode, z, rs, scratch);
 }
 // MODE is a template parameter: the ECDSA instance carries no decompression / projective-output code
-template <class C, int MODE> __global__ void __launch_bounds__(BLK, ECB_FAST_MIN_CTAS) k_verify_main(int n, const u8* q, const u8* rs, const u8* z, const u8* aux, const u32* scratch, const u32* gbig, int gw, u8* ok, u32* proj_out) {
+template <class C, int MODE> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_verify_main(int n, const u8* q, const u8* rs, const u8* z, const u8* aux, const u32* scratch, const u32* gbig, int gw, u8* ok, u32* proj_out) {
     Bodies<C>::body_verify_main(blockIdx.x * BLK + threadIdx.x, n, MODE, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_decode(int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {

@@ -180,8 +180,15 @@ template <class P> struct Mont {
     }
     ECB_FIELD_FN static E mul_fn(E a, E b) { E r; mul_body(r, a, b); return r; }
     ECB_FIELD_FN static E sqr_fn(E a) { E r; sqr_body(r, a); return r; }
+#ifdef ECB_FIELD_OUT_PTR   // experiment (bench/pointloop.cu): operands by value, result stored through a pointer by the callee
+    ECB_FIELD_FN static void mul_ofn(E* r, E a, E b) { E t; mul_body(t, a, b); *r = t; }
+    ECB_FIELD_FN static void sqr_ofn(E* r, E a) { E t; sqr_body(t, a); *r = t; }
+    ECB_DEV static void mul(E& r, const E& a, const E& b) { mul_ofn(&r, a, b); }
+    ECB_DEV static void sqr(E& r, const E& a) { sqr_ofn(&r, a); }
+#else
     ECB_DEV static void mul(E& r, const E& a, const E& b) { r = mul_fn(a, b); }
     ECB_DEV static void sqr(E& r, const E& a) { r = sqr_fn(a); }
+#endif
     ECB_DEV static void add(E& r, const E& a, const E& b) {
         u32 v[L];
         u32 c = add_n<L>(v, a.v, b.v);
