@@ -204,14 +204,16 @@ int build_tables(ecb200_ctx* c) {
 
 cudaStream_t pick(ecb200_ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->stream; }
 
-// Big fixed-base table for u1*G on the public-input path: entry (w << gw) + v = v * 2^(gw*w) * G in affine
-// internal limbs (64 MiB for a 256-bit curve at gw = 16; it lives in HBM/L2 and is gathered 64-96 B at a time).
+// Big fixed-base table for u1*G on the public-input path (jac.cuh add_fixed_base): signed gw-bit windows below the
+// top one, entry (w << (gw-1)) + v - 1 = v * 2^(gw*w) * G for 1 <= v <= 2^(gw-1); the top window is unsigned with
+// v up to 2^gw (v = 2^gw is 2^(8 FB) * G).  Affine internal limbs (34 MiB for a 256-bit curve at gw = 16; it lives in
+// HBM/L2 and is gathered 64-96 B at a time).
 // Built on first use with the engine's own kernels: scalar v << (gw*w), point G, Jacobian fast path, normalise.
 int ensure_gbig(ecb200_ctx* c, const CurveLaunch* cl) {
     if (c->gbig[cl->id]) return 0;
     const int FB = cl->FB, L = cl->L, gw = c->gw;
-    const int nwin = (8 * FB + gw - 1) / gw;
-    const size_t per = (size_t)1 << gw, ne = (size_t)nwin * per;
+    const int nwin = (8 * FB) / gw;
+    const size_t per = (size_t)1 << (gw - 1), top_base = (size_t)(nwin - 1) * per, ne = top_base + 2 * per;
     std::vector<uint8_t> gxy(2 * FB);
     hex_to(gxy.data(), GX[cl->id], FB);
     hex_to(gxy.data() + FB, GY[cl->id], FB);
@@ -230,9 +232,10 @@ int ensure_gbig(ecb200_ctx* c, const CurveLaunch* cl) {
         std::fill(sc.begin(), sc.end(), 0);
         for (size_t e = 0; e < cnt; e++) {
             size_t idx = off + e;
-            size_t w = idx >> gw, v = idx & (per - 1);
-            int bit = (int)w * gw;
             uint8_t* s = &sc[e * FB];
+            if (idx == ne - 1) { memcpy(s, cl->r_mod_n, FB); continue; }   // v = 2^gw in the top window: 2^(8 FB) mod n
+            size_t w = idx < top_base ? idx >> (gw - 1) : (size_t)(nwin - 1), v = idx - w * per + 1;
+            int bit = (int)w * gw;
             for (int b = 0; b < gw; b++)
                 if ((v >> b) & 1) { int pos = bit + b; s[FB - 1 - pos / 8] |= (uint8_t)(1u << (pos % 8)); }
         }

@@ -160,21 +160,43 @@ template <class C> struct Jac {
         F::cmov(a.y, ny, mask);
     }
 
-    // ---- u1 * G from the big fixed-base table: tab[(w << gw) + v] = v * 2^(gw*w) * G (affine limbs, v >= 1)
+    // ---- u1 * G from the big fixed-base table (gw-bit windows, gw divides 32).  All windows but the top one are
+    // SIGNED: with the bias 2^(gw-1) added to each of them, window w holds d_w + 2^(gw-1), d_w in [-2^(gw-1), 2^(gw-1));
+    // the top window absorbs the carry and stays unsigned, v in [0, 2^gw] (so no extra addition for a carry window).
+    //   tab[(w << (gw-1)) + v - 1]        = v * 2^(gw*w) * G, 1 <= v <= 2^(gw-1), w < nwin-1   (negative digits negate y)
+    //   tab[((nwin-1) << (gw-1)) + v - 1] = v * 2^(gw*(nwin-1)) * G, 1 <= v <= 2^gw
+    // 34 MiB instead of the 64 MiB of an all-unsigned table for a 256-bit curve at gw = 16.
     ECB_DEV static void add_fixed_base(J& acc, const u32* u1, const u32* tab, int gw) {
-        const int nwin = (32 * L + gw - 1) / gw;
-        const u32 vmask = (1u << gw) - 1u;
+        const int nwin = (32 * L) / gw;
+        const u32 half = 1u << (gw - 1);
+        u32 bias = 0;
+        for (int b = gw - 1; b < 32; b += gw) bias |= 1u << b;
+        u32 kb[L + 1];
+        kb[0] = add_cc(u1[0], L == 1 ? (bias & 0x7FFFFFFFu) : bias);
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) kb[i] = addc_cc(u1[i], i == L - 1 ? (bias & 0x7FFFFFFFu) : bias);   // no bias on the top window
+        kb[L] = addc(0u, 0u);
+        const u32 vmask = (gw == 32) ? 0xFFFFFFFFu : ((1u << gw) - 1u);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
         for (int w = 0; w < nwin; w++) {
             const int bit = w * gw;
-            u32 v = (u1[bit >> 5] >> (bit & 31)) & vmask;   // gw divides 32
-            if (v) {
+            const u32 raw = (kb[bit >> 5] >> (bit & 31)) & vmask;
+            u32 mag, neg = 0;
+            if (w == nwin - 1) {
+                mag = raw + (kb[L] << gw);                       // unsigned, up to 2^gw
+            } else {
+                const int d = (int)raw - (int)half;
+                neg = (u32)(d >> 31);
+                mag = (u32)((d ^ (int)neg) - (int)neg);
+            }
+            if (mag) {
                 A g;
-                const u32* e = tab + ((size_t)((size_t)w << gw) + v) * 2 * L;
+                const u32* e = tab + (((size_t)w << (gw - 1)) + mag - 1) * 2 * L;
                 ECB_UNROLL
                 for (int l = 0; l < L; l++) { g.x.v[l] = e[l]; g.y.v[l] = e[L + l]; }
+                cneg_y(g, neg);
                 madd(acc, acc, g, nullptr);
             }
         }
@@ -238,21 +260,17 @@ struct K256Fast {
         //    (tab[j-1], zr[j-2]) - 736 bytes of local memory per thread instead of the 1.7 KB of full J entries
         A tab[8];
         E zr[7];
-        J cur;
+        J& cur = acc;                               // the accumulator's storage doubles as the running multiple (smaller frame)
         tab[0] = Q;
-        {
-            J one;
-            JJ::from_affine(one, Q);
-            JJ::dbl(cur, one);                      // Z2 = 2 y1  (Z1 = 1)
-        }
+        JJ::from_affine(cur, Q);
+        JJ::dbl(cur, cur);                          // Z2 = 2 y1  (Z1 = 1)
         tab[1].x = cur.X; tab[1].y = cur.Y; zr[0] = cur.Z;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
         for (int j = 3; j <= 8; j++) {   // (j-1)Q + Q never hits an exceptional case (the order of Q is a large prime)
-            J prev = cur;
             E z;
-            JJ::madd(cur, prev, Q, &z);
+            JJ::madd(cur, cur, Q, &z);   // in place: madd reads p completely before it writes r
             tab[j - 1].x = cur.X; tab[j - 1].y = cur.Y;
             zr[j - 2] = z;
         }

@@ -72,9 +72,10 @@ template <class C> struct Emu {
         return out;
     }
 
-    // big fixed-base table with gw-bit windows: entry (w << gw) + v = v * 2^(gw*w) * G
+    // big fixed-base table: signed gw-bit windows below the top one (entry (w << (gw-1)) + v - 1 = v * 2^(gw*w) * G,
+    // v <= 2^(gw-1)), unsigned top window with v up to 2^gw (the last entry is 2^(8FB) * G)
     static std::vector<u32> gbig(int gw) {
-        const int nwin = (32 * L + gw - 1) / gw, per = 1 << gw, ne = nwin * per;
+        const int nwin = (32 * L) / gw, per = 1 << (gw - 1), top_base = (nwin - 1) * per, ne = top_base + 2 * per;
         std::vector<u8> pts(2 * FB * (size_t)ne), ks(FB * (size_t)ne, 0);
         typename EC<C>::Aff g;
         EC<C>::generator(g);
@@ -82,8 +83,14 @@ template <class C> struct Emu {
         for (int e = 0; e < ne; e++) {
             C::F::to_limbs(t, g.x); store_be<L>(&pts[2 * FB * (size_t)e], t);
             C::F::to_limbs(t, g.y); store_be<L>(&pts[2 * FB * (size_t)e + FB], t);
-            int w = e / per, v = e % per, bit = w * gw;
-            for (int b = 0; b < gw; b++) if ((v >> b) & 1) { int pos = bit + b; ks[FB * (size_t)e + FB - 1 - pos / 8] |= (u8)(1u << (pos % 8)); }
+            if (e == ne - 1) {
+                u32 one[L];
+                for (int l = 0; l < L; l++) one[l] = C::Fn::Params::one(l);   // R mod n = 2^(8FB) mod n
+                store_be<L>(&ks[FB * (size_t)e], one);
+                continue;
+            }
+            int w = e < top_base ? e / per : nwin - 1, v = e - w * per + 1, bit = w * gw;
+            for (int b = 0; b < gw + 1; b++) if ((v >> b) & 1) { int pos = bit + b; if (pos < 8 * FB) ks[FB * (size_t)e + FB - 1 - pos / 8] |= (u8)(1u << (pos % 8)); }
         }
         std::vector<u32> proj(3 * L * (size_t)ne), out(2 * L * (size_t)ne);
         for (int i = 0; i < ne; i++) B::body_mul_var_fast(i, ne, pts.data(), nullptr, nullptr, ks.data(), proj.data(), nullptr);
