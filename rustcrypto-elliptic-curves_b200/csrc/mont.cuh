@@ -15,6 +15,10 @@
 
 namespace ecb {
 
+// true for the sparse primes whose reduction runs column by column (not ASC_OK): P-384, SM2
+template <class P, bool S = P::SPARSE> struct SparseColumnwise { static constexpr bool value = false; };
+template <class P> struct SparseColumnwise<P, true> { static constexpr bool value = !P::ASC_OK; };
+
 template <class P> struct Mont {
     static constexpr int L = P::L;
     typedef Fe<P::L> E;
@@ -87,44 +91,29 @@ template <class P> struct Mont {
                 }
             }
         } else {
-            u32 q[L], alo = 0, ahi = 0;
+            // Column by column with a signed 64-bit accumulator in plain integer arithmetic (no carry-flag chains: the
+            // compiler is free to use three-input adds, and no long-lived carry predicates compete with the multiplier's -
+            // with pass-wise chains here ptxas ran out of predicate registers for L = 12 and spilled them into LOP3 bit
+            // twiddling, 109 extra instructions per P-384 multiplication).
+            //   column i <  L:  acc += t[i] + sum_k s_k Q[i - e_k];             Q[i]   = low word, acc >>= 32
+            //   column i >= L:  acc += t[i] + Q[i - L] + sum_k s_k Q[i - e_k];  r[i-L] = low word, acc >>= 32   (Q indices < L only)
+            long long acc = 0;
             ECB_UNROLL
-            for (int i = 0; i < L; i++) {
-                if (i < P::te(0)) { q[i] = t[i]; continue; }         // no term reaches these limbs
-                alo = add_cc(alo, t[i]);
-                ahi = addc(ahi, 0u);
+            for (int i = 0; i < 2 * L; i++) {
+                if (i < P::te(0)) continue;                          // no term reaches these limbs: Q[i] = t[i], carry 0
+                acc += (long long)(u64)t[i];
+                if (i >= L) acc += (long long)(u64)t[i - L];
                 ECB_UNROLL
                 for (int k = 0; k < P::NT; k++) {
-                    if (P::te(k) > i) continue;
-                    if (P::ts(k) > 0) { alo = add_cc(alo, q[i - P::te(k)]); ahi = addc(ahi, 0u); }
-                    else { alo = sub_cc(alo, q[i - P::te(k)]); ahi = subc(ahi, 0u); }
+                    const int src = i - P::te(k);
+                    if (src < 0 || src >= L) continue;
+                    if (P::ts(k) > 0) acc += (long long)(u64)t[src]; else acc -= (long long)(u64)t[src];
                 }
-                q[i] = alo;
-                alo = ahi;
-                ahi = (u32)((int)ahi >> 31);
+                if (i < L) t[i] = (u32)acc; else h[i - L] = (u32)acc;
+                acc >>= 32;
             }
-            ECB_UNROLL
-            for (int i = 0; i < L; i++) t[i] = q[i];
-            ECB_UNROLL
-            for (int k = 0; k < P::NT; k++) {
-                const int e = P::te(k);
-                if (P::ts(k) > 0) {
-                    h[0] = add_cc(h[0], t[L - e]);
-                    ECB_UNROLL
-                    for (int j = 1; j < L; j++) h[j] = addc_cc(h[j], j < e ? t[L - e + j] : 0u);
-                    top = addc(top, 0u);
-                } else {
-                    h[0] = sub_cc(h[0], t[L - e]);
-                    ECB_UNROLL
-                    for (int j = 1; j < L; j++) h[j] = subc_cc(h[j], j < e ? t[L - e + j] : 0u);
-                    top = subc(top, 0u);
-                }
-            }
-            // signed carry out of the low half (alo, sign-extended by ahi)
-            h[0] = add_cc(h[0], alo);
-            ECB_UNROLL
-            for (int j = 1; j < L; j++) h[j] = addc_cc(h[j], ahi);
-            top = addc(top, ahi);
+            final_sub(r, h, (u32)acc);
+            return;
         }
         // + Q * 2^(32L)
         h[0] = add_cc(h[0], t[0]);
@@ -180,13 +169,24 @@ template <class P> struct Mont {
     }
     ECB_FIELD_FN static E mul_fn(E a, E b) { E r; mul_body(r, a, b); return r; }
     ECB_FIELD_FN static E sqr_fn(E a) { E r; sqr_body(r, a); return r; }
+    // Two-call form for the column-wise sparse reduction (P-384, SM2): product and reduction as separate functions.
+    // Inside one function ptxas interleaves the reduction's columns with the multiplier's row chains, runs out of the
+    // seven predicate registers for the carries and spills them into LOP3 bit twiddling (442 of 757 instructions of the
+    // P-384 multiplication); across a call boundary it cannot.  The 2L-limb product travels in registers.
+    struct Wide { u32 v[2 * L]; };
+    static constexpr bool SPLIT = SparseColumnwise<P>::value;
+    ECB_FIELD_FN static Wide mulw_fn(E a, E b) { Wide t; mul_wide<L>(t.v, a.v, b.v); return t; }
+    ECB_FIELD_FN static E redc_fn(Wide t) { E r; redc(r.v, t.v); return r; }
 #ifdef ECB_FIELD_OUT_PTR   // experiment (bench/pointloop.cu): operands by value, result stored through a pointer by the callee
     ECB_FIELD_FN static void mul_ofn(E* r, E a, E b) { E t; mul_body(t, a, b); *r = t; }
     ECB_FIELD_FN static void sqr_ofn(E* r, E a) { E t; sqr_body(t, a); *r = t; }
     ECB_DEV static void mul(E& r, const E& a, const E& b) { mul_ofn(&r, a, b); }
     ECB_DEV static void sqr(E& r, const E& a) { sqr_ofn(&r, a); }
 #else
-    ECB_DEV static void mul(E& r, const E& a, const E& b) { r = mul_fn(a, b); }
+    ECB_DEV static void mul(E& r, const E& a, const E& b) {
+        if constexpr (SPLIT) { Wide t = mulw_fn(a, b); r = redc_fn(t); }
+        else r = mul_fn(a, b);
+    }
     ECB_DEV static void sqr(E& r, const E& a) { r = sqr_fn(a); }
 #endif
     ECB_DEV static void add(E& r, const E& a, const E& b) {
