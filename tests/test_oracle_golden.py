@@ -264,3 +264,20 @@ def test_decompress_roundtrip(cname):
     assert o.decompress(c, c.p, 0) is None
     bad = next(x for x in range(1, 50) if o.sqrt_mod(c, (x ** 3 + c.a * x + c.b) % c.p) is None)
     assert o.decompress(c, bad, 0) is None
+
+
+def test_generated_constants_match_oracle():
+    """tools/gen_consts.py carries its own copy of the curve parameters (the product's build tooling does not import
+    oracle/): they must be the oracle's, and regenerating the header must reproduce the committed file."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_consts", os.path.join(root, "tools", "gen_consts.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    for name in ("K256", "P256", "P384", "SM2"):
+        a, b = getattr(g.o, name), getattr(o, name)
+        for f in ("p", "a", "b", "n", "gx", "gy", "fb", "cid", "compress", "low_s"):
+            assert getattr(a, f) == getattr(b, f), (name, f)
+    for f in ("K256_LAMBDA", "K256_BETA", "K256_MINUS_B1", "K256_MINUS_B2", "K256_G1", "K256_G2"):
+        assert getattr(g.o, f) == getattr(o, f)

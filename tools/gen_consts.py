@@ -2,15 +2,48 @@
 """Generate rustcrypto-elliptic-curves_b200/csrc/curve_consts.cuh (limb tables for every modulus and curve).
 
 Constants come from SURVEY.md App. A / the reference (k256/src/arithmetic/mul.rs:129-152,
-projective.rs:29-34, */src/arithmetic.rs, */src/lib.rs ORDER); derived values (R, R^2, n0', b3 in
+projective.rs:29-34, */src/arithmetic.rs, */src/lib.rs ORDER) and are embedded below; derived values (R, R^2, n0', b3 in
 Montgomery form ...) are computed here with Python integers.  Usage: python tools/gen_consts.py
 """
 import os
-import sys
+from types import SimpleNamespace as NS
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-from oracle import ecoracle as o  # noqa: E402  (build-time generator, not product code)
+
+# Curve parameters (SURVEY.md App. A; k256/src/arithmetic/field.rs:312-313, k256/src/lib.rs:76, k256 affine.rs:63-75,
+# mul.rs:129-152, projective.rs:29-34; p256/src/arithmetic.rs:37-59, p256/src/lib.rs:74; p384/src/arithmetic.rs:36-61,
+# p384/src/lib.rs:50; sm2/src/arithmetic.rs:37-58, sm2/src/lib.rs:60).  Self-contained on purpose: the product's
+# build tooling does not import oracle/ (tests/test_oracle_golden.py::test_generated_constants_match_oracle compares).
+_P256_P = 0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF
+_P384_P = 2**384 - 2**128 - 2**96 + 2**32 - 1
+_SM2_P = 0xFFFFFFFEFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFF00000000FFFFFFFFFFFFFFFF
+o = NS(
+    K256=NS(name="k256", cid=0, p=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEFFFFFC2F, a=0, b=7,
+            n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141,
+            gx=0x79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798,
+            gy=0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8, fb=32, compress=True, low_s=True),
+    P256=NS(name="p256", cid=1, p=_P256_P, a=_P256_P - 3,
+            b=0x5AC635D8AA3A93E7B3EBBD55769886BC651D06B0CC53B0F63BCE3C3E27D2604B,
+            n=0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551,
+            gx=0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
+            gy=0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5, fb=32, compress=False, low_s=False),
+    P384=NS(name="p384", cid=2, p=_P384_P, a=_P384_P - 3,
+            b=0xB3312FA7E23EE7E4988E056BE3F82D19181D9C6EFE8141120314088F5013875AC656398D8A2ED19D2A85C8EDD3EC2AEF,
+            n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFC7634D81F4372DDF581A0DB248B0A77AECEC196ACCC52973,
+            gx=0xAA87CA22BE8B05378EB1C71EF320AD746E1D3B628BA79B9859F741E082542A385502F25DBF55296C3A545E3872760AB7,
+            gy=0x3617DE4A96262C6F5D9E98BF9292DC29F8F41DBD289A147CE9DA3113B5F0B8C00A60B1CE1D7E819D7A431D7C90EA0E5F, fb=48, compress=False, low_s=False),
+    SM2=NS(name="sm2", cid=3, p=_SM2_P, a=_SM2_P - 3,
+           b=0x28E9FA9E9D9F5E344D5A9E4BCF6509A7F39789F515AB8F92DDBCBD414D940E93,
+           n=0xFFFFFFFEFFFFFFFFFFFFFFFFFFFFFFFF7203DF6B21C6052B53BBF40939D54123,
+           gx=0x32C4AE2C1F1981195F9904466A39C9948FE30BBFF2660BE1715A4589334C74C7,
+           gy=0xBC3736A2F4F6779C59BDCEE36B692153D0A9877CC62A474002DF32E52139F0A0, fb=32, compress=False, low_s=False),
+    K256_LAMBDA=0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72,
+    K256_BETA=0x7AE96A2B657C07106E64479EAC3434E99CF0497512F58995C1396C28719501EE,
+    K256_MINUS_B1=0xE4437ED6010E88286F547FA90ABFE4C3,
+    K256_MINUS_B2=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFE8A280AC50774346DD765CDA83DB1562C,
+    K256_G1=0x3086D221A7D46BCDE86C90E49284EB153DAA8A1471E8CA7FE893209A45DBB031,
+    K256_G2=0xE4437ED6010E88286F547FA90ABFE4C4221208AC9DF506C61571B4AE8AC47F71,
+)
 
 
 def limbs(v, L):
