@@ -500,8 +500,11 @@ template <class C> struct Bodies {
     }
     // q: x||y (ECDSA / SM2DSA), x only (Schnorr); aux: recovery ids (VM_RECOVER), zin: e bytes (VM_SM2DSA target).
     // VM_SCHNORR / VM_RECOVER write the result point to proj_out (identity for rejected rows) and the validity so far to ok_out.
+    // NS / stab / sstride: window-table entries kept in shared memory (secp256k1 GLV path, jac.cuh WinTab); NS = 0: none
+    template <int NS = 0>
     ECB_DEV static void body_verify_main(int tid, int n, int mode, const u8* q, const u8* rs, const u8* zin, const u8* aux,
-                                         const u32* scratch, const u32* gbig, int gw, u8* ok_out, u32* proj_out) {
+                                         const u32* scratch, const u32* gbig, int gw, u8* ok_out, u32* proj_out,
+                                         u32* stab = nullptr, int sstride = 0) {
         if (tid >= n) return;
         const u32* rec = scratch + (size_t)tid * PREP_WORDS;
         typename JJ::A Q;
@@ -541,7 +544,7 @@ template <class C> struct Bodies {
             valid = valid && (fl & 1u);
             sp.neg1 = (u32)0 - ((fl >> 1) & 1u);
             sp.neg2 = (u32)0 - ((fl >> 2) & 1u);
-            K256Fast::mul_glv(acc, Q, sp);
+            K256Fast::template mul_glv<NS>(acc, Q, sp, stab, sstride);
         } else {
             u32 u2[L];
             ECB_UNROLL
@@ -718,7 +721,9 @@ template <class C> struct Bodies {
     // ------------------------------------------------------------------ variable-base k*P, vartime fast path (v2)
     // pts: n x 2FB big-endian affine bytes (aff_limbs == nullptr), or internal affine limbs produced by the
     // normalisation kernel from projective inputs (all-zero entry = identity); output projective limbs
-    ECB_DEV static void body_mul_var_fast(int tid, int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* out, u8* invalid) {
+    template <int NS = 0>
+    ECB_DEV static void body_mul_var_fast(int tid, int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* out, u8* invalid,
+                                          u32* stab = nullptr, int sstride = 0) {
         if (tid >= n) return;
         Aff a;
         bool ok, isinf;
@@ -742,7 +747,7 @@ template <class C> struct Bodies {
             if constexpr (C::A_IS_ZERO) {
                 K256Glv::Split sp;
                 K256Glv::decompose(sp, kk);
-                K256Fast::mul_glv(acc, Q, sp);
+                K256Fast::template mul_glv<NS>(acc, Q, sp, stab, sstride);
             } else {
                 JJ::mul_window_signed(acc, Q, kk);
             }

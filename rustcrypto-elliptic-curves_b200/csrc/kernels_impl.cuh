@@ -32,15 +32,29 @@ template <class C> __global__ void __launch_bounds__(BLK) k_normalize(int n, con
 template <class C> __global__ void __launch_bounds__(BLK) k_verify(int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok) {
     Bodies<C>::body_verify(blockIdx.x * BLK + threadIdx.x, n, q, z, rs, gtab, ok);
 }
+// secp256k1: ECB_WIN_SMEM_ENTRIES of the 8 per-thread window-table entries live in dynamic shared memory (jac.cuh
+// WinTab).  Measured on the B200 at 2^22 rows with 7 entries (56 KB per CTA, still 4 CTAs per SM): DRAM traffic of the
+// verify kernel 7.3 -> 3.3 GB per launch, but 4 % slower (85.7 vs 82.1 ms) - the 224 KB carve-out leaves almost no L1
+// for the remaining local frames and the fixed-base gathers; with 4 entries (32 KB per CTA) 4.5 GB and 1 % slower.
+// Throughput wins: the default keeps the table in local memory.
+#ifndef ECB_WIN_SMEM_ENTRIES
+#define ECB_WIN_SMEM_ENTRIES 0
+#endif
+template <class C> constexpr int win_smem_entries() { return C::A_IS_ZERO ? ECB_WIN_SMEM_ENTRIES : 0; }
+template <class C> constexpr u32 win_smem_bytes() { return (u32)win_smem_entries<C>() * 16u * 4u * BLK; }
+extern __shared__ __align__(16) u32 ecb_dyn_smem[];
+
 template <class C> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_mul_var_fast(int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
-    Bodies<C>::body_mul_var_fast(blockIdx.x * BLK + threadIdx.x, n, pts, aff_limbs, inf, k, proj, invalid);
+    Bodies<C>::template body_mul_var_fast<win_smem_entries<C>()>(blockIdx.x * BLK + threadIdx.x, n, pts, aff_limbs, inf, k, proj, invalid,
+                                                                  ecb_dyn_smem + threadIdx.x, BLK);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_verify_prep(int n, int mode, const u8* z, const u8* rs, u32* scratch) {
     Bodies<C>::body_verify_prep(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, mode, z, rs, scratch);
 }
 // MODE is a template parameter: the ECDSA instance carries no decompression / projective-output code
 template <class C, int MODE> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_verify_main(int n, const u8* q, const u8* rs, const u8* z, const u8* aux, const u32* scratch, const u32* gbig, int gw, u8* ok, u32* proj_out) {
-    Bodies<C>::body_verify_main(blockIdx.x * BLK + threadIdx.x, n, MODE, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+    Bodies<C>::template body_verify_main<win_smem_entries<C>()>(blockIdx.x * BLK + threadIdx.x, n, MODE, q, rs, z, aux, scratch, gbig, gw, ok, proj_out,
+                                                                 ecb_dyn_smem + threadIdx.x, BLK);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_decode(int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
     Bodies<C>::body_decode(blockIdx.x * BLK + threadIdx.x, n, mode, enc, stride, xy, status);
@@ -181,7 +195,12 @@ template <class C> struct Launch {
     }
     static void mul_var_fast(cudaStream_t s, int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
         if (n <= 0) return;
-        k_mul_var_fast<C><<<grid(n), BLK, 0, s>>>(n, pts, aff_limbs, inf, k, proj, invalid);
+        static bool attr_set = false;
+        if (!attr_set && win_smem_bytes<C>() > 0) {
+            cudaFuncSetAttribute(k_mul_var_fast<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem_bytes<C>());
+            attr_set = true;
+        }
+        k_mul_var_fast<C><<<grid(n), BLK, win_smem_bytes<C>(), s>>>(n, pts, aff_limbs, inf, k, proj, invalid);
         g_launch_count++;
     }
     static int ept_threads(int n) {   // threads for the Montgomery-trick kernels: as few rows per thread as keeps ~4 CTAs per SM busy
@@ -199,12 +218,20 @@ template <class C> struct Launch {
                             const u32* gbig, int gw, u8* ok, u32* proj_out) {
         if (n <= 0) return;
         // Schnorr exists for secp256k1 only, SM2DSA for SM2 only (abi.cu rejects other combinations before launching)
-        if (mode == VM_ECDSA) k_verify_main<C, VM_ECDSA><<<grid(n), BLK, 0, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
-        else if (mode == VM_RECOVER) k_verify_main<C, VM_RECOVER><<<grid(n), BLK, 0, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+        const u32 sm = win_smem_bytes<C>();
+        static bool attr_set = false;
+        if (!attr_set && sm > 0) {
+            cudaFuncSetAttribute(k_verify_main<C, VM_ECDSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_verify_main<C, VM_RECOVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if constexpr (C::A_IS_ZERO) cudaFuncSetAttribute(k_verify_main<C, VM_SCHNORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            attr_set = true;
+        }
+        if (mode == VM_ECDSA) k_verify_main<C, VM_ECDSA><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+        else if (mode == VM_RECOVER) k_verify_main<C, VM_RECOVER><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
         else if (mode == VM_SCHNORR) {
-            if constexpr (C::A_IS_ZERO) k_verify_main<C, VM_SCHNORR><<<grid(n), BLK, 0, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+            if constexpr (C::A_IS_ZERO) k_verify_main<C, VM_SCHNORR><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
         } else if (mode == VM_SM2DSA) {
-            if constexpr (C::ID == 3) k_verify_main<C, VM_SM2DSA><<<grid(n), BLK, 0, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+            if constexpr (C::ID == 3) k_verify_main<C, VM_SM2DSA><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
         }
         g_launch_count++;
     }

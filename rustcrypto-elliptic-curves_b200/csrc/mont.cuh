@@ -125,7 +125,10 @@ template <class P> struct Mont {
 
     // Montgomery reduction of t[0..2L): r = t * R^-1 mod p   (t < p * R)
     ECB_DEV static void redc(u32* r, u32* t) {
-        if constexpr (P::SPARSE) { redc_sparse(r, t); return; }
+        if constexpr (P::SPARSE) redc_sparse(r, t);
+        else redc_generic(r, t);
+    }
+    ECB_DEV static void redc_generic(u32* r, u32* t) {
         // Row i adds m_i * p at limb i as two aligned-pair carry chains (even j, odd j).  The chain
         // carry-outs (weight i+L and i+L+1) never feed a later m_i, so they are collected in cy[]
         // and added once at the end instead of being rippled to the top in every row.
