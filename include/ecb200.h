@@ -143,8 +143,10 @@ int ecb200_ecdsa_verify_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t*
  */
 
 /* decode modes of ecb200_decode_points */
-#define ECB200_DECODE_SEC1 0u    /* tag 02/03 + x, tag 04 + x + y, all-zero slot = identity */
-#define ECB200_DECODE_COMPACT 1u /* x only, even root (DecompactPoint; BIP340 x-only keys) */
+#define ECB200_DECODE_SEC1 0u    /* tag 02/03 + x, tag 05 + x (compact), tag 04 + x + y, all-zero slot = identity */
+#define ECB200_DECODE_COMPACT 1u /* x only: DecompactPoint::decompact - the even root on secp256k1 (BIP340 x-only keys,
+                                    k256 affine.rs:204-211), the root with the smaller y on the primeorder curves
+                                    (primeorder/src/affine.rs:66-77,148-156) */
 
 /* xy[i] = the affine point encoded in slot i; status[i] = 1 point, 2 identity, 0 invalid (xy zeroed unless 1).
  * Replaces `AffinePoint::from_encoded_point` / `DecompressPoint::decompress` / `DecompactPoint::decompact`

@@ -290,6 +290,9 @@ def sec1_decode(c: Curve, data: bytes) -> Tuple[bool, Point]:
         if (y & 1) != (data[0] & 1):
             y = c.p - y
         return True, (x, y)
+    if len(data) == 1 + c.fb and data[0] == 5:            # sec1::Tag::Compact -> decompact (x only)
+        P = decompact(c, int.from_bytes(data[1:], "big"))
+        return (P is not None), P
     if len(data) == 1 + 2 * c.fb and data[0] == 4:
         x = int.from_bytes(data[1:1 + c.fb], "big")
         y = int.from_bytes(data[1 + c.fb:], "big")
@@ -462,6 +465,15 @@ def decompress(c: Curve, x: int, y_is_odd: int) -> Optional[Point]:
     if (y & 1) != (y_is_odd & 1):
         y = (c.p - y) % c.p
     return (x, y)
+
+
+def decompact(c: Curve, x: int) -> Optional[Point]:
+    """DecompactPoint::decompact.  k256 (affine.rs:204-211) takes the EVEN root (Taproot / BIP340 convention); the
+    primeorder curves (primeorder/src/affine.rs:148-156 + to_compact :66-77) take the root with the SMALLER integer y."""
+    P = decompress(c, x, 0)
+    if P is None or c.name == "k256":
+        return P
+    return (P[0], min(P[1], c.p - P[1]))
 
 
 def sign_prehashed(c: Curve, d: int, k: int, z_bytes: bytes) -> Optional[Tuple[int, int, int]]:

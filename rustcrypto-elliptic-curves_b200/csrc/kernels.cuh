@@ -498,6 +498,20 @@ template <class C> struct Bodies {
         F::select(Q.y, odd == (y_is_odd & 1u), beta, nb);
         return ok;
     }
+    // DecompactPoint::decompact: secp256k1 takes the even root (k256 affine.rs:204-211, the BIP340 convention); the
+    // primeorder curves take the root with the smaller integer y (primeorder/src/affine.rs:148-156 with to_compact :66-77)
+    ECB_DEV static bool decompact(typename JJ::A& Q, const u32* x) {
+        bool ok = decompress(Q, x, 0u);
+        if constexpr (!C::A_IS_ZERO) {
+            E ny;
+            F::neg(ny, Q.y);
+            u32 a[L], b[L];
+            F::to_limbs(a, Q.y);
+            F::to_limbs(b, ny);
+            F::select(Q.y, geq_n<L>(b, a), Q.y, ny);      // keep y when y <= p - y
+        }
+        return ok;
+    }
     // q: x||y (ECDSA / SM2DSA), x only (Schnorr); aux: recovery ids (VM_RECOVER), zin: e bytes (VM_SM2DSA target).
     // VM_SCHNORR / VM_RECOVER write the result point to proj_out (identity for rejected rows) and the validity so far to ok_out.
     // NS / stab / sstride: window-table entries kept in shared memory (secp256k1 GLV path, jac.cuh WinTab); NS = 0: none
@@ -574,8 +588,8 @@ template <class C> struct Bodies {
 
     // ------------------------------------------------------------------ SEC1 decoding
     // FromEncodedPoint (k256 affine.rs:241-270, primeorder affine.rs:164-195).  enc: n slots of `stride` bytes.
-    // DEC_SEC1: tag 02/03 + x (stride >= 1+FB), tag 04 + x + y (stride >= 1+2FB), all-zero slot = identity;
-    // DEC_COMPACT: x only, even root (DecompactPoint, BIP340 keys).  status: 1 point, 2 identity, 0 invalid; xy zeroed unless 1.
+    // DEC_SEC1: tag 02/03 + x, tag 05 + x (compact) (stride >= 1+FB), tag 04 + x + y (stride >= 1+2FB), all-zero slot =
+    // identity; DEC_COMPACT: x only, decompact (even root on secp256k1 = BIP340 keys; smaller y on the primeorder curves).  status: 1 point, 2 identity, 0 invalid; xy zeroed unless 1.
     ECB_DEV static void body_decode(int tid, int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
         if (tid >= n) return;
         const u8* e = enc + (size_t)tid * stride;
@@ -585,10 +599,13 @@ template <class C> struct Bodies {
         u32 x[L];
         if (mode == DEC_COMPACT) {
             load_be<L>(x, e);
-            st = decompress(Q, x, 0u) ? 1u : 0u;
+            st = decompact(Q, x) ? 1u : 0u;
         } else {
             const u32 tag = e[0];
-            if ((tag == 2u || tag == 3u) && stride >= 1 + FB) {
+            if (tag == 5u && stride >= 1 + FB) {          // sec1::Tag::Compact
+                load_be<L>(x, e + 1);
+                st = decompact(Q, x) ? 1u : 0u;
+            } else if ((tag == 2u || tag == 3u) && stride >= 1 + FB) {
                 load_be<L>(x, e + 1);
                 st = decompress(Q, x, tag & 1u) ? 1u : 0u;
             } else if (tag == 4u && stride >= 1 + 2 * FB) {

@@ -41,7 +41,11 @@ def decode_cases(c, n_random=12, seed=5):
     add(b"\x02" + be(non_residue_x(c), fb), 0, None)                         # no square root
     add(b"\x04" + be(c.gx, fb) + be(c.gy ^ 1, fb), 0, None)                  # off curve
     add(b"\x04" + be(c.gx, fb) + be(c.p, fb), 0, None)                       # y = p
-    add(b"\x05" + be(c.gx, fb), 0, None)                                     # unknown tag
+    for i in range(3):                                                        # tag 05 = SEC1 compact: decompact
+        P = o.mul_gen(c, rng.randrange(1, c.n))
+        add(b"\x05" + be(P[0], fb), 1, o.decompact(c, P[0]))
+    add(b"\x05" + be(non_residue_x(c), fb), 0, None)
+    add(b"\x06" + be(c.gx, fb), 0, None)                                     # unknown tags
     add(b"\x01" + be(c.gx, fb), 0, None)
     return b"".join(slots), stride, bytes(status), b"".join(xy)
 
@@ -52,8 +56,7 @@ def compact_cases(c, n_random=8, seed=6):
     enc, status, xy = [], [], []
     for _ in range(n_random):
         P = o.mul_gen(c, rng.randrange(1, c.n))
-        if P[1] & 1:
-            P = (P[0], c.p - P[1])
+        P = o.decompact(c, P[0])          # k256: even root; primeorder curves: the smaller y
         enc.append(be(P[0], fb)); status.append(1); xy.append(be(P[0], fb) + be(P[1], fb))
     for x in (c.p, non_residue_x(c)):
         enc.append(be(x, fb)); status.append(0); xy.append(bytes(2 * fb))

@@ -281,3 +281,21 @@ def test_generated_constants_match_oracle():
             assert getattr(a, f) == getattr(b, f), (name, f)
     for f in ("K256_LAMBDA", "K256_BETA", "K256_MINUS_B1", "K256_MINUS_B2", "K256_G1", "K256_G2"):
         assert getattr(g.o, f) == getattr(o, f)
+
+
+@pytest.mark.parametrize("cname", ["k256", "p256", "p384", "sm2"])
+def test_decompact_conventions(cname):
+    """k256 decompact = even root (k256 affine.rs:204-211); primeorder decompact = to_compact(decompress(x, 0)), the
+    root with the smaller y (primeorder/src/affine.rs:66-77,148-156).  SEC1 tag 05 goes through the same function."""
+    import random
+    c = o.curve(cname)
+    rng = random.Random(8 + c.cid)
+    for _ in range(12):
+        P = o.mul_gen(c, rng.randrange(1, c.n))
+        D = o.decompact(c, P[0])
+        assert D[0] == P[0] and D[1] in (P[1], c.p - P[1])
+        if cname == "k256":
+            assert D[1] % 2 == 0
+        else:
+            assert D[1] <= c.p - D[1]
+        assert o.sec1_decode(c, b"\x05" + P[0].to_bytes(c.fb, "big")) == (True, D)
