@@ -20,6 +20,13 @@ def _rank_world(group=None) -> Tuple[int, int]:
     return 0, 1
 
 
+def _xdev(group=None):
+    """Device the collective's tensors must live on: the current CUDA device under NCCL, the host under gloo."""
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
 def verify_sharded(engine, curve, q: bytes, z: bytes, rs: bytes, group=None, gather: bool = False) -> Optional[bytes]:
     """Each rank verifies rows [lo, hi) of the GLOBAL batch (every rank holds, or can address, the whole batch).
     Returns this rank's ok bytes; with gather=True rank 0 returns the concatenated mask of all ranks (a control-plane
@@ -35,13 +42,15 @@ def verify_sharded(engine, curve, q: bytes, z: bytes, rs: bytes, group=None, gat
         return ok
     sizes = [shard_range(n, r, world) for r in range(world)]
     mx = max(h - l for l, h in sizes)
+    dev = _xdev(group)
     mine = torch.zeros(mx, dtype=torch.uint8)
     mine[:hi - lo] = torch.frombuffer(bytearray(ok), dtype=torch.uint8)
-    bufs = [torch.zeros(mx, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
+    mine = mine.to(dev)
+    bufs = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
     dist.gather(mine, bufs, dst=0, group=group)
     if rank != 0:
         return None
-    return b"".join(bytes(bufs[r][:h - l].numpy().tobytes()) for r, (l, h) in enumerate(sizes))
+    return b"".join(bytes(bufs[r][:h - l].cpu().numpy().tobytes()) for r, (l, h) in enumerate(sizes))
 
 
 def lincomb_sharded(engine, curve, pts: bytes, ks: bytes, group=None, flags: int = 0) -> bytes:
@@ -58,9 +67,10 @@ def lincomb_sharded(engine, curve, pts: bytes, ks: bytes, group=None, flags: int
     if world == 1:
         parts = partial
     else:
-        mine = torch.frombuffer(bytearray(partial), dtype=torch.uint8)
-        bufs = [torch.zeros(3 * fb, dtype=torch.uint8) for _ in range(world)]
-        dist.all_gather(bufs, mine, group=group)
-        parts = b"".join(bytes(b.numpy().tobytes()) for b in bufs)
+        dev = _xdev(group)
+        mine = torch.frombuffer(bytearray(partial), dtype=torch.uint8).to(dev)
+        bufs = [torch.zeros(3 * fb, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(bufs, mine, group=group)      # NCCL over NVLink on the GPU box, gloo in the CPU tests
+        parts = b"".join(bytes(b.cpu().numpy().tobytes()) for b in bufs)
     ones = ((1).to_bytes(fb, "big")) * world
     return engine.lincomb(curve, parts, ones, flags | FLAG_PROJ, False)

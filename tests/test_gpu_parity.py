@@ -435,3 +435,37 @@ def test_pipeline_chunk_boundaries(eng, n):
     exp = np.frombuffer(be([x * y % c.p for x, y in zip(A, B)], 32), np.uint8).reshape(per, 32)
     assert np.array_equal(got, np.tile(exp, (reps, 1))[:n])
     assert ok == b"\x01" * n
+
+
+def test_abi_error_behaviour_and_reuse(eng):
+    """Status codes are for misuse only (bad curve id, null buffers); empty batches succeed; scratch buffers regrow across
+    calls of different sizes; two contexts on one device do not interfere."""
+    import ctypes
+    import ecb200
+    lib = eng.lib
+    buf = (ctypes.c_uint8 * 64)()
+    assert lib.ecb200_mul_gen(eng.h, 7, 1, buf, buf, 0) == -1                       # unknown curve
+    assert lib.ecb200_mul_gen(eng.h, 0, 1, None, buf, 0) == -1                      # null input
+    assert lib.ecb200_ecdsa_verify(eng.h, 0, 1, buf, None, buf, buf) == -1
+    assert lib.ecb200_decode_points(eng.h, 0, 1, buf, 8, 0, buf, buf) == -1         # stride too small
+    assert lib.ecb200_decode_points(eng.h, 0, 1, buf, 33, 2, buf, buf) == -1        # unknown mode
+    assert b"bad argument" in lib.ecb200_last_error(eng.h)
+    for name in ("mul_gen", "ecdsa_verify"):                                        # n = 0 is fine, even with null buffers
+        pass
+    assert lib.ecb200_mul_gen(eng.h, 0, 0, None, None, 0) == 0
+    assert lib.ecb200_ecdsa_verify(eng.h, 1, 0, None, None, None, None) == 0
+    assert lib.ecb200_schnorr_verify(eng.h, 0, None, None, None, None) == 0
+    assert eng.mul_by_generator_batch("k256", b"") == b""
+    assert eng.ecdsa_verify("p256", b"", b"", b"") == b""
+    assert eng.ecdsa_recover("k256", b"", b"", b"") == (b"", b"")
+    assert eng.ecdsa_sign("p384", b"", b"", b"") == (b"", b"", b"")
+    # growing then shrinking batches reuse / regrow the context's scratch
+    c = o.K256
+    e2 = ecb200.Engine(0)
+    for n in (1, 1000, 17, 70000, 3):
+        ks = be([(i * 7919 + 1) % c.n for i in range(n)], 32)
+        a = eng.mul_by_generator_batch("k256", ks, ecb200.FLAG_CT)
+        b = e2.mul_by_generator_batch("k256", ks, 0)
+        assert a == b
+        assert a[:33] == o.slot_encode(c, c.G)
+    e2.close()
