@@ -155,3 +155,57 @@ def test_next_rows_large_batch_properties(eng):
         di, ki = int.from_bytes(d[i].tobytes(), "big"), int.from_bytes(k[i].tobytes(), "big")
         r, s, recid = o.sign_prehashed(c, di, ki, z[i].tobytes())
         assert rs[64 * i:64 * i + 64] == nextrows.be(r, 32) + nextrows.be(s, 32) and rid[i] == recid
+
+
+def test_dev_pointer_variants(eng, golden):
+    """_dev entry points (device buffers + stream) of the rows not exercised by bench.py: decode and SM2DSA."""
+    import torch
+    dev = torch.device("cuda:0")
+    st = torch.cuda.Stream(device=dev)
+    c = o.SM2
+    qb, eb, rsb, exp = nextrows.sm2dsa_cases(golden, n_random=16)
+    n = len(exp)
+    t = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
+    d_ok = torch.zeros(n, dtype=torch.uint8, device=dev)
+    with torch.cuda.stream(st):
+        eng.sm2dsa_verify_dev(n, t(qb), t(eb), t(rsb), d_ok, st.cuda_stream)
+    st.synchronize()
+    assert bytes(d_ok.cpu().numpy().tobytes()) == exp
+    for cname in ("k256", "p384"):
+        c = o.curve(cname)
+        slots, stride, status, xy = nextrows.decode_cases(c, n_random=10)
+        n = len(status)
+        d_xy = torch.zeros(n * 2 * c.fb, dtype=torch.uint8, device=dev)
+        d_st = torch.zeros(n, dtype=torch.uint8, device=dev)
+        with torch.cuda.stream(st):
+            eng.decode_points_dev(cname, n, t(slots), stride, 0, d_xy, d_st, st.cuda_stream)
+        st.synchronize()
+        assert bytes(d_st.cpu().numpy().tobytes()) == status and bytes(d_xy.cpu().numpy().tobytes()) == xy
+
+
+@pytest.mark.parametrize("gw", [4, 8])
+def test_fixed_base_window_widths(gw):
+    """ECB200_GW selects the window width of the big fixed-base table (signed windows, unsigned top window): every width
+    gives the oracle's answers on the crafted rows, incl. top-window carries."""
+    import os
+    import ecb200
+    from tests import crafted
+    os.environ["ECB200_GW"] = str(gw)
+    try:
+        e = ecb200.Engine(0)
+    finally:
+        del os.environ["ECB200_GW"]
+    for cname in ("k256", "p256"):
+        c = o.curve(cname)
+        rows = crafted.exceptional_rows(c) + crafted.reduced_x_rows(c)
+        # u1 with all-ones / alternating top windows: z chosen so that u1 = z / s hits them (s = 1 => u1 = z)
+        rng = random.Random(gw)
+        for u1 in ((1 << (8 * c.fb)) - 1, c.n - 1, int("8" * (2 * c.fb), 16) % c.n, int("7F" * c.fb, 16), 1 << (8 * c.fb - 1)):
+            row = crafted.craft(c, u1 % c.n, rng.randrange(1, c.n), rng.randrange(1, c.n))
+            if row:
+                rows.append(row)
+        keys = [r[0] for r in rows]; hs = [r[1] for r in rows]; sigs = [(r[2], r[3]) for r in rows]
+        got = e.verify_prehash_batch(cname, keys, hs, sigs)
+        assert got == [o.verify_prehash(c, Q, h, r, s) for Q, h, (r, s) in zip(keys, hs, sigs)]
+        assert sum(got) > 5
+    e.close()
