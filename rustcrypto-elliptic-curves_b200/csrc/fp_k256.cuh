@@ -146,6 +146,19 @@ struct FpK256 {
         sub(r, z, a);
     }
     ECB_DEV static void dbl(E& r, const E& a) { add(r, a, a); }
+    // r = a / 2 = (a + (a odd ? p : 0)) >> 1: the masked addition leaves a 257-bit value whose bit 256 is the carry
+    ECB_DEV static void half(E& r, const E& a) {
+        const u32 m = (u32)0 - (a.v[0] & 1u);
+        u32 t[8];
+        t[0] = add_cc(a.v[0], m & p(0));
+        t[1] = addc_cc(a.v[1], m & p(1));
+        ECB_UNROLL
+        for (int i = 2; i < 8; i++) t[i] = addc_cc(a.v[i], m);
+        const u32 c = addc(0u, 0u);
+        ECB_UNROLL
+        for (int i = 0; i < 7; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+        r.v[7] = (t[7] >> 1) | (c << 31);
+    }
     // r = a * k for a small constant k (k*2^256 must stay far below 2^320: k < 2^16 here)
     ECB_DEV static void mul_small(E& r, const E& a, u32 k) {
         u32 e[9], o[9];

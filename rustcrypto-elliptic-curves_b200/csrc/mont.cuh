@@ -226,6 +226,18 @@ template <class P> struct Mont {
         sub(r, z, a);
     }
     ECB_DEV static void dbl(E& r, const E& a) { add(r, a, a); }
+    // r = a / 2 (Montgomery form is linear, so this is the plain halving): (a + (a odd ? p : 0)) >> 1
+    ECB_DEV static void half(E& r, const E& a) {
+        const u32 m = (u32)0 - (a.v[0] & 1u);
+        u32 t[L];
+        t[0] = add_cc(a.v[0], masked_p(0, m));
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) t[i] = addc_cc(a.v[i], masked_p(i, m));
+        const u32 c = addc(0u, 0u);
+        ECB_UNROLL
+        for (int i = 0; i < L - 1; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+        r.v[L - 1] = (t[L - 1] >> 1) | (c << 31);
+    }
     // small constant multiples by addition chains (only 2,3,4,8 are needed by the formulas)
     ECB_DEV static void mul_small(E& r, const E& a, u32 k) {
         E t;
