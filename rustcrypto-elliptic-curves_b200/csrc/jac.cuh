@@ -34,7 +34,7 @@ template <class C> struct Jac {
     // Both forms are the textbook Jacobian doubling divided through by powers of two (Z3 = Y Z instead of 2 Y Z, so
     // X3 and Y3 carry 1/4 and 1/8): with L = M/2 the formulas need 6 (a = 0) / 8 (a = -3) add-type field operations
     // instead of 10 / 12 - every one of them is 19-26 instructions of carry chain plus canonicalisation.
-    ECB_POINT_FN static void dbl(J& r, const J& p) {
+    ECB_DEV static void dbl_body(J& r, const J& p) {
         if constexpr (C::A_IS_ZERO) {
             // a = 0:  S = Y^2, L = 3 X^2 / 2, T = X S, X3 = L^2 - 2T, Y3 = L (T - X3) - S^2, Z3 = Y Z     (3M + 4S)
             E s_, l, t, u;
@@ -69,6 +69,16 @@ template <class C> struct Jac {
             F::sub(r.Y, t, s_);
             r.Z = u;
         }
+    }
+    ECB_POINT_FN static void dbl(J& r, const J& p) { dbl_body(r, p); }
+    // n doublings in one call: the point is read from and written back to local memory once instead of n times
+    ECB_POINT_FN static void dbl_n(J& r, int n) {
+        J t = r;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int i = 0; i < n; i++) dbl_body(t, t);
+        r = t;
     }
     // doubling of an affine point (Z = 1): used for the exceptional branch and table starts
     ECB_DEV static void dbl_affine(J& r, const A& q) {
@@ -232,7 +242,7 @@ template <class C> struct Jac {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-                for (int d = 0; d < 4; d++) dbl(acc, acc);
+                dbl_n(acc, 4);
             }
             u32 mag, neg;
             digit16(kb, i, top, mag, neg);
@@ -331,7 +341,7 @@ struct K256Fast {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-                for (int d = 0; d < 4; d++) JJ::dbl(acc, acc);
+                JJ::dbl_n(acc, 4);
             }
             u32 mag, neg;
             K256Glv::digit(s.a1, i, mag, neg);
