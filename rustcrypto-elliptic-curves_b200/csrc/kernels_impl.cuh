@@ -7,12 +7,17 @@
 namespace ecb {
 
 constexpr int BLK = 128;   // threads per CTA of the arithmetic kernels (register-heavy: 2-4 CTAs per SM)
+// Resident CTAs per SM the public-input kernels are compiled for (register cap 65536 / (128 N)).  Measured on the B200
+// (k256 verify at 2^22 rows / P-256 verify at 2^20, M rows/s): N = 3: 50.7 / 27.6, 4: 50.7 / 28.5, 5: 51.9 / 28.7,
+// 6: 52.7 / 28.9, 7: 53.0 / 29.1, 8: 52.7 / 29.1.  6 (80 registers, ~120 bytes of spills) is the knee for the 8-limb curves;
+// the 12-limb curve keeps 4 (3 was slower, see git history).
 #ifndef ECB_FAST_MIN_CTAS
-#define ECB_FAST_MIN_CTAS 4   // resident CTAs per SM the public-input kernels are compiled for (register cap 65536/(128*N))
+#define ECB_FAST_MIN_CTAS 6
 #endif
-// (3 CTAs per SM / 168 registers for the 12-limb curve removes its 52 bytes of spills but was slower on the B200:
-// P-384 P*k 5.66 -> 5.23 M/s, so every curve keeps 4)
-template <class C> constexpr int fast_min_ctas() { return ECB_FAST_MIN_CTAS; }
+#ifndef ECB_FAST_MIN_CTAS_WIDE
+#define ECB_FAST_MIN_CTAS_WIDE 4
+#endif
+template <class C> constexpr int fast_min_ctas() { return C::L > 8 ? ECB_FAST_MIN_CTAS_WIDE : ECB_FAST_MIN_CTAS; }
 
 template <class C> __global__ void __launch_bounds__(BLK) k_field_op(int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
     Bodies<C>::body_field_op(blockIdx.x * BLK + threadIdx.x, n, which, op, a, b, out, ok);
