@@ -18,11 +18,18 @@ constexpr int BLK = 128;   // threads per CTA of the arithmetic kernels (registe
 #define ECB_FAST_MIN_CTAS_WIDE 4
 #endif
 template <class C> constexpr int fast_min_ctas() { return C::L > 8 ? ECB_FAST_MIN_CTAS_WIDE : ECB_FAST_MIN_CTAS; }
+// same knob for the secret-scalar kernels (complete formulas, full table scans).  Measured (k256 G*k CT at 2^18 / k256 P*k CT /
+// P-256 G*k CT / P-256 P*k CT, M/s): unconstrained (146-154 registers, 3 CTAs) 93.5 / 37.7 / 70.5 / 15.6,
+// 4: 95.5 / 39.4 / 73.6 / 16.3, 5: 93.4 / 39.3 / 70.2 / 15.6, 6: 91.5 / 39.7 / 60.8 / 16.2.
+#ifndef ECB_CT_MIN_CTAS
+#define ECB_CT_MIN_CTAS 4
+#endif
+template <class C> constexpr int ct_min_ctas() { return C::L > 8 ? 3 : ECB_CT_MIN_CTAS; }
 
 template <class C> __global__ void __launch_bounds__(BLK) k_field_op(int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
     Bodies<C>::body_field_op(blockIdx.x * BLK + threadIdx.x, n, which, op, a, b, out, ok);
 }
-template <class C, bool CT> __global__ void __launch_bounds__(BLK) k_mul_var(int n, u32 flags, const u8* pts, const u8* inf, const u8* k, u32* proj, u8* invalid) {
+template <class C, bool CT> __global__ void __launch_bounds__(BLK, ct_min_ctas<C>()) k_mul_var(int n, u32 flags, const u8* pts, const u8* inf, const u8* k, u32* proj, u8* invalid) {
     Bodies<C>::template body_mul_var<CT>(blockIdx.x * BLK + threadIdx.x, n, flags, pts, inf, k, proj, invalid);
 }
 template <class C, bool CT> __global__ void __launch_bounds__(BLK) k_mul_gen(int n, const u8* k, const u32* tab, u32* proj) {
@@ -110,7 +117,7 @@ template <class C> __global__ void __launch_bounds__(BLK) k_sum(int n, const u32
 // copy per CTA (cp.async.bulk global -> shared, completion on an mbarrier; UBLKCP in SASS).
 __device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 
-template <class C, bool CT> __global__ void __launch_bounds__(BLK) k_mul_gen_smem(int n, const u8* k, const u32* tab, u32 tab_bytes, u32* proj) {
+template <class C, bool CT> __global__ void __launch_bounds__(BLK, ct_min_ctas<C>()) k_mul_gen_smem(int n, const u8* k, const u32* tab, u32 tab_bytes, u32* proj) {
     extern __shared__ __align__(128) u32 stab[];
     __shared__ __align__(8) unsigned long long bar;
     if (threadIdx.x == 0) {
