@@ -173,8 +173,11 @@ template <class C> struct Launch {
     }
     static void normalize(cudaStream_t s, int n, const u32* proj, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
         if (n <= 0) return;
-        // elements per thread: as few as keeps >= ~4 CTAs per SM busy, at most EPT
-        int ept = (n + 148 * 4 * BLK - 1) / (148 * 4 * BLK);
+        // elements per thread: the kernel is one ~270-multiplication inversion chain per thread plus 5 multiplications per
+        // element, so below ~2 warps per SM sub-partition it is latency-bound and more elements per thread are free:
+        // aim at 1 CTA per SM, at most EPT (config 1 at 2^16, whole call: 0.944 ms with one element per thread, 0.890 ms at
+        // 2 CTAs per SM, 0.865 ms at 1)
+        int ept = (n + 148 * 1 * BLK - 1) / (148 * 1 * BLK);
         if (ept < 1) ept = 1;
         if (ept > Bodies<C>::EPT) ept = Bodies<C>::EPT;
         int threads = (n + ept - 1) / ept;
@@ -215,8 +218,8 @@ template <class C> struct Launch {
         k_mul_var_fast<C><<<grid(n), BLK, win_smem_bytes<C>(), s>>>(n, pts, aff_limbs, inf, k, proj, invalid);
         g_launch_count++;
     }
-    static int ept_threads(int n) {   // threads for the Montgomery-trick kernels: as few rows per thread as keeps ~4 CTAs per SM busy
-        int ept = (n + 148 * 4 * BLK - 1) / (148 * 4 * BLK);
+    static int ept_threads(int n) {   // threads for the Montgomery-trick kernels: rows per thread that keep ~1 CTA per SM busy (latency-bound below that, see normalize)
+        int ept = (n + 148 * 1 * BLK - 1) / (148 * 1 * BLK);
         if (ept < 1) ept = 1;
         if (ept > Bodies<C>::PREP_EPT) ept = Bodies<C>::PREP_EPT;
         return (n + ept - 1) / ept;
