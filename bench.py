@@ -188,14 +188,14 @@ def run_reference(args):
     dt = time.time() - t
     value = n * args.steps / dt
     sample = f"{n} rows per step ({n0} distinct signatures tiled), {args.steps} steps"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "secp256k1 ECDSA verify_prehash throughput", "value": round(value, 1), "unit": "verifies/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (5x52 field, u128 accumulators)",
         "data": "synthetic", "config": config_block(args.gpus, bounded=sample),
         "cpu_baseline": {"value": round(value, 1), "unit": "verifies/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 1), "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference = C++ port of the reference's CPU algorithms (oracle/ecport.cpp, OpenMP); the Rust reference cannot be built here (no cargo/rustc)"}))
+        "note": "reference = C++ port of the reference's CPU algorithms (oracle/ecport.cpp, OpenMP); the Rust reference cannot be built here (no cargo/rustc)"})
 
 
 def importlib_pkg():
@@ -215,7 +215,27 @@ def config_block(n_gpus, bounded=None):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Rank 0 must print ONE JSON line: route everything libraries write to fd 1 (NCCL's version banner, torchrun
+    chatter) to stderr and keep a private handle on the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -237,7 +257,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib_pkg()
     wl = pkg.workloads
@@ -328,7 +347,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(q, z, rs, exp)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
