@@ -209,3 +209,18 @@ def test_fixed_base_window_widths(gw):
         assert got == [o.verify_prehash(c, Q, h, r, s) for Q, h, (r, s) in zip(keys, hs, sigs)]
         assert sum(got) > 5
     e.close()
+
+
+def test_plain_c_client(tmp_path):
+    """A plain C program compiled against include/ecb200.h and linked with libecb200.so (no Python in the loop)."""
+    import os
+    import subprocess
+    import ecb200
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cabi_client")
+    libdir = os.path.dirname(ecb200.LIB_PATH)
+    subprocess.check_call(["gcc", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cabi", "client.c"), "-o", exe,
+                           "-L", libdir, "-lecb200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "cabi client ok" in out.stdout
