@@ -469,3 +469,24 @@ def test_abi_error_behaviour_and_reuse(eng):
         assert a == b
         assert a[:33] == o.slot_encode(c, c.G)
     e2.close()
+
+
+@pytest.mark.parametrize("cname,lg", [("k256", 22), ("p256", 21)])
+def test_verify_full_size_mask(eng, cname, lg):
+    """BASELINE.json's full batch size (2^22 secp256k1 rows; 2^21 P-256 rows to bound the tier's run time): the accept
+    mask must equal the one implied by construction (1/16 of the rows corrupted in five ways), a sampled subset must agree
+    with the oracle, and verifying the reversed batch must give the reversed mask (position independence)."""
+    import ecb200
+    wl = __import__("importlib").import_module("rustcrypto-elliptic-curves_b200.workloads")
+    c = o.curve(cname)
+    n = 1 << lg
+    q, z, rs, exp = wl.make_verify_batch(wl.EngineBackend(eng, cname), cname, n, 0xB2000003 + c.cid)
+    ok = np.frombuffer(eng.ecdsa_verify(cname, q, z, rs), np.uint8)
+    assert np.array_equal(ok, exp)
+    assert n - n // 16 <= int(exp.sum()) < n          # 1/16 corrupted; the high-s twins still verify on P-256
+    for i in list(range(0, n, n // 97)) + [5, 21, 37, 53, 69]:
+        Q = (int.from_bytes(q[i, :c.fb].tobytes(), "big"), int.from_bytes(q[i, c.fb:].tobytes(), "big"))
+        r, s = int.from_bytes(rs[i, :c.fb].tobytes(), "big"), int.from_bytes(rs[i, c.fb:].tobytes(), "big")
+        assert bool(ok[i]) == o.verify_prehashed(c, Q, z[i].tobytes(), r, s), i
+    okr = np.frombuffer(eng.ecdsa_verify(cname, q[::-1].copy(), z[::-1].copy(), rs[::-1].copy()), np.uint8)
+    assert np.array_equal(okr[::-1], ok)
