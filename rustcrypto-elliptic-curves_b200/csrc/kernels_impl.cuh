@@ -141,6 +141,16 @@ template <class C, bool CT> __global__ void __launch_bounds__(BLK, ct_min_ctas<C
 // ---------------------------------------------------------------------------------------------
 template <class C> struct Launch {
     static int grid(int n) { return (n + BLK - 1) / BLK; }
+    // The opt-in for > 48 KB of dynamic shared memory is per function AND per device: remember it per device, so a process
+    // that drives several GPUs (one context each) sets it on every one of them.
+    static bool first_use_on_device(bool (&seen)[64]) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return true;
+        if (seen[dev]) return false;
+        seen[dev] = true;
+        return true;
+    }
 
     static void field_op(cudaStream_t s, int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
         if (n <= 0) return;
@@ -156,11 +166,10 @@ template <class C> struct Launch {
     static void mul_gen(cudaStream_t s, bool ct, int n, const u8* k, const u32* tab, u32* proj) {
         if (n <= 0) return;
         const u32 bytes = (u32)Bodies<C>::GEN_WINDOWS * 8u * 2u * C::L * 4u;   // 33 KB (L = 8), 74.5 KB (L = 12)
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool seen[64] = {};
+        if (first_use_on_device(seen)) {
             cudaFuncSetAttribute(k_mul_gen_smem<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
             cudaFuncSetAttribute(k_mul_gen_smem<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-            attr_set = true;
         }
         if (ct) k_mul_gen_smem<C, true><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
         else k_mul_gen_smem<C, false><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
@@ -210,11 +219,9 @@ template <class C> struct Launch {
     }
     static void mul_var_fast(cudaStream_t s, int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
         if (n <= 0) return;
-        static bool attr_set = false;
-        if (!attr_set && win_smem_bytes<C>() > 0) {
+        static bool seen[64] = {};
+        if (win_smem_bytes<C>() > 0 && first_use_on_device(seen))
             cudaFuncSetAttribute(k_mul_var_fast<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem_bytes<C>());
-            attr_set = true;
-        }
         k_mul_var_fast<C><<<grid(n), BLK, win_smem_bytes<C>(), s>>>(n, pts, aff_limbs, inf, k, proj, invalid);
         g_launch_count++;
     }
@@ -234,12 +241,11 @@ template <class C> struct Launch {
         if (n <= 0) return;
         // Schnorr exists for secp256k1 only, SM2DSA for SM2 only (abi.cu rejects other combinations before launching)
         const u32 sm = win_smem_bytes<C>();
-        static bool attr_set = false;
-        if (!attr_set && sm > 0) {
+        static bool seen[64] = {};
+        if (sm > 0 && first_use_on_device(seen)) {
             cudaFuncSetAttribute(k_verify_main<C, VM_ECDSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             cudaFuncSetAttribute(k_verify_main<C, VM_RECOVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             if constexpr (C::A_IS_ZERO) cudaFuncSetAttribute(k_verify_main<C, VM_SCHNORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            attr_set = true;
         }
         if (mode == VM_ECDSA) k_verify_main<C, VM_ECDSA><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
         else if (mode == VM_RECOVER) k_verify_main<C, VM_RECOVER><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
