@@ -74,7 +74,9 @@ struct ecb200_ctx {
     uint32_t* gbig[4] = {};                  // big fixed-base tables of the public-input fast path (built on first use)
     int gw = 16;                             // window width of gbig (ECB200_GW = 4, 8 or 16)
     bool verify_v1 = false;                  // ECB200_VERIFY_V1=1: complete-formula verify kernel (A/B comparisons)
+    bool use_wintab = true;                  // ECB200_WINTAB=0: per-thread Jacobian window tables on the primeorder curves (A/B comparisons)
     DevBuf prep, aff;                        // verify_prep scratch; affine limbs of normalised projective inputs
+    DevBuf wtab;                             // per-row affine window tables of the primeorder public-input path (23 L words per row)
     DevBuf kxy, kst;                         // decoded keys (x||y) and their status bytes; also xy / identity flags of the Schnorr epilogue
     DevBuf proj;                             // projective scratch (n x 3L limbs) — shared by all entry points
     DevBuf partial, one_point;
@@ -240,7 +242,7 @@ int ensure_gbig(ecb200_ctx* c, const CurveLaunch* cl) {
                 if ((v >> b) & 1) { int pos = bit + b; s[FB - 1 - pos / 8] |= (uint8_t)(1u << (pos % 8)); }
         }
         CU(c, cudaMemcpyAsync(d_k, sc.data(), cnt * FB, cudaMemcpyHostToDevice, c->stream));
-        cl->mul_var_fast(c->stream, (int)cnt, d_pts, nullptr, nullptr, d_k, d_proj, nullptr);
+        cl->mul_var_fast(c->stream, (int)cnt, d_pts, nullptr, nullptr, d_k, d_proj, nullptr, nullptr);
         cl->normalize(c->stream, (int)cnt, d_proj, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, c->gbig[cl->id] + off * 2 * L);
         CU(c, cudaGetLastError());
         CU(c, cudaStreamSynchronize(c->stream));
@@ -261,6 +263,17 @@ int mul_gen_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* 
     CU(c, cudaGetLastError());
     return 0;
 }
+// Primeorder curves: make the window tables {1..8}P of all n rows affine with one inversion per 16 rows x 7 entries
+// (k_wintab), so that the window loop of the public-input kernels runs on mixed additions.  *out stays NULL on secp256k1
+// (shared-Z table inside the kernel, no inversion needed) and with ECB200_WINTAB=0 (A/B: per-thread Jacobian tables).
+int window_tables(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_pts, const uint32_t* d_aff, cudaStream_t s, uint32_t** out) {
+    *out = nullptr;
+    if (cl->id == ECB200_K256 || !c->use_wintab || n == 0) return 0;
+    CU(c, c->wtab.reserve(n * 23 * (size_t)cl->L * 4));
+    cl->wintab(s, (int)n, d_pts, d_aff, (uint32_t*)c->wtab.p);
+    *out = (uint32_t*)c->wtab.p;
+    return 0;
+}
 int mul_var_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_pts, const uint8_t* d_inf, const uint8_t* d_k,
                  uint8_t* d_out, uint8_t* d_invalid, uint32_t flags, cudaStream_t s) {
     CU(c, c->proj.reserve(n * 3 * cl->L * 4));
@@ -273,9 +286,15 @@ int mul_var_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* 
         CU(c, c->aff.reserve(n * 2 * cl->L * 4));
         cl->load_proj(s, (int)n, d_pts, proj, nullptr);
         cl->normalize(s, (int)n, proj, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, (uint32_t*)c->aff.p);
-        cl->mul_var_fast(s, (int)n, nullptr, (const uint32_t*)c->aff.p, nullptr, d_k, proj, d_invalid);
+        uint32_t* wt = nullptr;
+        int r = window_tables(c, cl, n, nullptr, (const uint32_t*)c->aff.p, s, &wt);
+        if (r) return r;
+        cl->mul_var_fast(s, (int)n, nullptr, (const uint32_t*)c->aff.p, nullptr, d_k, proj, d_invalid, wt);
     } else {
-        cl->mul_var_fast(s, (int)n, d_pts, nullptr, d_inf, d_k, proj, d_invalid);
+        uint32_t* wt = nullptr;
+        int r = window_tables(c, cl, n, d_pts, nullptr, s, &wt);
+        if (r) return r;
+        cl->mul_var_fast(s, (int)n, d_pts, nullptr, d_inf, d_k, proj, d_invalid, wt);
     }
     cl->normalize(s, (int)n, proj, 0, resolve_compress(cl, flags) ? 1 : 0, d_out, nullptr, nullptr);
     CU(c, cudaGetLastError());
@@ -299,13 +318,16 @@ int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d
         if (r) return r;
         CU(c, c->prep.reserve(n * (size_t)cl->prep_words * 4));
         cl->verify_prep(s, (int)n, mode, d_z, d_rs, (uint32_t*)c->prep.p);
+        uint32_t* wt = nullptr;
+        r = window_tables(c, cl, n, d_q, nullptr, s, &wt);
+        if (r) return r;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (c->timing) {
             CU(c, cudaEventCreate(&e0));
             CU(c, cudaEventCreate(&e1));
             CU(c, cudaEventRecord(e0, s));
         }
-        cl->verify_main(s, (int)n, mode, d_q, d_rs, d_z, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, nullptr);
+        cl->verify_main(s, (int)n, mode, d_q, d_rs, d_z, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, nullptr, wt);
         if (c->timing) {
             CU(c, cudaEventRecord(e1, s));
             c->timed.emplace_back(e0, e1);
@@ -338,7 +360,7 @@ int schnorr_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* 
     CU(c, c->kxy.reserve(n * 2 * (size_t)cl->FB));
     CU(c, c->kst.reserve(n));
     cl->verify_prep(s, (int)n, VM_SCHNORR, d_e, d_sig, (uint32_t*)c->prep.p);
-    cl->verify_main(s, (int)n, VM_SCHNORR, d_pk, d_sig, d_e, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, (uint32_t*)c->proj.p);
+    cl->verify_main(s, (int)n, VM_SCHNORR, d_pk, d_sig, d_e, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, (uint32_t*)c->proj.p, nullptr);
     cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 1 /*NORM_XY_BYTES*/, 0, (uint8_t*)c->kxy.p, (uint8_t*)c->kst.p, nullptr);
     cl->finish(s, (int)n, FIN_SCHNORR, (const uint8_t*)c->kxy.p, 0, (const uint8_t*)c->kst.p, d_sig, d_ok);
     CU(c, cudaGetLastError());
@@ -352,7 +374,7 @@ int recover_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* 
     CU(c, c->prep.reserve(n * (size_t)cl->prep_words * 4));
     CU(c, c->proj.reserve(n * 3 * (size_t)cl->L * 4));
     cl->verify_prep(s, (int)n, VM_RECOVER, d_z, d_rs, (uint32_t*)c->prep.p);
-    cl->verify_main(s, (int)n, VM_RECOVER, nullptr, d_rs, d_z, d_recid, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, (uint32_t*)c->proj.p);
+    cl->verify_main(s, (int)n, VM_RECOVER, nullptr, d_rs, d_z, d_recid, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, (uint32_t*)c->proj.p, nullptr);
     cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 0, resolve_compress(cl, flags) ? 1 : 0, d_keys, nullptr, nullptr);
     cl->finish(s, (int)n, FIN_RECOVER, d_keys, (int)slot_bytes(cl, flags), nullptr, nullptr, d_ok);
     CU(c, cudaGetLastError());
@@ -487,6 +509,7 @@ int ecb200_init(int device, ecb200_ctx** out) {
              cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
     if (const char* e = getenv("ECB200_GW")) { int g = atoi(e); if (g == 4 || g == 8 || g == 16) c->gw = g; }
     if (const char* e = getenv("ECB200_VERIFY_V1")) c->verify_v1 = atoi(e) != 0;
+    if (const char* e = getenv("ECB200_WINTAB")) c->use_wintab = atoi(e) != 0;
     if (!ok || build_tables(c) != 0) {
         fprintf(stderr, "ecb200_init failed: %s (%s)\n", c->err.c_str(), cudaGetErrorString(cudaGetLastError()));
         ecb200_destroy(c);
@@ -508,6 +531,7 @@ void ecb200_destroy(ecb200_ctx* c) {
     }
     c->prep.release();
     c->aff.release();
+    c->wtab.release();
     c->kxy.release();
     c->kst.release();
     c->proj.release();
@@ -679,7 +703,7 @@ int ecb200_lincomb(ecb200_ctx* c, int curve, size_t n_terms, const uint8_t* pts,
                         (const uint8_t*)c->d_in[0][1].p, (uint32_t*)c->proj.p + off * 3 * L, nullptr);
         else
             cl->mul_var_fast(s, (int)cnt, (const uint8_t*)c->d_in[0][0].p, nullptr, nullptr, (const uint8_t*)c->d_in[0][1].p,
-                             (uint32_t*)c->proj.p + off * 3 * L, nullptr);
+                             (uint32_t*)c->proj.p + off * 3 * L, nullptr, nullptr);
         CU(c, cudaStreamSynchronize(s));   // staging buffers are reused by the next piece
     }
     uint32_t* d_sum = (uint32_t*)c->one_point.p;

@@ -518,7 +518,7 @@ template <class C> struct Bodies {
     template <int NS = 0>
     ECB_DEV static void body_verify_main(int tid, int n, int mode, const u8* q, const u8* rs, const u8* zin, const u8* aux,
                                          const u32* scratch, const u32* gbig, int gw, u8* ok_out, u32* proj_out,
-                                         u32* stab = nullptr, int sstride = 0) {
+                                         u32* stab = nullptr, int sstride = 0, const u32* wtab = nullptr) {
         if (tid >= n) return;
         const u32* rec = scratch + (size_t)tid * PREP_WORDS;
         typename JJ::A Q;
@@ -564,7 +564,12 @@ template <class C> struct Bodies {
             ECB_UNROLL
             for (int l = 0; l < L; l++) u2[l] = rec[L + l];
             valid = valid && (rec[2 * L] & 1u);
-            JJ::mul_window_signed(acc, Q, u2);
+            // ECDSA / SM2DSA: the key's window table was made affine for the whole batch by k_wintab; recovery derives its
+            // point inside this kernel and keeps the per-thread Jacobian table
+            // (a run-time switch on purpose: with the Jacobian loop compiled out, ptxas allocated the P-384 squarer so badly
+            // - predicate spills, 367 instead of 272 instructions - that the kernel lost 10 %; P-256 was 1 % slower too)
+            if (wtab && (mode == VM_ECDSA || mode == VM_SM2DSA)) JJ::mul_window_affine(acc, wtab + (size_t)tid * 16 * L, u2);
+            else JJ::mul_window_signed(acc, Q, u2);
         }
         JJ::add_fixed_base(acc, u1, gbig, gw);
         if (mode == VM_ECDSA) {
@@ -735,12 +740,105 @@ template <class C> struct Bodies {
         }
     }
 
+    // ------------------------------------------------------------------ per-row affine window tables (primeorder public-input path)
+    // wtab[row][j] = (j+1) * Q_row as AFFINE field-internal limbs (x|y, 2L words), j = 0..7, for the window loop of
+    // Jac::mul_window_affine.  Pass 1 builds the Jacobian multiples 2Q..8Q of every row a thread owns (rows tid, tid +
+    // nthreads, ...; X, Y parked in the table slots, Z_2..Z_8 in zbuf) and multiplies the rows' Z-products together;
+    // one Fermat inversion per thread; pass 2 unwinds Montgomery's trick at both levels (across the rows, then inside
+    // a row) and rewrites the slots as (X/Z^2, Y/Z^3).  An invalid or identity point is replaced by the generator: its
+    // row is rejected (or answered with the identity) by the consumer, the table only has to stay invertible.  On these
+    // curves (cofactor 1, prime order) no multiple 2Q..8Q of a valid Q is the identity, so no Z is zero.
+    //   pts: n x 2FB bytes (x||y) or aff_limbs: n x 2L field-internal limbs;  zbuf: n x 7L words of scratch.
+    static constexpr int WT_EPT = 16;
+    ECB_DEV static void body_wintab(int tid, int nthreads, int n, const u8* pts, const u32* aff_limbs, u32* wtab, u32* zbuf) {
+        E pref[WT_EPT];
+        E run;
+        F::set_one(run);
+        int cnt = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < WT_EPT; j++) {
+            const int i = tid + j * nthreads;
+            if (i >= n) break;
+            Aff a;
+            bool ok;
+            if (aff_limbs) { load_aff_limbs(a, aff_limbs + (size_t)i * 2 * L); ok = G::on_curve(a); }
+            else ok = G::load_affine(a, pts + (size_t)i * 2 * FB);
+            if (!ok) G::generator(a);
+            typename JJ::A Q;
+            Q.x = a.x; Q.y = a.y;
+            u32* row = wtab + (size_t)i * 16 * L;
+            u32* zr = zbuf + (size_t)i * 7 * L;
+            store_entry(row, Q.x, Q.y);
+            typename JJ::J d2, t, d4;
+            E prod;
+            JJ::dbl_affine(d2, Q);                 store_entry(row + 2 * L, d2.X, d2.Y);  store_fe(zr, d2.Z);          prod = d2.Z;
+            JJ::madd(t, d2, Q, nullptr);           store_entry(row + 4 * L, t.X, t.Y);    store_fe(zr + L, t.Z);       F::mul(prod, prod, t.Z);
+            JJ::dbl(d4, d2);                       store_entry(row + 6 * L, d4.X, d4.Y);  store_fe(zr + 2 * L, d4.Z);  F::mul(prod, prod, d4.Z);
+            JJ::dbl(d2, t);                        /* 6Q */
+            JJ::madd(t, d4, Q, nullptr);           store_entry(row + 8 * L, t.X, t.Y);    store_fe(zr + 3 * L, t.Z);   F::mul(prod, prod, t.Z);
+            store_entry(row + 10 * L, d2.X, d2.Y); store_fe(zr + 4 * L, d2.Z);            F::mul(prod, prod, d2.Z);
+            JJ::madd(t, d2, Q, nullptr);           store_entry(row + 12 * L, t.X, t.Y);   store_fe(zr + 5 * L, t.Z);   F::mul(prod, prod, t.Z);
+            JJ::dbl(d4, d4);                       store_entry(row + 14 * L, d4.X, d4.Y); store_fe(zr + 6 * L, d4.Z);  F::mul(prod, prod, d4.Z);
+            pref[j] = run;
+            F::mul(run, run, prod);
+            cnt++;
+        }
+        if (cnt == 0) return;
+        E inv;
+        F::inv(inv, run);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = cnt - 1; j >= 0; j--) {
+            const int i = tid + j * nthreads;
+            u32* row = wtab + (size_t)i * 16 * L;
+            const u32* zr = zbuf + (size_t)i * 7 * L;
+            E z[7], c[7];
+            ECB_UNROLL
+            for (int k = 0; k < 7; k++) load_fe(z[k], zr + k * L);
+            c[0] = z[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int k = 1; k < 7; k++) F::mul(c[k], c[k - 1], z[k]);      // c[6] = this row's Z-product
+            E u;
+            F::mul(u, inv, pref[j]);                                        // 1 / c[6]
+            F::mul(inv, inv, c[6]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int k = 6; k >= 0; k--) {
+                E zi;
+                if (k > 0) { F::mul(zi, u, c[k - 1]); F::mul(u, u, z[k]); } else zi = u;   // zi = 1 / z[k]
+                E zi2, zi3, x, y;
+                u32* e = row + (size_t)(k + 1) * 2 * L;
+                load_fe(x, e); load_fe(y, e + L);
+                F::sqr(zi2, zi);
+                F::mul(zi3, zi2, zi);
+                F::mul(x, x, zi2);
+                F::mul(y, y, zi3);
+                store_entry(e, x, y);
+            }
+        }
+    }
+    ECB_DEV static void store_fe(u32* dst, const E& a) {
+        ECB_UNROLL
+        for (int l = 0; l < L; l++) dst[l] = a.v[l];
+    }
+    ECB_DEV static void load_fe(E& a, const u32* src) {
+        ECB_UNROLL
+        for (int l = 0; l < L; l++) a.v[l] = src[l];
+    }
+    ECB_DEV static void store_entry(u32* dst, const E& x, const E& y) { store_fe(dst, x); store_fe(dst + L, y); }
+
     // ------------------------------------------------------------------ variable-base k*P, vartime fast path (v2)
     // pts: n x 2FB big-endian affine bytes (aff_limbs == nullptr), or internal affine limbs produced by the
     // normalisation kernel from projective inputs (all-zero entry = identity); output projective limbs
     template <int NS = 0>
     ECB_DEV static void body_mul_var_fast(int tid, int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* out, u8* invalid,
-                                          u32* stab = nullptr, int sstride = 0) {
+                                          u32* stab = nullptr, int sstride = 0, const u32* wtab = nullptr) {
         if (tid >= n) return;
         Aff a;
         bool ok, isinf;
@@ -766,7 +864,8 @@ template <class C> struct Bodies {
                 K256Glv::decompose(sp, kk);
                 K256Fast::template mul_glv<NS>(acc, Q, sp, stab, sstride);
             } else {
-                JJ::mul_window_signed(acc, Q, kk);
+                if (wtab) JJ::mul_window_affine(acc, wtab + (size_t)tid * 16 * L, kk);
+                else JJ::mul_window_signed(acc, Q, kk);
             }
             JJ::to_proj(r, acc);
         }

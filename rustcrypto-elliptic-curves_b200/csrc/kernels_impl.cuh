@@ -56,17 +56,28 @@ template <class C> constexpr int win_smem_entries() { return C::A_IS_ZERO ? ECB_
 template <class C> constexpr u32 win_smem_bytes() { return (u32)win_smem_entries<C>() * 16u * 4u * BLK; }
 extern __shared__ __align__(16) u32 ecb_dyn_smem[];
 
-template <class C> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_mul_var_fast(int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
+// wtab != NULL: window tables come from k_wintab (affine, global memory) instead of a per-thread Jacobian table (primeorder curves)
+template <class C> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_mul_var_fast(int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid,
+                                                                                                       const u32* wtab) {
     Bodies<C>::template body_mul_var_fast<win_smem_entries<C>()>(blockIdx.x * BLK + threadIdx.x, n, pts, aff_limbs, inf, k, proj, invalid,
-                                                                  ecb_dyn_smem + threadIdx.x, BLK);
+                                                                      ecb_dyn_smem + threadIdx.x, BLK, wtab);
+}
+// per-row affine window tables {1..8}Q for the primeorder public-input kernels (Montgomery's trick over the rows a thread owns)
+#ifndef ECB_WT_MIN_CTAS
+#define ECB_WT_MIN_CTAS 4
+#endif
+template <class C> constexpr int wt_min_ctas() { return C::L > 8 ? 3 : ECB_WT_MIN_CTAS; }
+template <class C> __global__ void __launch_bounds__(BLK, wt_min_ctas<C>()) k_wintab(int n, const u8* pts, const u32* aff_limbs, u32* wtab, u32* zbuf) {
+    Bodies<C>::body_wintab(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, pts, aff_limbs, wtab, zbuf);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_verify_prep(int n, int mode, const u8* z, const u8* rs, u32* scratch) {
     Bodies<C>::body_verify_prep(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, mode, z, rs, scratch);
 }
 // MODE is a template parameter: the ECDSA instance carries no decompression / projective-output code
-template <class C, int MODE> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_verify_main(int n, const u8* q, const u8* rs, const u8* z, const u8* aux, const u32* scratch, const u32* gbig, int gw, u8* ok, u32* proj_out) {
+template <class C, int MODE> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_verify_main(int n, const u8* q, const u8* rs, const u8* z, const u8* aux, const u32* scratch, const u32* gbig, int gw, u8* ok, u32* proj_out,
+                                                                                                        const u32* wtab) {
     Bodies<C>::template body_verify_main<win_smem_entries<C>()>(blockIdx.x * BLK + threadIdx.x, n, MODE, q, rs, z, aux, scratch, gbig, gw, ok, proj_out,
-                                                                 ecb_dyn_smem + threadIdx.x, BLK);
+                                                                 ecb_dyn_smem + threadIdx.x, BLK, wtab);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_decode(int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
     Bodies<C>::body_decode(blockIdx.x * BLK + threadIdx.x, n, mode, enc, stride, xy, status);
@@ -217,12 +228,34 @@ template <class C> struct Launch {
         k_verify<C><<<grid(n), BLK, 0, s>>>(n, q, z, rs, gtab, ok);
         g_launch_count++;
     }
-    static void mul_var_fast(cudaStream_t s, int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid) {
+    // Affine window tables for n rows (primeorder curves only; a no-op on secp256k1, whose shared-Z table needs no inversion).
+    // wtab: n x 16L words of tables followed by n x 7L words of scratch for the Z coordinates (wintab_words(n) in all).
+    static void wintab(cudaStream_t s, int n, const u8* pts, const u32* aff_limbs, u32* wtab) {
+        if (n <= 0 || C::A_IS_ZERO) return;
+        // One launch per round of at most one wave of resident CTAs x WT_EPT rows per thread: a launch never ends in a
+        // nearly empty second wave, and the rounds are equal (2^22 rows = 3 rounds of 13 rows per thread, not 2 + a rest).
+        // Small batches still take 3 rows per thread so that the inversion (~270 multiplications) is shared.
+        const long wave = (long)148 * wt_min_ctas<C>() * BLK;
+        const int rounds = (int)((n + wave * Bodies<C>::WT_EPT - 1) / (wave * Bodies<C>::WT_EPT));
+        const int per_round = (n + rounds - 1) / rounds;
+        u32* zbuf = wtab + (size_t)n * 16 * C::L;
+        for (int off = 0; off < n; off += per_round) {
+            const int cnt = n - off < per_round ? n - off : per_round;
+            int ept = (int)((cnt + wave - 1) / wave);
+            if (ept < 3) ept = 3;
+            const int threads = (cnt + ept - 1) / ept;
+            k_wintab<C><<<grid(threads), BLK, 0, s>>>(cnt, pts ? pts + (size_t)off * 2 * C::FB : nullptr, aff_limbs ? aff_limbs + (size_t)off * 2 * C::L : nullptr,
+                                                      wtab + (size_t)off * 16 * C::L, zbuf + (size_t)off * 7 * C::L);
+            g_launch_count++;
+        }
+    }
+    static void mul_var_fast(cudaStream_t s, int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid,
+                             const u32* wtab) {
         if (n <= 0) return;
         static bool seen[64] = {};
         if (win_smem_bytes<C>() > 0 && first_use_on_device(seen))
             cudaFuncSetAttribute(k_mul_var_fast<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem_bytes<C>());
-        k_mul_var_fast<C><<<grid(n), BLK, win_smem_bytes<C>(), s>>>(n, pts, aff_limbs, inf, k, proj, invalid);
+        k_mul_var_fast<C><<<grid(n), BLK, win_smem_bytes<C>(), s>>>(n, pts, aff_limbs, inf, k, proj, invalid, C::A_IS_ZERO ? nullptr : wtab);
         g_launch_count++;
     }
     static int ept_threads(int n) {   // threads for the Montgomery-trick kernels: rows per thread that keep ~1 CTA per SM busy (latency-bound below that, see normalize)
@@ -237,7 +270,7 @@ template <class C> struct Launch {
         g_launch_count++;
     }
     static void verify_main(cudaStream_t s, int n, int mode, const u8* q, const u8* rs, const u8* z, const u8* aux, const u32* scratch,
-                            const u32* gbig, int gw, u8* ok, u32* proj_out) {
+                            const u32* gbig, int gw, u8* ok, u32* proj_out, const u32* wtab) {
         if (n <= 0) return;
         // Schnorr exists for secp256k1 only, SM2DSA for SM2 only (abi.cu rejects other combinations before launching)
         const u32 sm = win_smem_bytes<C>();
@@ -247,12 +280,13 @@ template <class C> struct Launch {
             cudaFuncSetAttribute(k_verify_main<C, VM_RECOVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             if constexpr (C::A_IS_ZERO) cudaFuncSetAttribute(k_verify_main<C, VM_SCHNORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         }
-        if (mode == VM_ECDSA) k_verify_main<C, VM_ECDSA><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
-        else if (mode == VM_RECOVER) k_verify_main<C, VM_RECOVER><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+        if (C::A_IS_ZERO) wtab = nullptr;
+        if (mode == VM_ECDSA) k_verify_main<C, VM_ECDSA><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out, wtab);
+        else if (mode == VM_RECOVER) k_verify_main<C, VM_RECOVER><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out, nullptr);
         else if (mode == VM_SCHNORR) {
-            if constexpr (C::A_IS_ZERO) k_verify_main<C, VM_SCHNORR><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+            if constexpr (C::A_IS_ZERO) k_verify_main<C, VM_SCHNORR><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out, nullptr);
         } else if (mode == VM_SM2DSA) {
-            if constexpr (C::ID == 3) k_verify_main<C, VM_SM2DSA><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out);
+            if constexpr (C::ID == 3) k_verify_main<C, VM_SM2DSA><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out, wtab);
         }
         g_launch_count++;
     }
@@ -275,7 +309,7 @@ template <class C> struct Launch {
         static CurveLaunch t = {
             C::ID, C::L, C::FB, C::A_IS_ZERO ? 8 : 15, Bodies<C>::GEN_WINDOWS, 8, C::COMPRESS_DEFAULT, {0},
             &field_op, &mul_var, &mul_gen, &load_proj, &normalize, &sum, &proj_to_bytes, &verify,
-            &mul_var_fast, &verify_prep, &verify_main, &decode, &finish, &sign_finish, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
+            &mul_var_fast, &verify_prep, &verify_main, &decode, &finish, &sign_finish, &wintab, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
         static bool init = false;
         if (!init) {   // R mod n (the Montgomery "one" of the scalar field) as big-endian bytes
             for (int i = 0; i < C::L; i++) {

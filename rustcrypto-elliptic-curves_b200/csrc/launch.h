@@ -28,16 +28,20 @@ struct CurveLaunch {
     void (*verify)(cudaStream_t s, int n, const uint8_t* q, const uint8_t* z, const uint8_t* rs, const uint32_t* gtab,
                    uint8_t* ok);
     // fast public-input path (jac.cuh)
+    // wtab: per-row affine window tables made by `wintab` (primeorder curves), or NULL = per-thread Jacobian tables
     void (*mul_var_fast)(cudaStream_t s, int n, const uint8_t* pts, const uint32_t* aff_limbs, const uint8_t* inf,
-                         const uint8_t* k, uint32_t* proj, uint8_t* invalid);
+                         const uint8_t* k, uint32_t* proj, uint8_t* invalid, const uint32_t* wtab);
     // mode = VM_* (kernels.cuh): ECDSA verify, SM2DSA verify, BIP340 Schnorr verify, ECDSA public-key recovery
     void (*verify_prep)(cudaStream_t s, int n, int mode, const uint8_t* z, const uint8_t* rs, uint32_t* scratch);
     void (*verify_main)(cudaStream_t s, int n, int mode, const uint8_t* q, const uint8_t* rs, const uint8_t* z, const uint8_t* aux,
-                        const uint32_t* scratch, const uint32_t* gbig, int gw, uint8_t* ok, uint32_t* proj_out);
+                        const uint32_t* scratch, const uint32_t* gbig, int gw, uint8_t* ok, uint32_t* proj_out, const uint32_t* wtab);
     void (*decode)(cudaStream_t s, int n, int mode, const uint8_t* enc, int stride, uint8_t* xy, uint8_t* status);
     void (*finish)(cudaStream_t s, int n, int kind, const uint8_t* a, int stride, const uint8_t* inf, const uint8_t* rs, uint8_t* ok);
     void (*sign_finish)(cudaStream_t s, int n, const uint8_t* d, const uint8_t* k, const uint8_t* z, const uint32_t* aff,
                         uint8_t* rs_out, uint8_t* recid_out, uint8_t* ok_out);
+    // affine window tables {1..8}Q of n points (x||y bytes or field-internal limbs) into wtab (23 L words per row: 16 L of
+    // table, 7 L of scratch); no-op on secp256k1
+    void (*wintab)(cudaStream_t s, int n, const uint8_t* pts, const uint32_t* aff_limbs, uint32_t* wtab);
     int prep_words;   // u32 words of scratch per row between verify_prep and verify_main
     int sum_blocks;
 };

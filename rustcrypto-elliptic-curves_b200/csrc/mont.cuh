@@ -190,6 +190,9 @@ template <class P> struct Mont {
         if constexpr (SPLIT) { Wide t = mulw_fn(a, b); r = redc_fn(t); }
         else r = mul_fn(a, b);
     }
+    // The squaring stays one function.  Splitting it like mul costs P-384 3-6 % (measured); whether the one-function form
+    // hits the predicate spills depends on the kernel it is compiled into (ptxas allocates registers across the call
+    // graph): check `tools/sass_funcs.py` for P2R / LOP3 in the squarer after touching a kernel that calls it.
     ECB_DEV static void sqr(E& r, const E& a) { r = sqr_fn(a); }
 #endif
     ECB_DEV static void add(E& r, const E& a, const E& b) {

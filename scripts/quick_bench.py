@@ -31,7 +31,11 @@ def rand_scalars(n, fb, seed):
     return a
 
 
-for cname, n in (("k256", 1 << 18), ("p256", 1 << 17), ("sm2", 1 << 17), ("p384", 1 << 16)):
+# usage: quick_bench.py [curve,curve,...] [log2 n]   (default: every curve at its quick size)
+CASES = (("k256", 1 << 18), ("p256", 1 << 17), ("sm2", 1 << 17), ("p384", 1 << 16))
+if len(sys.argv) > 1:
+    CASES = tuple((c, (1 << int(sys.argv[2])) if len(sys.argv) > 2 else dict(CASES)[c]) for c in sys.argv[1].split(","))
+for cname, n in CASES:
     c = o.curve(cname)
     fb = c.fb
     ks = torch.from_numpy(rand_scalars(n, fb, 1)).to(dev)

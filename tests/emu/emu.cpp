@@ -110,7 +110,11 @@ template <class C> struct Emu {
         int need = (n + B::PREP_EPT - 1) / B::PREP_EPT;
         if (nthreads < need) nthreads = need;
         for (int t = 0; t < nthreads; t++) B::body_verify_prep(t, nthreads, n, mode, z, rs, scratch.data());
-        for (int i = 0; i < n; i++) B::body_verify_main(i, n, mode, q, rs, z, aux, scratch.data(), gt.data(), gw, ok, proj.data());
+        // primeorder curves, ECDSA / SM2DSA: affine window tables for the whole batch first (as abi.cu window_tables does)
+        std::vector<u32> wt;
+        if (!C::A_IS_ZERO && (mode == VM_ECDSA || mode == VM_SM2DSA)) wt = wintab(n, q, nullptr, nthreads);
+        for (int i = 0; i < n; i++)
+            B::body_verify_main(i, n, mode, q, rs, z, aux, scratch.data(), gt.data(), gw, ok, proj.data(), nullptr, 0, wt.empty() ? nullptr : wt.data());
         if (mode == VM_SCHNORR) {
             std::vector<u8> xy((size_t)2 * FB * n), inf(n);
             normalize(n, proj.data(), NORM_XY_BYTES, 0, xy.data(), inf.data(), nullptr, 0);
@@ -120,6 +124,13 @@ template <class C> struct Emu {
             const int stride = compress ? 1 + FB : 1 + 2 * FB;
             for (int i = 0; i < n; i++) B::body_finish(i, n, FIN_RECOVER, out, stride, nullptr, nullptr, ok);
         }
+    }
+    static std::vector<u32> wintab(int n, const u8* pts, const u32* aff, int nthreads) {
+        std::vector<u32> wt((size_t)n * 23 * L);
+        int need = (n + B::WT_EPT - 1) / B::WT_EPT;
+        if (nthreads < need) nthreads = need;
+        for (int t = 0; t < nthreads; t++) B::body_wintab(t, nthreads, n, pts, aff, wt.data(), wt.data() + (size_t)n * 16 * L);
+        return wt;
     }
     static void verify2(int n, const u8* q, const u8* z, const u8* rs, u8* ok, int nthreads) {
         verify_mode(VM_ECDSA, n, q, z, rs, nullptr, ok, nullptr, 0, nthreads);
@@ -139,7 +150,9 @@ template <class C> struct Emu {
     }
     static void mul_var_fast(int n, const u8* pts, const u8* inf, const u8* k, u8* out, int compress, u8* invalid) {
         std::vector<u32> proj((size_t)3 * L * n);
-        for (int i = 0; i < n; i++) B::body_mul_var_fast(i, n, pts, nullptr, inf, k, proj.data(), invalid);
+        std::vector<u32> wt;
+        if (!C::A_IS_ZERO) wt = wintab(n, pts, nullptr, (n + 2) / 3);   // three rows per logical thread
+        for (int i = 0; i < n; i++) B::body_mul_var_fast(i, n, pts, nullptr, inf, k, proj.data(), invalid, nullptr, 0, wt.empty() ? nullptr : wt.data());
         normalize(n, proj.data(), NORM_SEC1, compress, out, nullptr, nullptr, 0);
     }
     static void field_op(int which, int op, int n, const u8* a, const u8* b, u8* out, u8* ok) {
