@@ -259,9 +259,8 @@ template <class C> struct Jac {
     // ---- the same loop over an AFFINE table {1..8}Q that lives in global memory (2L limbs per entry, built for the whole
     // batch by k_wintab: Jacobian multiples, then ONE field inversion per thread shared by up to 16 rows x 7 entries through
     // Montgomery's trick).  Every window addition becomes a mixed addition: 8M+3S instead of 11M+5S, 60 times per row.
-#ifndef ECB_WT_PREFETCH
-#define ECB_WT_PREFETCH 0
-#endif
+    // Measured and not kept: prefetch.global.L1 / .L2 of the entry before the four doublings (+-0.1 %: six resident CTAs
+    // already hide the gather), the Jacobian loop compiled out of the kernel (see kernels.cuh body_verify_main).
     ECB_DEV static void load_entry(A& e, const u32* p) {
 #if defined(__CUDA_ARCH__)
         const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -291,16 +290,6 @@ template <class C> struct Jac {
             u32 mag, neg;
             digit16(kb, i, top, mag, neg);
             const u32* ent = tab + (size_t)(mag ? mag - 1 : 0) * 2 * L;
-#if defined(__CUDA_ARCH__) && ECB_WT_PREFETCH
-            // the digit is known before the four doublings: start pulling the entry towards the SM now
-            if (ECB_WT_PREFETCH == 1) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(ent));
-                if (L > 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(ent + 2 * L - 1));
-            } else {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ent));
-                if (L > 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(ent + 2 * L - 1));
-            }
-#endif
             if (i != top) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1

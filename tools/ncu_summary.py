@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """Summarise one kernel of an ncu report (--set full) as a markdown table + opcode histogram.
-usage: ncu_summary.py report.ncu-rep [out.md] [title]"""
+usage: ncu_summary.py report.ncu-rep [out.md] [title] [kernel-name regex, for reports holding several kernels]"""
 import csv, io, subprocess, sys, json, os
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
 out = sys.argv[2] if len(sys.argv) > 2 else None
 title = sys.argv[3] if len(sys.argv) > 3 else os.path.basename(rep)
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+kfilter = ["--kernel-name", "regex:" + sys.argv[4]] if len(sys.argv) > 4 else []
+raw = subprocess.run(["ncu", "-i", rep] + kfilter + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 m = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
@@ -30,16 +31,18 @@ for k in WANT:
     if k in m:
         lines.append("| %s | %s | %s |" % (k, m[k][0], m[k][1]))
 # opcode histogram
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
+src = subprocess.run(["ncu", "-i", rep] + kfilter + ["--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
 start = next(i for i, l in enumerate(src) if l.startswith('"Address"'))
 import collections
 ops = collections.Counter(); tot = 0
-for row in csv.DictReader(io.StringIO("\n".join(src[start:]))):
+# a report captured with --import-source on lists the kernel twice (SASS view, then source-correlated view): first table only
+end = next((i for i in range(start + 1, len(src)) if src[i].startswith('"Address"')), len(src))
+for row in csv.DictReader(io.StringIO("\n".join(src[start:end]))):
     s = row["Source"].strip()
     if not s: continue
     t = s.split(); op = t[1] if t[0].startswith("@") else t[0]
     try: n = int(row["Instructions Executed"])
-    except ValueError: continue
+    except (ValueError, TypeError): continue
     ops[op.rstrip(";")] += n; tot += n
 lines += ["", "Executed warp instructions by opcode (top 16 of %d):" % tot, "", "| opcode | warp-inst | share |", "|---|---|---|"]
 for op, n in ops.most_common(16):
