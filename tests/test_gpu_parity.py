@@ -371,6 +371,66 @@ def test_verify_kernels_agree(golden):
     e2.close()
 
 
+@pytest.mark.parametrize("cname", ["p256", "p384", "sm2"])
+def test_window_table_paths_agree(eng, cname):
+    """Primeorder public-input path: batch-affine window tables (k_wintab, the default) against per-thread Jacobian tables
+    (ECB200_WINTAB=0) on the same rows — signatures incl. corrupted ones and off-curve keys, P*k with identity / invalid /
+    repeated points and projective inputs — at a size that gives every k_wintab thread several rows and a ragged tail."""
+    import os
+    import ecb200
+    c = o.curve(cname)
+    fb = c.fb
+    os.environ["ECB200_WINTAB"] = "0"
+    try:
+        e0 = ecb200.Engine(0)
+    finally:
+        del os.environ["ECB200_WINTAB"]
+    rng = random.Random(5 + c.cid)
+    base = make_sigs(c, rng, 24)
+    n = 5003                                            # > 3 rows per thread for part of the grid, not a multiple of anything
+    keys, hs, sigs = [], [], []
+    for i in range(n):
+        Q, h, r, s = base[i % len(base)]
+        if i % 7 == 3:
+            s ^= 1 << (i % 200)
+        if i % 11 == 5:
+            Q = (Q[0], Q[1] ^ 1)                        # off-curve key: the table kernel substitutes G, the row is rejected
+        if i % 13 == 6:
+            Q = (0, 0)
+        keys.append(Q); hs.append(h); sigs.append((r, s))
+    a = eng.verify_prehash_batch(cname, keys, hs, sigs)
+    b = e0.verify_prehash_batch(cname, keys, hs, sigs)
+    assert a == b and 0 < sum(a) < n
+    sample = list(range(0, n, 97))
+    assert [a[i] for i in sample] == [o.verify_prehash(c, keys[i], hs[i], *sigs[i]) for i in sample]
+    # P*k, public scalars
+    m = 1200
+    pts = [o.mul_gen(c, rng.randrange(1, c.n)) for _ in range(16)]
+    pb = bytearray(b"".join(be(pts[i % 16], fb) for i in range(m)))
+    kb = be([rng.randrange(c.n) if i % 17 else (0, 1, c.n - 1)[i % 3] for i in range(m)], fb)
+    inf = bytearray(m)
+    for i in range(0, m, 19):
+        inf[i] = 1
+    pb[2 * fb * 7: 2 * fb * 8] = be((1, 1), fb)         # off-curve
+    out1, inv1 = eng.mul_batch(cname, bytes(pb), kb, bytes(inf), 0)
+    out0, inv0 = e0.mul_batch(cname, bytes(pb), kb, bytes(inf), 0)
+    assert out1 == out0 and inv1 == inv0 and inv1[7] == 1
+    good = bytearray(pb)
+    good[2 * fb * 7: 2 * fb * 8] = be(c.G, fb)          # oracle on the batch with the invalid row replaced; that row itself = identity slot
+    exp = o.batch_mul_var_affine(c, bytes(good), bytes(inf), kb)
+    st = len(out1) // m
+    assert out1[:7 * st] == exp[:7 * st] and out1[8 * st:] == exp[8 * st:] and out1[7 * st:8 * st] == bytes(st)
+    xyz = bytearray()
+    for i in range(m):
+        P = pts[i % 16]
+        lam = rng.randrange(1, c.p)
+        xyz += be((0, 5, 0), fb) if i % 23 == 4 else be((P[0] * lam % c.p, P[1] * lam % c.p, lam), fb)
+    out1, _ = eng.mul_batch(cname, bytes(xyz), kb, None, 8)
+    out0, _ = e0.mul_batch(cname, bytes(xyz), kb, None, 8)
+    assert out1 == out0 == o.batch_mul_var_proj(c, bytes(xyz), kb)
+    e0.close()
+
+
 def test_large_batch_properties(eng):
     """Size-independent properties at a large size (2^18 here keeps the GPU test tier short; bench.py runs
     the full BASELINE sizes): (a) k*G via fixed-base == via variable-base with P = G; (b) (k1+k2)G ==
