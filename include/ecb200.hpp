@@ -6,8 +6,8 @@
 //
 //   reference item (file:line)                                                  here
 //   --------------------------------------------------------------------------  -----------------------------------------
-//   k256::Secp256k1 / p256::NistP256 / p384::NistP384 / sm2::Sm2                 curve markers (Curve::ORDER, FieldBytesSize)
-//     (k256/src/lib.rs:76-111, p256/src/lib.rs:74-120, p384/src/lib.rs:50-76, sm2/src/lib.rs:60-85)
+//   k256::Secp256k1 / p256::NistP256 / p384::NistP384 / sm2::Sm2 / p192::NistP192 curve markers (Curve::ORDER, FieldBytesSize)
+//     (k256/src/lib.rs:76-111, p256/src/lib.rs:74-120, p384/src/lib.rs:50-76, sm2/src/lib.rs:60-85, p192/src/lib.rs:42-66)
 //   Scalar: PrimeField::{from_repr,to_repr}, Reduce::reduce_bytes, IsHigh        Scalar<C>
 //     (k256/src/arithmetic/scalar.rs:340-377,519-523,700-713)
 //   AffinePoint {x, y, infinity}, ToEncodedPoint, AffineCoordinates              AffinePoint<C>, EncodedPoint<C>
@@ -153,6 +153,15 @@ struct Sm2 {         // sm2/src/lib.rs:60-85
     static constexpr bool LOW_S_ONLY = false;
     static constexpr const char* NAME = "sm2";
     static std::array<uint8_t, 32> order() { return detail::from_hex<32>("FFFFFFFEFFFFFFFFFFFFFFFFFFFFFFFF7203DF6B21C6052B53BBF40939D54123"); }
+};
+
+struct NistP192 {    // p192/src/lib.rs:42-66 (the primeorder template on 24-byte fields)
+    static constexpr int ID = ECB200_P192;
+    static constexpr size_t FB = 24;
+    static constexpr bool COMPRESS_POINTS = false;
+    static constexpr bool LOW_S_ONLY = false;
+    static constexpr const char* NAME = "p192";
+    static std::array<uint8_t, 24> order() { return detail::from_hex<24>("FFFFFFFFFFFFFFFFFFFFFFFF99DEF836146BC9B1B4D22831"); }
 };
 
 template <class C> using FieldBytes = std::array<uint8_t, C::FB>;   // big-endian, `elliptic_curve::FieldBytes<C>`
@@ -714,6 +723,18 @@ using Signature = ecb200::ecdsa::Signature<NistP384>;
 using VerifyingKey = ecb200::ecdsa::VerifyingKey<NistP384>;
 }  // namespace ecdsa
 }  // namespace p384
+namespace p192 {
+using Curve = NistP192;
+using FieldBytes = ecb200::FieldBytes<NistP192>;
+using Scalar = ecb200::Scalar<NistP192>;
+using AffinePoint = ecb200::AffinePoint<NistP192>;
+using ProjectivePoint = ecb200::ProjectivePoint<NistP192>;
+using EncodedPoint = ecb200::EncodedPoint<NistP192>;
+namespace ecdsa {
+using Signature = ecb200::ecdsa::Signature<NistP192>;
+using VerifyingKey = ecb200::ecdsa::VerifyingKey<NistP192>;
+}  // namespace ecdsa
+}  // namespace p192
 namespace sm2 {
 using Curve = Sm2;
 using FieldBytes = ecb200::FieldBytes<Sm2>;

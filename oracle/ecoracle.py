@@ -89,7 +89,18 @@ SM2 = Curve(
     gy=0xBC3736A2F4F6779C59BDCEE36B692153D0A9877CC62A474002DF32E52139F0A0,
     fb=32, compress=False, low_s=False)
 
-CURVES = {c.name: c for c in (K256, P256, P384, SM2)}
+# p192/src/arithmetic.rs:36-55 (a = -3, b, generator), p192/src/arithmetic/field.rs:43 (modulus), p192/src/lib.rs:42 (order)
+_P192_P = 2**192 - 2**64 - 1
+P192 = Curve(
+    "p192", 4,
+    p=_P192_P, a=-3 % _P192_P,
+    b=0x64210519E59C80E70FA7E9AB72243049FEB8DEECC146B9B1,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFF99DEF836146BC9B1B4D22831,
+    gx=0x188DA80EB03090F67CBF20EB43A18800F4FF0AFD82FF1012,
+    gy=0x07192B95FFC8DA78631011ED6B24CDD573F977A11E794811,
+    fb=24, compress=False, low_s=False)
+
+CURVES = {c.name: c for c in (K256, P256, P384, SM2, P192)}
 BY_ID = {c.cid: c for c in CURVES.values()}
 
 

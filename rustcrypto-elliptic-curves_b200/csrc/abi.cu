@@ -59,6 +59,7 @@ struct PinBuf {
 };
 
 constexpr size_t CHUNK = (size_t)1 << 20;   // elements per pipelined chunk of the host entry points
+constexpr int NCURVE = 5;                   // K256, P256, P384, SM2, P192 (ecb200_curve)
 constexpr int NSLOT = 2;                    // double buffering: H2D / kernel / D2H of adjacent chunks overlap
 
 }  // namespace
@@ -68,10 +69,10 @@ struct ecb200_ctx {
     cudaStream_t stream = nullptr;           // compute stream of the host entry points
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[NSLOT] = {}, ev_done[NSLOT] = {}, ev_out[NSLOT] = {};
-    const CurveLaunch* cl[4] = {};
-    uint32_t* gtab[4] = {};                  // affine multiples 1..ngtab of G (internal limbs)
-    uint32_t* gentab[4] = {};                // fixed-base window tables (k256)
-    uint32_t* gbig[4] = {};                  // big fixed-base tables of the public-input fast path (built on first use)
+    const CurveLaunch* cl[NCURVE] = {};
+    uint32_t* gtab[NCURVE] = {};                  // affine multiples 1..ngtab of G (internal limbs)
+    uint32_t* gentab[NCURVE] = {};                // fixed-base window tables (k256)
+    uint32_t* gbig[NCURVE] = {};                  // big fixed-base tables of the public-input fast path (built on first use)
     int gw = 16;                             // window width of gbig (ECB200_GW = 4, 8 or 16)
     bool verify_v1 = false;                  // ECB200_VERIFY_V1=1: complete-formula verify kernel (A/B comparisons)
     bool use_wintab = true;                  // ECB200_WINTAB=0: per-thread Jacobian window tables on the primeorder curves (A/B comparisons)
@@ -105,7 +106,7 @@ int fail(ecb200_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
     } while (0)
 
 const CurveLaunch* curve_of(ecb200_ctx* c, int curve) {
-    if (!c || curve < 0 || curve > 3) return nullptr;
+    if (!c || curve < 0 || curve >= NCURVE) return nullptr;
     return c->cl[curve];
 }
 bool resolve_compress(const CurveLaunch* cl, uint32_t flags) {
@@ -141,16 +142,18 @@ int build_table(ecb200_ctx* c, const CurveLaunch* cl, const std::vector<uint8_t>
 }
 
 // generator coordinates as canonical bytes
-const char* GX[4] = {
+const char* GX[NCURVE] = {
     "79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798",
     "6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296",
     "AA87CA22BE8B05378EB1C71EF320AD746E1D3B628BA79B9859F741E082542A385502F25DBF55296C3A545E3872760AB7",
-    "32C4AE2C1F1981195F9904466A39C9948FE30BBFF2660BE1715A4589334C74C7"};
-const char* GY[4] = {
+    "32C4AE2C1F1981195F9904466A39C9948FE30BBFF2660BE1715A4589334C74C7",
+    "188DA80EB03090F67CBF20EB43A18800F4FF0AFD82FF1012"};
+const char* GY[NCURVE] = {
     "483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8",
     "4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5",
     "3617DE4A96262C6F5D9E98BF9292DC29F8F41DBD289A147CE9DA3113B5F0B8C00A60B1CE1D7E819D7A431D7C90EA0E5F",
-    "BC3736A2F4F6779C59BDCEE36B692153D0A9877CC62A474002DF32E52139F0A0"};
+    "BC3736A2F4F6779C59BDCEE36B692153D0A9877CC62A474002DF32E52139F0A0",
+    "07192B95FFC8DA78631011ED6B24CDD573F977A11E794811"};
 
 void hex_to(uint8_t* dst, const char* hex, int nbytes) {
     for (int i = 0; i < nbytes; i++) {
@@ -161,7 +164,7 @@ void hex_to(uint8_t* dst, const char* hex, int nbytes) {
 }
 
 int build_tables(ecb200_ctx* c) {
-    for (int id = 0; id < 4; id++) {
+    for (int id = 0; id < NCURVE; id++) {
         const CurveLaunch* cl = c->cl[id];
         const int FB = cl->FB;
         std::vector<uint8_t> gxy(2 * FB);
@@ -479,7 +482,7 @@ int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, co
 // ===============================================================================================
 extern "C" {
 
-size_t ecb200_field_bytes(int curve) { return curve == ECB200_P384 ? 48 : (curve >= 0 && curve <= 3 ? 32 : 0); }
+size_t ecb200_field_bytes(int curve) { return curve == ECB200_P384 ? 48 : curve == ECB200_P192 ? 24 : (curve >= 0 && curve <= 3 ? 32 : 0); }
 size_t ecb200_point_slot_bytes(int curve, uint32_t flags) {
     size_t fb = ecb200_field_bytes(curve);
     if (!fb) return 0;
@@ -500,6 +503,7 @@ int ecb200_init(int device, ecb200_ctx** out) {
     c->cl[1] = launch_p256();
     c->cl[2] = launch_p384();
     c->cl[3] = launch_sm2();
+    c->cl[4] = launch_p192();
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -524,7 +528,7 @@ void ecb200_destroy(ecb200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < NCURVE; i++) {
         if (c->gtab[i]) cudaFree(c->gtab[i]);
         if (c->gentab[i]) cudaFree(c->gentab[i]);
         if (c->gbig[i]) cudaFree(c->gbig[i]);

@@ -263,12 +263,22 @@ template <class C> struct Jac {
     // already hide the gather), the Jacobian loop compiled out of the kernel (see kernels.cuh body_verify_main).
     ECB_DEV static void load_entry(A& e, const u32* p) {
 #if defined(__CUDA_ARCH__)
-        const uint4* q = reinterpret_cast<const uint4*>(p);
-        ECB_UNROLL
-        for (int k = 0; k < L / 4; k++) {
-            uint4 a = __ldg(q + k), b = __ldg(q + L / 4 + k);
-            e.x.v[4 * k] = a.x; e.x.v[4 * k + 1] = a.y; e.x.v[4 * k + 2] = a.z; e.x.v[4 * k + 3] = a.w;
-            e.y.v[4 * k] = b.x; e.y.v[4 * k + 1] = b.y; e.y.v[4 * k + 2] = b.z; e.y.v[4 * k + 3] = b.w;
+        if constexpr (L % 4 == 0) {
+            const uint4* q = reinterpret_cast<const uint4*>(p);
+            ECB_UNROLL
+            for (int k = 0; k < L / 4; k++) {
+                uint4 a = __ldg(q + k), b = __ldg(q + L / 4 + k);
+                e.x.v[4 * k] = a.x; e.x.v[4 * k + 1] = a.y; e.x.v[4 * k + 2] = a.z; e.x.v[4 * k + 3] = a.w;
+                e.y.v[4 * k] = b.x; e.y.v[4 * k + 1] = b.y; e.y.v[4 * k + 2] = b.z; e.y.v[4 * k + 3] = b.w;
+            }
+        } else {   // L = 6: 24-byte coordinates, 8-byte aligned
+            const uint2* q = reinterpret_cast<const uint2*>(p);
+            ECB_UNROLL
+            for (int k = 0; k < L / 2; k++) {
+                uint2 a = __ldg(q + k), b = __ldg(q + L / 2 + k);
+                e.x.v[2 * k] = a.x; e.x.v[2 * k + 1] = a.y;
+                e.y.v[2 * k] = b.x; e.y.v[2 * k + 1] = b.y;
+            }
         }
 #else
         ECB_UNROLL

@@ -194,6 +194,7 @@ template <class C> struct Emu {
         case 1: Emu<CurveP256>::CALL; break;          \
         case 2: Emu<CurveP384>::CALL; break;          \
         case 3: Emu<CurveSM2>::CALL; break;           \
+        case 4: Emu<CurveP192>::CALL; break;          \
         default: return -1;                           \
     }
 

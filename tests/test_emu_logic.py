@@ -10,7 +10,7 @@ from oracle import ecoracle as o
 from tests import emu_lib
 
 lib = emu_lib.load()
-CUR = ["k256", "p256", "p384", "sm2"]
+CUR = ["k256", "p256", "p384", "sm2", "p192"]
 
 
 def field_op(c, which, op, a_list, b_list=None):

@@ -37,6 +37,12 @@ o = NS(
            n=0xFFFFFFFEFFFFFFFFFFFFFFFFFFFFFFFF7203DF6B21C6052B53BBF40939D54123,
            gx=0x32C4AE2C1F1981195F9904466A39C9948FE30BBFF2660BE1715A4589334C74C7,
            gy=0xBC3736A2F4F6779C59BDCEE36B692153D0A9877CC62A474002DF32E52139F0A0, fb=32, compress=False, low_s=False),
+    # p192/src/arithmetic.rs:36-55, p192/src/arithmetic/field.rs:43, p192/src/lib.rs:42 ("then p192 ... via the same template")
+    P192=NS(name="p192", cid=4, p=2**192 - 2**64 - 1, a=2**192 - 2**64 - 1 - 3,
+            b=0x64210519E59C80E70FA7E9AB72243049FEB8DEECC146B9B1,
+            n=0xFFFFFFFFFFFFFFFFFFFFFFFF99DEF836146BC9B1B4D22831,
+            gx=0x188DA80EB03090F67CBF20EB43A18800F4FF0AFD82FF1012,
+            gy=0x07192B95FFC8DA78631011ED6B24CDD573F977A11E794811, fb=24, compress=False, low_s=False),
     K256_LAMBDA=0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72,
     K256_BETA=0x7AE96A2B657C07106E64479EAC3434E99CF0497512F58995C1396C28719501EE,
     K256_MINUS_B1=0xE4437ED6010E88286F547FA90ABFE4C3,
@@ -92,14 +98,14 @@ def mont_params(name, m, L, comment):
 def main():
     out = []
     out.append("// GENERATED by tools/gen_consts.py — do not edit.\n#pragma once\n#include \"bigint.cuh\"\n#include \"fp_k256.cuh\"\n#include \"mont.cuh\"\n\nnamespace ecb {\n\n")
-    for c in (o.K256, o.P256, o.P384, o.SM2):
+    for c in (o.K256, o.P256, o.P384, o.SM2, o.P192):
         L = c.fb // 4
         up = c.name.upper()
         if c.name != "k256":
             out.append(mont_params(up + "P", c.p, L, "%s base field modulus" % c.name))
         out.append(mont_params(up + "N", c.n, L, "%s group order" % c.name))
     # curve descriptors
-    for c in (o.K256, o.P256, o.P384, o.SM2):
+    for c in (o.K256, o.P256, o.P384, o.SM2, o.P192):
         L = c.fb // 4
         up = c.name.upper()
         R = 1 << (32 * L)
