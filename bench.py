@@ -443,6 +443,14 @@ def other_configs(pkg, eng, dev, ts):
         ms = timed(lambda: eng.mul_var_dev(cname, n, d_p, None, d_k, o, None, 0, st))
         res.append({"config": f"5: {cname} P*k, 2^20 on 1 GPU, uncompressed SEC1", "value": round(n / ms * 1e3, 1), "unit": "scalar-mul/s",
                     "ms": round(ms, 4), "roofline_frac": roofline("mul_var", cname, n / ms * 1e3, ms, n, None)["frac"]})
+    # SURVEY §8 f4 tail: the primeorder template on 24-byte fields (P-192), verify at 2^20
+    n = 1 << 20
+    q, z, rs, exp = wl.make_verify_batch(wl.EngineBackend(eng, "p192"), "p192", n, 0xB2000008)
+    d_q, d_z, d_rs = torch.from_numpy(q).to(dev), torch.from_numpy(z).to(dev), torch.from_numpy(rs).to(dev)
+    d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: eng.ecdsa_verify_dev("p192", n, d_q, d_z, d_rs, d_ok, st))
+    res.append({"config": "f4: p192 ECDSA verify_prehash, 2^20 rows", "value": round(n / ms * 1e3, 1), "unit": "verifies/s", "ms": round(ms, 4),
+                "mask_ok": bool(np.array_equal(d_ok.cpu().numpy(), exp))})
     # SURVEY §8f rows at 2^20 (k256): compressed-key verify, recovery, BIP340 (inputs made by the engine's own signer)
     n = 1 << 20
     rng = np.random.default_rng(0xB2000007)

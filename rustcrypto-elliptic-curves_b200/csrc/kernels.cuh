@@ -749,7 +749,10 @@ template <class C> struct Bodies {
     // row is rejected (or answered with the identity) by the consumer, the table only has to stay invertible.  On these
     // curves (cofactor 1, prime order) no multiple 2Q..8Q of a valid Q is the identity, so no Z is zero.
     //   pts: n x 2FB bytes (x||y) or aff_limbs: n x 2L field-internal limbs;  zbuf: n x 7L words of scratch.
-    static constexpr int WT_EPT = 16;
+#ifndef ECB_WT_EPT
+#define ECB_WT_EPT 16
+#endif
+    static constexpr int WT_EPT = ECB_WT_EPT;
     ECB_DEV static void body_wintab(int tid, int nthreads, int n, const u8* pts, const u32* aff_limbs, u32* wtab, u32* zbuf) {
         E pref[WT_EPT];
         E run;

@@ -17,13 +17,14 @@ ORDERS = {
     1: 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551,
     2: 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFC7634D81F4372DDF581A0DB248B0A77AECEC196ACCC52973,
     3: 0xFFFFFFFEFFFFFFFFFFFFFFFFFFFFFFFF7203DF6B21C6052B53BBF40939D54123,
+    4: 0xFFFFFFFFFFFFFFFFFFFFFFFF99DEF836146BC9B1B4D22831,
 }
-LOW_S = {0: True, 1: False, 2: False, 3: False}
+LOW_S = {0: True, 1: False, 2: False, 3: False, 4: False}
 N_KEYS = 1 << 16
 
 
 def random_scalars(n: int, fb: int, seed: int) -> np.ndarray:
-    """n x fb uniform bytes with the top bit cleared (< 2^(8fb-1) < n for all four curves; never zero in practice)."""
+    """n x fb uniform bytes with the top bit cleared (< 2^(8fb-1) < n for every curve; never zero in practice)."""
     rng = np.random.default_rng(seed)
     a = rng.integers(0, 256, size=(n, fb), dtype=np.uint8)
     a[:, 0] &= 0x7F
