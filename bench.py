@@ -205,10 +205,15 @@ def importlib_pkg():
     return pkg
 
 
-def config_block(n_gpus, bounded=None):
-    c = {"workload": "BASELINE configs[2]: secp256k1 ECDSA verify_prehash, 2^22 signatures per GPU (2^16 distinct keys, 1/16 rows corrupted), "
-                     "sharded by index range, no collective", "rows_per_gpu": 1 << 22, "global_rows": (1 << 22) * n_gpus,
-         "curve": "k256", "l2_policy": "inputs (671 MB per step) larger than L2 (126 MB)", "parallelism": f"index-shard x{n_gpus}"}
+def config_block(n_gpus, bounded=None, curve="k256", log2_rows=22):
+    rows = 1 << log2_rows
+    if curve == "k256":
+        what = "BASELINE configs[2]: secp256k1 ECDSA verify_prehash, 2^%d signatures per GPU" % log2_rows
+    else:   # --curve p256: BASELINE configs[3] (P-256 verify via the primeorder path), same construction, same sharding
+        what = "BASELINE configs[3]: p256 ECDSA verify_prehash, 2^%d signatures per GPU" % log2_rows
+    c = {"workload": what + " (2^16 distinct keys, 1/16 rows corrupted), sharded by index range, no collective",
+         "rows_per_gpu": rows, "global_rows": rows * n_gpus, "curve": curve,
+         "l2_policy": "inputs (%d MB per step) larger than L2 (126 MB)" % (rows * 160 // 1000000), "parallelism": f"index-shard x{n_gpus}"}
     if bounded:
         c["bounded_sample"] = bounded
     return c
@@ -242,6 +247,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--log2-rows", type=int, default=22, help="rows per GPU (default 2^22 = the BASELINE config)")
+    ap.add_argument("--curve", default="k256", choices=["k256", "p256"], help="k256 = BASELINE configs[2] (the headline), p256 = configs[3]")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -265,11 +271,12 @@ def main():
     ts = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(ts)
     st = ts.cuda_stream
-    curve, n = "k256", 1 << args.log2_rows
+    curve, n = args.curve, 1 << args.log2_rows
     fb = 32
+    seed = 0xB2000003 if curve == "k256" else 0xB2000004
 
     # ---- inputs (synthetic, generated by the engine; not timed)
-    q, z, rs, exp = wl.make_verify_batch(wl.EngineBackend(eng, curve), curve, n, 0xB2000003 + 1000 * rank)
+    q, z, rs, exp = wl.make_verify_batch(wl.EngineBackend(eng, curve), curve, n, seed + 1000 * rank)
     d_q, d_z, d_rs = torch.from_numpy(q).to(dev), torch.from_numpy(z).to(dev), torch.from_numpy(rs).to(dev)
     d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
     h_ok = np.empty(n, np.uint8)
@@ -333,18 +340,19 @@ def main():
     e2e_value = n * world * args.steps / dt
 
     out = {
-        "metric": "secp256k1 ECDSA verify_prehash throughput", "value": round(value, 1), "unit": "verifies/s", "n_gpus": world,
+        "metric": ("secp256k1" if curve == "k256" else "P-256") + " ECDSA verify_prehash throughput", "value": round(value, 1), "unit": "verifies/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (8x32, IMAD.WIDE carry chains)", "data": "synthetic",
-        "config": config_block(world), "clocks": clocks, "gpu_launches": int(launches),
+        "config": config_block(world, None, curve, args.log2_rows), "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": round(e2e_value, 1), "unit": "verifies/s", "h2d_bytes_per_step": int(n * 5 * fb), "d2h_bytes_per_step": int(n),
                 "ms_per_step": round(dt / args.steps * 1e3, 3), "api": "ecb200_ecdsa_verify (host pointers to page-locked buffers; chunked H2D / compute / D2H overlap inside the call)"},
-        "roofline": roofline("verify", curve, value / world, ms_step, n, clocks.get("sm_mhz"), kernel_ms, "k_verify_main<CurveK256, VM_ECDSA>"),
+        "roofline": roofline("verify", curve, value / world, ms_step, n, clocks.get("sm_mhz"), kernel_ms,
+                             "k_verify_main<CurveK256, VM_ECDSA>" if curve == "k256" else "k_verify_main<CurveP256, VM_ECDSA> (+ k_wintab<CurveP256> before it)"),
     }
 
-    if rank == 0 and world == 1 and not args.no_others:
+    if rank == 0 and world == 1 and not args.no_others and curve == "k256":
         out["others"] = other_configs(pkg, eng, dev, ts)
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and curve == "k256":
         out["cpu_baseline"] = cpu_baseline(q, z, rs, exp)
     if rank == 0:
         emit(out)
