@@ -11,7 +11,7 @@
  *
  * Conventions
  *   - All integers cross the boundary as big-endian byte strings of FB bytes (FB = 32 for
- *     K256/P256/SM2, 48 for P384, 24 for P192), arrays of structures, one element after another — the layout of
+ *     K256/P256/SM2, 48 for P384, 24 for P192, 28 for P224), arrays of structures, one element after another — the layout of
  *     `FieldBytes` / `Scalar::to_bytes()` / `EncodedPoint` coordinates in the reference.
  *   - Caller owns every buffer; the library copies and never retains.  Host entry points take host
  *     pointers (pageable or pinned) and return when the results are in the output buffers.
@@ -42,7 +42,8 @@ typedef enum {
     ECB200_P256 = 1, /* NIST P-256 — p256/src/lib.rs:74-120 */
     ECB200_P384 = 2, /* NIST P-384 — p384/src/lib.rs:50-76 */
     ECB200_SM2 = 3,  /* SM2        — sm2/src/lib.rs:60-85 */
-    ECB200_P192 = 4  /* NIST P-192 — p192/src/lib.rs:42-66 (the primeorder template on 24-byte fields) */
+    ECB200_P192 = 4, /* NIST P-192 — p192/src/lib.rs:42-66 (the primeorder template on 24-byte fields) */
+    ECB200_P224 = 5  /* NIST P-224 — p224/src/lib.rs (28-byte fields, 7 limbs, p = 1 mod 4) */
 } ecb200_curve;
 
 typedef enum {
@@ -60,7 +61,7 @@ typedef enum {
                                        (k256 compressed, k256/src/lib.rs:108-111; others uncompressed) */
 #define ECB200_FLAG_PROJ 8u         /* input points are X||Y||Z homogeneous projective (x = X/Z), 3*FB bytes each */
 
-/* Field bytes of a curve (24, 32 or 48); 0 for an unknown curve. */
+/* Field bytes of a curve (24, 28, 32 or 48); 0 for an unknown curve. */
 size_t ecb200_field_bytes(int curve);
 /* Output slot size for one encoded point under `flags`: 1+FB (compressed) or 1+2*FB.
  * A slot holds the SEC1 encoding; the identity is an all-zero slot (tag 00), which is also

@@ -164,6 +164,15 @@ struct NistP192 {    // p192/src/lib.rs:42-66 (the primeorder templ
     static std::array<uint8_t, 24> order() { return detail::from_hex<24>("FFFFFFFFFFFFFFFFFFFFFFFF99DEF836146BC9B1B4D22831"); }
 };
 
+struct NistP224 {    // p224/src/lib.rs (28-byte fields)
+    static constexpr int ID = ECB200_P224;
+    static constexpr size_t FB = 28;
+    static constexpr bool COMPRESS_POINTS = false;
+    static constexpr bool LOW_S_ONLY = false;
+    static constexpr const char* NAME = "p224";
+    static std::array<uint8_t, 28> order() { return detail::from_hex<28>("FFFFFFFFFFFFFFFFFFFFFFFFFFFF16A2E0B8F03E13DD29455C5C2A3D"); }
+};
+
 template <class C> using FieldBytes = std::array<uint8_t, C::FB>;   // big-endian, `elliptic_curve::FieldBytes<C>`
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -735,6 +744,18 @@ using Signature = ecb200::ecdsa::Signature<NistP192>;
 using VerifyingKey = ecb200::ecdsa::VerifyingKey<NistP192>;
 }  // namespace ecdsa
 }  // namespace p192
+namespace p224 {
+using Curve = NistP224;
+using FieldBytes = ecb200::FieldBytes<NistP224>;
+using Scalar = ecb200::Scalar<NistP224>;
+using AffinePoint = ecb200::AffinePoint<NistP224>;
+using ProjectivePoint = ecb200::ProjectivePoint<NistP224>;
+using EncodedPoint = ecb200::EncodedPoint<NistP224>;
+namespace ecdsa {
+using Signature = ecb200::ecdsa::Signature<NistP224>;
+using VerifyingKey = ecb200::ecdsa::VerifyingKey<NistP224>;
+}  // namespace ecdsa
+}  // namespace p224
 namespace sm2 {
 using Curve = Sm2;
 using FieldBytes = ecb200::FieldBytes<Sm2>;

@@ -100,7 +100,18 @@ P192 = Curve(
     gy=0x07192B95FFC8DA78631011ED6B24CDD573F977A11E794811,
     fb=24, compress=False, low_s=False)
 
-CURVES = {c.name: c for c in (K256, P256, P384, SM2, P192)}
+# p224/src/arithmetic.rs (a = -3, b, generator), p224/src/arithmetic/field.rs (modulus), p224/src/lib.rs (order)
+_P224_P = 2**224 - 2**96 + 1
+P224 = Curve(
+    "p224", 5,
+    p=_P224_P, a=-3 % _P224_P,
+    b=0xB4050A850C04B3ABF54132565044B0B7D7BFD8BA270B39432355FFB4,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFF16A2E0B8F03E13DD29455C5C2A3D,
+    gx=0xB70E0CBD6BB4BF7F321390B94A03C1D356C21122343280D6115C1D21,
+    gy=0xBD376388B5F723FB4C22DFE6CD4375A05A07476444D5819985007E34,
+    fb=28, compress=False, low_s=False)
+
+CURVES = {c.name: c for c in (K256, P256, P384, SM2, P192, P224)}
 BY_ID = {c.cid: c for c in CURVES.values()}
 
 
@@ -116,10 +127,33 @@ def inv_mod(x: int, m: int) -> int:
 
 
 def sqrt_mod(c: Curve, v: int) -> Optional[int]:
-    """sqrt for p = 3 (mod 4) (all four curves): k256 field.rs:220-255, p256 field.rs:385-411,
-    p384 field.rs:95-117, sm2 field.rs `sqrt`."""
-    r = pow(v, (c.p + 1) // 4, c.p)
-    return r if r * r % c.p == v % c.p else None
+    """sqrt for p = 3 (mod 4): k256 field.rs:220-255, p256 field.rs:385-411, p384 field.rs:95-117, sm2 field.rs `sqrt`,
+    p192 field.rs:103-108; Tonelli-Shanks for p = 1 (mod 4) (P-224, p224/src/arithmetic/field.rs:103-233).  Either root
+    may come back; callers select by parity / size."""
+    p = c.p
+    v %= p
+    if p % 4 == 3:
+        r = pow(v, (p + 1) // 4, p)
+        return r if r * r % p == v else None
+    if v == 0:
+        return 0
+    if pow(v, (p - 1) // 2, p) != 1:
+        return None
+    s, t = 0, p - 1
+    while t % 2 == 0:
+        s, t = s + 1, t // 2
+    g = 2
+    while pow(g, (p - 1) // 2, p) != p - 1:
+        g += 1
+    z, x, b, m = pow(g, t, p), pow(v, (t + 1) // 2, p), pow(v, t, p), s
+    while b != 1:
+        k, t2 = 0, b
+        while t2 != 1:
+            t2, k = t2 * t2 % p, k + 1
+        zz = pow(z, 1 << (m - k - 1), p)
+        x, z = x * zz % p, zz * zz % p
+        b, m = b * z % p, k
+    return x
 
 
 def on_curve(c: Curve, x: int, y: int) -> bool:

@@ -18,7 +18,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 from . import ecoracle as o
 
-NID = {"k256": 714, "p256": 415, "p384": 715, "sm2": 1172, "p192": 409}   # 409 = NID_X9_62_prime192v1
+NID = {"k256": 714, "p256": 415, "p384": 715, "sm2": 1172, "p192": 409, "p224": 713}   # 409 = NID_X9_62_prime192v1, 713 = NID_secp224r1
 _lib = None
 
 

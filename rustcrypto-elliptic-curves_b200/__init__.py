@@ -29,8 +29,8 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ECB200_LIB") or os.path.join(HERE, "libecb200.so")
 
-K256, P256, P384, SM2, P192 = 0, 1, 2, 3, 4
-CURVE_IDS = {"k256": K256, "secp256k1": K256, "p256": P256, "p384": P384, "sm2": SM2, "p192": P192}
+K256, P256, P384, SM2, P192, P224 = 0, 1, 2, 3, 4, 5
+CURVE_IDS = {"k256": K256, "secp256k1": K256, "p256": P256, "p384": P384, "sm2": SM2, "p192": P192, "p224": P224}
 
 FLAG_CT = 1
 FLAG_COMPRESSED = 2
@@ -115,7 +115,7 @@ def curve_id(curve) -> int:
 
 def field_bytes(curve) -> int:
     cid = curve_id(curve)
-    return 48 if cid == P384 else 24 if cid == P192 else 32
+    return 48 if cid == P384 else 24 if cid == P192 else 28 if cid == P224 else 32
 
 
 def slot_bytes(curve, flags: int = 0) -> int:

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libecb200.so")
-UNITS = ["abi", "curve_k256", "curve_p256", "curve_p384", "curve_sm2", "curve_p192"]
+UNITS = ["abi", "curve_k256", "curve_p256", "curve_p384", "curve_sm2", "curve_p192", "curve_p224"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

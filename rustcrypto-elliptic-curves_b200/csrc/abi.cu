@@ -59,7 +59,7 @@ struct PinBuf {
 };
 
 constexpr size_t CHUNK = (size_t)1 << 20;   // elements per pipelined chunk of the host entry points
-constexpr int NCURVE = 5;                   // K256, P256, P384, SM2, P192 (ecb200_curve)
+constexpr int NCURVE = 6;                   // K256, P256, P384, SM2, P192, P224 (ecb200_curve)
 constexpr int NSLOT = 2;                    // double buffering: H2D / kernel / D2H of adjacent chunks overlap
 
 }  // namespace
@@ -147,13 +147,15 @@ const char* GX[NCURVE] = {
     "6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296",
     "AA87CA22BE8B05378EB1C71EF320AD746E1D3B628BA79B9859F741E082542A385502F25DBF55296C3A545E3872760AB7",
     "32C4AE2C1F1981195F9904466A39C9948FE30BBFF2660BE1715A4589334C74C7",
-    "188DA80EB03090F67CBF20EB43A18800F4FF0AFD82FF1012"};
+    "188DA80EB03090F67CBF20EB43A18800F4FF0AFD82FF1012",
+    "B70E0CBD6BB4BF7F321390B94A03C1D356C21122343280D6115C1D21"};
 const char* GY[NCURVE] = {
     "483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8",
     "4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5",
     "3617DE4A96262C6F5D9E98BF9292DC29F8F41DBD289A147CE9DA3113B5F0B8C00A60B1CE1D7E819D7A431D7C90EA0E5F",
     "BC3736A2F4F6779C59BDCEE36B692153D0A9877CC62A474002DF32E52139F0A0",
-    "07192B95FFC8DA78631011ED6B24CDD573F977A11E794811"};
+    "07192B95FFC8DA78631011ED6B24CDD573F977A11E794811",
+    "BD376388B5F723FB4C22DFE6CD4375A05A07476444D5819985007E34"};
 
 void hex_to(uint8_t* dst, const char* hex, int nbytes) {
     for (int i = 0; i < nbytes; i++) {
@@ -482,7 +484,9 @@ int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, co
 // ===============================================================================================
 extern "C" {
 
-size_t ecb200_field_bytes(int curve) { return curve == ECB200_P384 ? 48 : curve == ECB200_P192 ? 24 : (curve >= 0 && curve <= 3 ? 32 : 0); }
+size_t ecb200_field_bytes(int curve) {
+    return curve == ECB200_P384 ? 48 : curve == ECB200_P192 ? 24 : curve == ECB200_P224 ? 28 : (curve >= 0 && curve <= 3 ? 32 : 0);
+}
 size_t ecb200_point_slot_bytes(int curve, uint32_t flags) {
     size_t fb = ecb200_field_bytes(curve);
     if (!fb) return 0;
@@ -504,6 +508,7 @@ int ecb200_init(int device, ecb200_ctx** out) {
     c->cl[2] = launch_p384();
     c->cl[3] = launch_sm2();
     c->cl[4] = launch_p192();
+    c->cl[5] = launch_p224();
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) == cudaSuccess;

@@ -130,8 +130,29 @@ template <int L> ECB_DEV void cmov_n(u32* r, const u32* a, u32 mask) {
 #else
 #define ECB_ASSERT_NO_CARRY() do { } while (0)
 #endif
+// Odd limb counts (P-224, L = 7): plain column-wise schoolbook with a three-word accumulator.  The aligned-pair scheme
+// below needs an even L; this one is about 30 % slower per product and only serves the curve that needs it.
+template <int L> ECB_DEV void mul_wide_columns(u32* r, const u32* a, const u32* b) {
+    u64 lo = 0;        // low 64 bits of the column sum
+    u32 hi = 0;        // overflow beyond 2^64
+    ECB_UNROLL
+    for (int k = 0; k < 2 * L - 1; k++) {
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) {
+            const int j = k - i;
+            if (j < 0 || j >= L) continue;
+            const u64 pr = (u64)a[i] * b[j];
+            lo += pr;
+            hi += lo < pr ? 1u : 0u;
+        }
+        r[k] = (u32)lo;
+        lo = (lo >> 32) | ((u64)hi << 32);
+        hi = 0;
+    }
+    r[2 * L - 1] = (u32)lo;
+}
 template <int L> ECB_DEV void mul_wide(u32* r, const u32* a, const u32* b) {
-    static_assert(L % 2 == 0, "even limb counts only");
+    if constexpr (L % 2 != 0) { mul_wide_columns<L>(r, a, b); return; }
     u32 e[2 * L], o[2 * L];
     ECB_UNROLL
     for (int i = 0; i < 2 * L; i++) { e[i] = 0; o[i] = 0; }
@@ -175,7 +196,7 @@ template <int L> ECB_DEV void mul_wide(u32* r, const u32* a, const u32* b) {
 
 // r[0..2L) = a^2: off-diagonal products once (same even/odd scheme), doubled, plus the diagonal.
 template <int L> ECB_DEV void sqr_wide(u32* r, const u32* a) {
-    static_assert(L % 2 == 0, "even limb counts only");
+    if constexpr (L % 2 != 0) { mul_wide_columns<L>(r, a, a); return; }
     u32 e[2 * L], o[2 * L];
     ECB_UNROLL
     for (int i = 0; i < 2 * L; i++) { e[i] = 0; o[i] = 0; }

@@ -271,6 +271,9 @@ template <class C> struct Jac {
                 e.x.v[4 * k] = a.x; e.x.v[4 * k + 1] = a.y; e.x.v[4 * k + 2] = a.z; e.x.v[4 * k + 3] = a.w;
                 e.y.v[4 * k] = b.x; e.y.v[4 * k + 1] = b.y; e.y.v[4 * k + 2] = b.z; e.y.v[4 * k + 3] = b.w;
             }
+        } else if constexpr (L % 2 != 0) {   // L = 7: 28-byte coordinates, word loads
+            ECB_UNROLL
+            for (int l = 0; l < L; l++) { e.x.v[l] = __ldg(p + l); e.y.v[l] = __ldg(p + L + l); }
         } else {   // L = 6: 24-byte coordinates, 8-byte aligned
             const uint2* q = reinterpret_cast<const uint2*>(p);
             ECB_UNROLL

@@ -51,6 +51,7 @@ const CurveLaunch* launch_p256();
 const CurveLaunch* launch_p384();
 const CurveLaunch* launch_sm2();
 const CurveLaunch* launch_p192();
+const CurveLaunch* launch_p224();
 
 // incremented by every kernel launch issued through the launchers (host side, not thread safe)
 extern uint64_t g_launch_count;

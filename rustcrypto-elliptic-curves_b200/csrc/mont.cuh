@@ -128,7 +128,31 @@ template <class P> struct Mont {
         if constexpr (P::SPARSE) redc_sparse(r, t);
         else redc_generic(r, t);
     }
+    // odd limb counts (P-224): row by row with a 64-bit running carry
+    ECB_DEV static void redc_rows(u32* r, u32* t) {
+        u32 top = 0;
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) {
+            const u32 m = t[i] * P::n0;
+            u64 c = 0;
+            ECB_UNROLL
+            for (int j = 0; j < L; j++) {
+                c += (u64)m * P::p(j) + t[i + j];
+                t[i + j] = (u32)c;
+                c >>= 32;
+            }
+            ECB_UNROLL
+            for (int j = i + L; j < 2 * L; j++) {
+                c += t[j];
+                t[j] = (u32)c;
+                c >>= 32;
+            }
+            top += (u32)c;
+        }
+        final_sub(r, t + L, top);
+    }
     ECB_DEV static void redc_generic(u32* r, u32* t) {
+        if constexpr (L % 2 != 0) { redc_rows(r, t); return; }
         // Row i adds m_i * p at limb i as two aligned-pair carry chains (even j, odd j).  The chain
         // carry-outs (weight i+L and i+L+1) never feed a later m_i, so they are collected in cy[]
         // and added once at the end instead of being rippled to the top in every row.
@@ -328,8 +352,44 @@ template <class P> struct Mont {
         for (int i = 1; i < L; i++) e[i] = subc_cc(P::p(i), 0u);
         pow_limbs(r, a, e);
     }
+    // p = 1 (mod 4) (P-224: p - 1 = 2^96 (2^128 - 1)): Tonelli-Shanks, variable time - square roots are only taken of public
+    // data (point decompression).  The reference runs the constant-time form of the same algorithm
+    // (p224/src/arithmetic/field.rs:103-233, S = 96, ROOT_OF_UNITY = 22^t); the root it returns is +-this one and the caller
+    // picks the sign by parity, so the decoded point is the same.  A non-residue returns garbage (callers check r^2 == a).
+    template <class PP = P> ECB_DEV static void sqrt_tonelli_shanks(E& r, const E& a) {
+        if (is_zero(a)) { r = a; return; }
+        u32 e[L];
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) e[i] = PP::ts_half_t(i);     // (t - 1) / 2, t = (p - 1) / 2^S odd
+        E w, x, b, z;
+        pow_limbs(w, a, e);
+        mul(x, a, w);                                            // a^((t+1)/2)
+        mul(b, x, w);                                            // a^t
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) z.v[i] = PP::ts_root(i);     // g^t for a non-residue g: order 2^S
+        int v = PP::TS_S;
+        E one;
+        set_one(one);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        while (!eq(b, one)) {
+            int k = 0;
+            E t2 = b;
+            while (k < v && !eq(t2, one)) { sqr(t2, t2); k++; }  // least k with b^(2^k) = 1
+            if (k >= v) { r = x; return; }                       // no such k below v: a is not a square
+            E zz = z;
+            for (int i = 0; i < v - k - 1; i++) sqr(zz, zz);
+            mul(x, x, zz);
+            sqr(z, zz);
+            mul(b, b, z);
+            v = k;
+        }
+        r = x;
+    }
     // a^((p+1)/4) for p = 3 mod 4 (p256 field.rs:385-411, p384 field.rs:95-117, sm2 field.rs sqrt)
     ECB_DEV static void sqrt_candidate(E& r, const E& a) {
+        if constexpr (P::SQRT_TS) { sqrt_tonelli_shanks(r, a); return; }
         u32 e[L];
         e[0] = add_cc(P::p(0), 1u);
         ECB_UNROLL

@@ -18,8 +18,9 @@ ORDERS = {
     2: 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFC7634D81F4372DDF581A0DB248B0A77AECEC196ACCC52973,
     3: 0xFFFFFFFEFFFFFFFFFFFFFFFFFFFFFFFF7203DF6B21C6052B53BBF40939D54123,
     4: 0xFFFFFFFFFFFFFFFFFFFFFFFF99DEF836146BC9B1B4D22831,
+    5: 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFF16A2E0B8F03E13DD29455C5C2A3D,
 }
-LOW_S = {0: True, 1: False, 2: False, 3: False, 4: False}
+LOW_S = {0: True, 1: False, 2: False, 3: False, 4: False, 5: False}
 N_KEYS = 1 << 16
 
 

@@ -122,6 +122,7 @@ static int host_only() {
     host_logic<NistP384>();
     host_logic<Sm2>();
     host_logic<NistP192>();
+    host_logic<NistP224>();
     // shard_range: contiguous, complete, floor boundaries
     for (size_t n : {0ul, 1ul, 7ul, 4194304ul, 4194305ul})
         for (size_t g : {1ul, 2ul, 3ul, 8ul}) {
@@ -398,6 +399,7 @@ int main(int argc, char** argv) {
         curve_tests<NistP384>(eng, cs);
         curve_tests<Sm2>(eng, cs);
         curve_tests<NistP192>(eng, cs);
+        curve_tests<NistP224>(eng, cs);
         schnorr_tests(eng, cs);
         sm2dsa_tests(eng, cs);
         CHECK(eng.launch_count() > 0, "kernels were launched");

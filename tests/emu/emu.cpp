@@ -195,6 +195,7 @@ template <class C> struct Emu {
         case 2: Emu<CurveP384>::CALL; break;          \
         case 3: Emu<CurveSM2>::CALL; break;           \
         case 4: Emu<CurveP192>::CALL; break;          \
+        case 5: Emu<CurveP224>::CALL; break;          \
         default: return -1;                           \
     }
 

@@ -137,7 +137,7 @@ def keccak256(data: bytes) -> bytes:
 
 
 def main():
-    group = {c: group_vectors(c) for c in ("k256", "p256", "p384", "p192")}
+    group = {c: group_vectors(c) for c in ("k256", "p256", "p384", "p192", "p224")}
     field = {c: field_vectors(c) for c in ("k256", "p256")}
     # risc0 8x32 KATs: k256/src/arithmetic/field/field_8x32_risc0.rs:225-303
     t = read("k256/src/arithmetic/field/field_8x32_risc0.rs")
@@ -147,11 +147,11 @@ def main():
     assert len(hx) == len(names), len(hx)
     field["k256_risc0_8x32"] = {"source": "k256/src/arithmetic/field/field_8x32_risc0.rs:225-303",
                                 **dict(zip(names, hx))}
-    ecdsa = {c: ecdsa_vectors(c) for c in ("k256", "p256", "p384", "p192")}
+    ecdsa = {c: ecdsa_vectors(c) for c in ("k256", "p256", "p384", "p192", "p224")}
     wyche = {c: {"source": f"{c}/src/test_vectors/data/wycheproof.blb",
-                 "hash": "sha384" if c == "p384" else "sha256",
+                 "hash": "sha384" if c == "p384" else "sha224" if c == "p224" else "sha256",
                  "rows": blobby_rows(f"{c}/src/test_vectors/data/wycheproof.blb")}
-             for c in ("k256", "p256", "p384")}
+             for c in ("k256", "p256", "p384", "p224")}
 
     misc = {}
     # p256 prehash-longer-than-field accept vector: p256/src/ecdsa.rs:137-169

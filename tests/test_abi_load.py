@@ -32,7 +32,7 @@ def test_library_exports_every_symbol():
 
 def test_size_helpers_need_no_gpu():
     lib = ecb200.load_library()
-    assert [lib.ecb200_field_bytes(c) for c in range(6)] == [32, 32, 48, 32, 24, 0]
+    assert [lib.ecb200_field_bytes(c) for c in range(7)] == [32, 32, 48, 32, 24, 28, 0]
     assert lib.ecb200_point_slot_bytes(0, 0) == 33 and lib.ecb200_point_slot_bytes(1, 0) == 65
     assert lib.ecb200_point_slot_bytes(2, 0) == 97 and lib.ecb200_point_slot_bytes(2, ecb200.FLAG_COMPRESSED) == 49
     assert ecb200.slot_bytes("k256") == 33 and ecb200.slot_bytes("sm2") == 65

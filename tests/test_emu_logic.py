@@ -10,7 +10,7 @@ from oracle import ecoracle as o
 from tests import emu_lib
 
 lib = emu_lib.load()
-CUR = ["k256", "p256", "p384", "sm2", "p192"]
+CUR = ["k256", "p256", "p384", "sm2", "p192", "p224"]
 
 
 def field_op(c, which, op, a_list, b_list=None):
@@ -191,7 +191,7 @@ def run_verify(c, rows):
     return list(ok2), o.batch_verify(c, q, z, rs)
 
 
-@pytest.mark.parametrize("cname", ["k256", "p256", "p384"])
+@pytest.mark.parametrize("cname", ["k256", "p256", "p384", "p224"])
 def test_verify_wycheproof_sample(golden, cname):
     c = o.curve(cname)
     blob = golden["wycheproof"][cname]

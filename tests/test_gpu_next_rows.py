@@ -9,7 +9,7 @@ from oracle import ecoracle as o
 from tests import nextrows
 
 pytestmark = pytest.mark.gpu
-CUR = ["k256", "p256", "p384", "sm2", "p192"]
+CUR = ["k256", "p256", "p384", "sm2", "p192", "p224"]
 
 
 @pytest.fixture(scope="module")

@@ -32,7 +32,7 @@ def hx(v, n):
 
 def write_fixture(path, golden):
     lines = []
-    for cname in ("k256", "p256", "p384", "sm2", "p192"):
+    for cname in ("k256", "p256", "p384", "sm2", "p192", "p224"):
         c = o.curve(cname)
         fb = c.fb
         # group vectors (sm2: the reference has none; the oracle, pinned by libcrypto in the CPU tier, supplies them)
@@ -137,7 +137,7 @@ def test_fixture_builder(tmp_path, golden):
     for line in p.read_text().splitlines()[1:]:
         k, c = line.split()[:2]
         kinds[(k, c)] = kinds.get((k, c), 0) + 1
-    for c in ("k256", "p256", "p384", "sm2", "p192"):
+    for c in ("k256", "p256", "p384", "sm2", "p192", "p224"):
         for k in ("add", "mul", "decode", "verify", "sign"):
             assert kinds.get((k, c), 0) >= 4, (k, c)
     assert kinds[("verify", "k256")] > 200 and kinds[("verify", "p256")] > 200 and kinds[("verify", "p384")] > 200
@@ -154,5 +154,5 @@ def test_host_mirror_on_gpu(tmp_path, golden):
     out = subprocess.run([exe, fx], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "host mirror ok" in out.stdout
-    for c in ("k256", "p256", "p384", "sm2", "p192"):
+    for c in ("k256", "p256", "p384", "sm2", "p192", "p224"):
         assert "%s: ok" % c in out.stdout

@@ -11,12 +11,12 @@ from oracle import ecoracle as o
 lc = pytest.importorskip("oracle.libcrypto_ref")
 try:
     lc.lib()
-    for _c in ("k256", "p256", "p384", "sm2", "p192"):
+    for _c in ("k256", "p256", "p384", "sm2", "p192", "p224"):
         lc.group(_c)
 except Exception as e:  # pragma: no cover
     pytest.skip("libcrypto unusable: %s" % e, allow_module_level=True)
 
-CUR = ["k256", "p256", "p384", "sm2", "p192"]
+CUR = ["k256", "p256", "p384", "sm2", "p192", "p224"]
 
 
 def be(v, n):

@@ -43,6 +43,12 @@ o = NS(
             n=0xFFFFFFFFFFFFFFFFFFFFFFFF99DEF836146BC9B1B4D22831,
             gx=0x188DA80EB03090F67CBF20EB43A18800F4FF0AFD82FF1012,
             gy=0x07192B95FFC8DA78631011ED6B24CDD573F977A11E794811, fb=24, compress=False, low_s=False),
+    # p224/src/arithmetic.rs (a = -3, b, generator), p224/src/arithmetic/field.rs (modulus, S = 96, generator 22), p224/src/lib.rs (order)
+    P224=NS(name="p224", cid=5, p=2**224 - 2**96 + 1, a=2**224 - 2**96 + 1 - 3,
+            b=0xB4050A850C04B3ABF54132565044B0B7D7BFD8BA270B39432355FFB4,
+            n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFF16A2E0B8F03E13DD29455C5C2A3D,
+            gx=0xB70E0CBD6BB4BF7F321390B94A03C1D356C21122343280D6115C1D21,
+            gy=0xBD376388B5F723FB4C22DFE6CD4375A05A07476444D5819985007E34, fb=28, compress=False, low_s=False),
     K256_LAMBDA=0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72,
     K256_BETA=0x7AE96A2B657C07106E64479EAC3434E99CF0497512F58995C1396C28719501EE,
     K256_MINUS_B1=0xE4437ED6010E88286F547FA90ABFE4C3,
@@ -74,7 +80,14 @@ def sparse_terms(m, L):
     return None
 
 
-def mont_params(name, m, L, comment):
+def nonresidue(m):
+    g = 2
+    while pow(g, (m - 1) // 2, m) != m - 1:
+        g += 1
+    return g
+
+
+def mont_params(name, m, L, comment, base_field=False):
     R = 1 << (32 * L)
     n0 = (-pow(m, -1, 1 << 32)) % (1 << 32)
     s = "// %s\nstruct %s {\n    static constexpr int L = %d;\n    static constexpr u32 n0 = 0x%08Xu;\n" % (comment, name, L, n0)
@@ -91,6 +104,16 @@ def mont_params(name, m, L, comment):
         s += "    ECB_HD static constexpr int ts(int k) { constexpr int t[%d] = {%s}; return t[k]; }\n" % (len(terms), ", ".join(str(sg) for _, sg in terms))
     else:
         s += "    static constexpr bool SPARSE = false;\n"
+    if base_field and m % 4 == 1:
+        # Tonelli-Shanks constants: m - 1 = 2^S * t, t odd; root = g^t in Montgomery form for the smallest non-residue g
+        S, t = 0, m - 1
+        while t % 2 == 0:
+            S, t = S + 1, t // 2
+        s += "    // p = 1 (mod 4): square roots by Tonelli-Shanks, p - 1 = 2^%d * t\n" % S
+        s += "    static constexpr bool SQRT_TS = true;\n    static constexpr int TS_S = %d;\n" % S
+        s += arr("ts_half_t", (t - 1) // 2, L) + arr("ts_root", pow(nonresidue(m), t, m) * R % m, L)
+    else:
+        s += "    static constexpr bool SQRT_TS = false;\n"
     s += "};\n\n"
     return s
 
@@ -98,14 +121,14 @@ def mont_params(name, m, L, comment):
 def main():
     out = []
     out.append("// GENERATED by tools/gen_consts.py — do not edit.\n#pragma once\n#include \"bigint.cuh\"\n#include \"fp_k256.cuh\"\n#include \"mont.cuh\"\n\nnamespace ecb {\n\n")
-    for c in (o.K256, o.P256, o.P384, o.SM2, o.P192):
+    for c in (o.K256, o.P256, o.P384, o.SM2, o.P192, o.P224):
         L = c.fb // 4
         up = c.name.upper()
         if c.name != "k256":
-            out.append(mont_params(up + "P", c.p, L, "%s base field modulus" % c.name))
+            out.append(mont_params(up + "P", c.p, L, "%s base field modulus" % c.name, base_field=True))
         out.append(mont_params(up + "N", c.n, L, "%s group order" % c.name))
     # curve descriptors
-    for c in (o.K256, o.P256, o.P384, o.SM2, o.P192):
+    for c in (o.K256, o.P256, o.P384, o.SM2, o.P192, o.P224):
         L = c.fb // 4
         up = c.name.upper()
         R = 1 << (32 * L)
