@@ -151,8 +151,37 @@ template <int L> ECB_DEV void mul_wide_columns(u32* r, const u32* a, const u32* 
     }
     r[2 * L - 1] = (u32)lo;
 }
+template <int L> ECB_DEV void mul_wide(u32* r, const u32* a, const u32* b);
+template <int L> ECB_DEV void sqr_wide(u32* r, const u32* a);
+// odd L on the device: zero-extend to L + 1 limbs and run the aligned-pair multiplier (the products with the zero limb
+// cost an instruction each but no carry logic); the column-wise form above stays as the host-emulation cross-check
+template <int L> ECB_DEV void mul_wide_padded(u32* r, const u32* a, const u32* b) {
+    u32 aa[L + 1], bb[L + 1], rr[2 * L + 2];
+    ECB_UNROLL
+    for (int i = 0; i < L; i++) { aa[i] = a[i]; bb[i] = b[i]; }
+    aa[L] = 0; bb[L] = 0;
+    mul_wide<L + 1>(rr, aa, bb);
+    ECB_UNROLL
+    for (int i = 0; i < 2 * L; i++) r[i] = rr[i];
+}
+template <int L> ECB_DEV void sqr_wide_padded(u32* r, const u32* a) {
+    u32 aa[L + 1], rr[2 * L + 2];
+    ECB_UNROLL
+    for (int i = 0; i < L; i++) aa[i] = a[i];
+    aa[L] = 0;
+    sqr_wide<L + 1>(rr, aa);
+    ECB_UNROLL
+    for (int i = 0; i < 2 * L; i++) r[i] = rr[i];
+}
 template <int L> ECB_DEV void mul_wide(u32* r, const u32* a, const u32* b) {
-    if constexpr (L % 2 != 0) { mul_wide_columns<L>(r, a, b); return; }
+    if constexpr (L % 2 != 0) {
+#if defined(__CUDA_ARCH__)
+        mul_wide_padded<L>(r, a, b);
+#else
+        mul_wide_columns<L>(r, a, b);
+#endif
+        return;
+    }
     u32 e[2 * L], o[2 * L];
     ECB_UNROLL
     for (int i = 0; i < 2 * L; i++) { e[i] = 0; o[i] = 0; }
@@ -196,7 +225,14 @@ template <int L> ECB_DEV void mul_wide(u32* r, const u32* a, const u32* b) {
 
 // r[0..2L) = a^2: off-diagonal products once (same even/odd scheme), doubled, plus the diagonal.
 template <int L> ECB_DEV void sqr_wide(u32* r, const u32* a) {
-    if constexpr (L % 2 != 0) { mul_wide_columns<L>(r, a, a); return; }
+    if constexpr (L % 2 != 0) {
+#if defined(__CUDA_ARCH__)
+        sqr_wide_padded<L>(r, a);
+#else
+        mul_wide_columns<L>(r, a, a);
+#endif
+        return;
+    }
     u32 e[2 * L], o[2 * L];
     ECB_UNROLL
     for (int i = 0; i < 2 * L; i++) { e[i] = 0; o[i] = 0; }

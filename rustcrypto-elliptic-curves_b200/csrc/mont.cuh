@@ -128,9 +128,10 @@ template <class P> struct Mont {
         if constexpr (P::SPARSE) redc_sparse(r, t);
         else redc_generic(r, t);
     }
-    // odd limb counts (P-224): row by row with a 64-bit running carry
+    // odd limb counts (P-224): row by row with a 64-bit running carry; a row's carry-out (weight L + i) never feeds a later
+    // multiplier m_i, so it is parked in cy[] and added once at the end
     ECB_DEV static void redc_rows(u32* r, u32* t) {
-        u32 top = 0;
+        u32 cy[L];
         ECB_UNROLL
         for (int i = 0; i < L; i++) {
             const u32 m = t[i] * P::n0;
@@ -141,15 +142,14 @@ template <class P> struct Mont {
                 t[i + j] = (u32)c;
                 c >>= 32;
             }
-            ECB_UNROLL
-            for (int j = i + L; j < 2 * L; j++) {
-                c += t[j];
-                t[j] = (u32)c;
-                c >>= 32;
-            }
-            top += (u32)c;
+            cy[i] = (u32)c;
         }
-        final_sub(r, t + L, top);
+        u32 v[L];
+        v[0] = add_cc(t[L], cy[0]);
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) v[i] = addc_cc(t[L + i], cy[i]);
+        const u32 top = addc(0u, 0u);
+        final_sub(r, v, top);
     }
     ECB_DEV static void redc_generic(u32* r, u32* t) {
         if constexpr (L % 2 != 0) { redc_rows(r, t); return; }
