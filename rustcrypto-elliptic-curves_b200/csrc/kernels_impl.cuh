@@ -29,8 +29,14 @@ template <class C> constexpr int ct_min_ctas() { return C::L > 8 ? 3 : ECB_CT_MI
 template <class C> __global__ void __launch_bounds__(BLK) k_field_op(int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
     Bodies<C>::body_field_op(blockIdx.x * BLK + threadIdx.x, n, which, op, a, b, out, ok);
 }
+// Curve descriptor with the two-call squarer (mont.cuh SQSPLIT), for the kernels in which ptxas compiles the one-function
+// squarer of P-384 with spilled carry predicates: the complete-formula (secret-scalar) scalar multiplication.
+template <class C> struct SplitSqr : C { typedef Mont<typename C::F::Params, true> F; };
+template <class C> struct CtCurve { typedef C type; };
+template <> struct CtCurve<CurveP384> { typedef SplitSqr<CurveP384> type; };
+
 template <class C, bool CT> __global__ void __launch_bounds__(BLK, ct_min_ctas<C>()) k_mul_var(int n, u32 flags, const u8* pts, const u8* inf, const u8* k, u32* proj, u8* invalid) {
-    Bodies<C>::template body_mul_var<CT>(blockIdx.x * BLK + threadIdx.x, n, flags, pts, inf, k, proj, invalid);
+    Bodies<typename CtCurve<C>::type>::template body_mul_var<CT>(blockIdx.x * BLK + threadIdx.x, n, flags, pts, inf, k, proj, invalid);
 }
 template <class C, bool CT> __global__ void __launch_bounds__(BLK) k_mul_gen(int n, const u8* k, const u32* tab, u32* proj) {
     Bodies<C>::template body_mul_gen<CT>(blockIdx.x * BLK + threadIdx.x, n, k, tab, proj);

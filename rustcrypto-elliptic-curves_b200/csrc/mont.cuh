@@ -19,7 +19,9 @@ namespace ecb {
 template <class P, bool S = P::SPARSE> struct SparseColumnwise { static constexpr bool value = false; };
 template <class P> struct SparseColumnwise<P, true> { static constexpr bool value = !P::ASC_OK; };
 
-template <class P> struct Mont {
+// SQSPLIT: the squaring is issued as two calls (product, reduction) like the multiplication of the column-wise curves.
+// A per-kernel choice (kernels_impl.cuh SplitSqr): see the note at sqr().
+template <class P, bool SQSPLIT = false> struct Mont {
     static constexpr int L = P::L;
     typedef Fe<P::L> E;
     static constexpr bool MONT = true;
@@ -214,10 +216,16 @@ template <class P> struct Mont {
         if constexpr (SPLIT) { Wide t = mulw_fn(a, b); r = redc_fn(t); }
         else r = mul_fn(a, b);
     }
-    // The squaring stays one function.  Splitting it like mul costs P-384 3-6 % (measured); whether the one-function form
-    // hits the predicate spills depends on the kernel it is compiled into (ptxas allocates registers across the call
-    // graph): check `tools/sass_funcs.py` for P2R / LOP3 in the squarer after touching a kernel that calls it.
-    ECB_DEV static void sqr(E& r, const E& a) { r = sqr_fn(a); }
+    // The squaring stays one function by default.  Splitting it like mul costs P-384 3-6 % where the one-function form
+    // compiles well (the public-input kernels); whether it hits the predicate spills depends on the kernel it is compiled
+    // into (ptxas allocates registers across the call graph) - the P-384 secret-scalar kernels do (367 instead of 272
+    // instructions) and take the split form, 7 % faster there.  Check `tools/sass_funcs.py` for P2R / LOP3 in the
+    // squarer after touching a kernel that calls it.
+    ECB_FIELD_FN static Wide sqrw_fn(E a) { Wide t; sqr_wide<L>(t.v, a.v); return t; }
+    ECB_DEV static void sqr(E& r, const E& a) {
+        if constexpr (SQSPLIT) { Wide t = sqrw_fn(a); r = redc_fn(t); }
+        else r = sqr_fn(a);
+    }
 #endif
     ECB_DEV static void add(E& r, const E& a, const E& b) {
         u32 v[L];
