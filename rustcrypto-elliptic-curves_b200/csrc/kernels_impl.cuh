@@ -26,15 +26,16 @@ template <class C> constexpr int fast_min_ctas() { return C::L > 8 ? ECB_FAST_MI
 #endif
 template <class C> constexpr int ct_min_ctas() { return C::L > 8 ? 3 : ECB_CT_MIN_CTAS; }
 
-template <class C> __global__ void __launch_bounds__(BLK) k_field_op(int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
-    Bodies<C>::body_field_op(blockIdx.x * BLK + threadIdx.x, n, which, op, a, b, out, ok);
-}
 // Curve descriptor with the two-call squarer (mont.cuh SQSPLIT), for the kernels in which ptxas compiles the one-function
-// squarer of P-384 with spilled carry predicates: the complete-formula (secret-scalar) scalar multiplication.
+// squarer of P-384 with spilled carry predicates (tools/sass_funcs.py): the complete-formula (secret-scalar) scalar
+// multiplication, normalisation (one 384-squaring inversion per thread), SEC1 decoding (square root), the window-table kernel.
 template <class C> struct SplitSqr : C { typedef Mont<typename C::F::Params, true> F; };
 template <class C> struct CtCurve { typedef C type; };
 template <> struct CtCurve<CurveP384> { typedef SplitSqr<CurveP384> type; };
 
+template <class C> __global__ void __launch_bounds__(BLK) k_field_op(int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
+    Bodies<C>::body_field_op(blockIdx.x * BLK + threadIdx.x, n, which, op, a, b, out, ok);
+}
 template <class C, bool CT> __global__ void __launch_bounds__(BLK, ct_min_ctas<C>()) k_mul_var(int n, u32 flags, const u8* pts, const u8* inf, const u8* k, u32* proj, u8* invalid) {
     Bodies<typename CtCurve<C>::type>::template body_mul_var<CT>(blockIdx.x * BLK + threadIdx.x, n, flags, pts, inf, k, proj, invalid);
 }
@@ -45,7 +46,7 @@ template <class C> __global__ void __launch_bounds__(BLK) k_load_proj(int n, con
     Bodies<C>::body_load_proj(blockIdx.x * BLK + threadIdx.x, n, xyz, proj, invalid);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_normalize(int n, const u32* proj, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
-    Bodies<C>::body_normalize(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, proj, mode, compress, out_bytes, out_inf, out_limbs);
+    Bodies<typename CtCurve<C>::type>::body_normalize(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, proj, mode, compress, out_bytes, out_inf, out_limbs);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_verify(int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok) {
     Bodies<C>::body_verify(blockIdx.x * BLK + threadIdx.x, n, q, z, rs, gtab, ok);
@@ -74,7 +75,7 @@ template <class C> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_
 #endif
 template <class C> constexpr int wt_min_ctas() { return C::L > 8 ? 3 : ECB_WT_MIN_CTAS; }
 template <class C> __global__ void __launch_bounds__(BLK, wt_min_ctas<C>()) k_wintab(int n, const u8* pts, const u32* aff_limbs, u32* wtab, u32* zbuf) {
-    Bodies<C>::body_wintab(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, pts, aff_limbs, wtab, zbuf);
+    Bodies<typename CtCurve<C>::type>::body_wintab(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, pts, aff_limbs, wtab, zbuf);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_verify_prep(int n, int mode, const u8* z, const u8* rs, u32* scratch) {
     Bodies<C>::body_verify_prep(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, mode, z, rs, scratch);
@@ -86,7 +87,7 @@ template <class C, int MODE> __global__ void __launch_bounds__(BLK, fast_min_cta
                                                                  ecb_dyn_smem + threadIdx.x, BLK, wtab);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_decode(int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
-    Bodies<C>::body_decode(blockIdx.x * BLK + threadIdx.x, n, mode, enc, stride, xy, status);
+    Bodies<typename CtCurve<C>::type>::body_decode(blockIdx.x * BLK + threadIdx.x, n, mode, enc, stride, xy, status);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_finish(int n, int kind, const u8* a, int stride, const u8* inf, const u8* rs, u8* ok) {
     Bodies<C>::body_finish(blockIdx.x * BLK + threadIdx.x, n, kind, a, stride, inf, rs, ok);
