@@ -39,6 +39,15 @@ struct DevBuf {
     }
 };
 
+// scratch that lives for one function call: freed on every return path (the CU() macro returns early on errors)
+struct ScopedDev {
+    void* p = nullptr;
+    ~ScopedDev() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+    template <class T> T* as() const { return (T*)p; }
+    void* release() { void* q = p; p = nullptr; return q; }
+};
+
 struct PinBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -60,6 +69,7 @@ struct PinBuf {
 
 constexpr size_t CHUNK = (size_t)1 << 20;   // elements per pipelined chunk of the host entry points
 constexpr int NCURVE = 6;                   // K256, P256, P384, SM2, P192, P224 (ecb200_curve)
+constexpr size_t MAX_ROWS = 0x7FFFFFFF;      // rows per device-pointer call (kernels index rows with int); host entry points chunk
 constexpr int NSLOT = 2;                    // double buffering: H2D / kernel / D2H of adjacent chunks overlap
 
 }  // namespace
@@ -123,21 +133,20 @@ int build_table(ecb200_ctx* c, const CurveLaunch* cl, const std::vector<uint8_t>
     const int FB = cl->FB, L = cl->L;
     std::vector<uint8_t> pts((size_t)entries * 2 * FB);
     for (int e = 0; e < entries; e++) memcpy(&pts[(size_t)e * 2 * FB], gxy.data(), 2 * FB);
-    uint8_t *d_pts = nullptr, *d_k = nullptr;
-    uint32_t* d_proj = nullptr;
-    CU(c, cudaMalloc(&d_pts, pts.size()));
-    CU(c, cudaMalloc(&d_k, scalars.size()));
-    CU(c, cudaMalloc(&d_proj, (size_t)entries * 3 * L * 4));
-    CU(c, cudaMalloc(out_tab, (size_t)entries * 2 * L * 4));
+    ScopedDev pts_b, k_b, proj_b, tab_b;
+    CU(c, pts_b.alloc(pts.size()));
+    CU(c, k_b.alloc(scalars.size()));
+    CU(c, proj_b.alloc((size_t)entries * 3 * L * 4));
+    CU(c, tab_b.alloc((size_t)entries * 2 * L * 4));
+    uint8_t *d_pts = pts_b.as<uint8_t>(), *d_k = k_b.as<uint8_t>();
+    uint32_t* d_proj = proj_b.as<uint32_t>();
     CU(c, cudaMemcpyAsync(d_pts, pts.data(), pts.size(), cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(d_k, scalars.data(), scalars.size(), cudaMemcpyHostToDevice, c->stream));
     cl->mul_var(c->stream, false, entries, 0, d_pts, nullptr, d_k, d_proj, nullptr);
-    cl->normalize(c->stream, entries, d_proj, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, *out_tab);
+    cl->normalize(c->stream, entries, d_proj, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, tab_b.as<uint32_t>());
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(c->stream));
-    cudaFree(d_pts);
-    cudaFree(d_k);
-    cudaFree(d_proj);
+    *out_tab = (uint32_t*)tab_b.release();   // the table outlives the call; everything else is freed here
     return 0;
 }
 
@@ -224,15 +233,16 @@ int ensure_gbig(ecb200_ctx* c, const CurveLaunch* cl) {
     std::vector<uint8_t> gxy(2 * FB);
     hex_to(gxy.data(), GX[cl->id], FB);
     hex_to(gxy.data() + FB, GY[cl->id], FB);
-    CU(c, cudaMalloc(&c->gbig[cl->id], ne * 2 * L * 4));
+    ScopedDev big_b, pts_b, k_b, proj_b;      // the table is published in c->gbig only when it is complete
+    CU(c, big_b.alloc(ne * 2 * L * 4));
     const size_t chunk = std::min<size_t>(ne, (size_t)1 << 18);
     std::vector<uint8_t> pts(chunk * 2 * FB), sc(chunk * FB);
     for (size_t e = 0; e < chunk; e++) memcpy(&pts[e * 2 * FB], gxy.data(), 2 * FB);
-    uint8_t *d_pts = nullptr, *d_k = nullptr;
-    uint32_t* d_proj = nullptr;
-    CU(c, cudaMalloc(&d_pts, pts.size()));
-    CU(c, cudaMalloc(&d_k, sc.size()));
-    CU(c, cudaMalloc(&d_proj, chunk * 3 * L * 4));
+    CU(c, pts_b.alloc(pts.size()));
+    CU(c, k_b.alloc(sc.size()));
+    CU(c, proj_b.alloc(chunk * 3 * L * 4));
+    uint8_t *d_pts = pts_b.as<uint8_t>(), *d_k = k_b.as<uint8_t>();
+    uint32_t *d_proj = proj_b.as<uint32_t>(), *d_big = big_b.as<uint32_t>();
     CU(c, cudaMemcpyAsync(d_pts, pts.data(), pts.size(), cudaMemcpyHostToDevice, c->stream));
     for (size_t off = 0; off < ne; off += chunk) {
         size_t cnt = std::min(chunk, ne - off);
@@ -248,13 +258,11 @@ int ensure_gbig(ecb200_ctx* c, const CurveLaunch* cl) {
         }
         CU(c, cudaMemcpyAsync(d_k, sc.data(), cnt * FB, cudaMemcpyHostToDevice, c->stream));
         cl->mul_var_fast(c->stream, (int)cnt, d_pts, nullptr, nullptr, d_k, d_proj, nullptr, nullptr);
-        cl->normalize(c->stream, (int)cnt, d_proj, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, c->gbig[cl->id] + off * 2 * L);
+        cl->normalize(c->stream, (int)cnt, d_proj, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, d_big + off * 2 * L);
         CU(c, cudaGetLastError());
         CU(c, cudaStreamSynchronize(c->stream));
     }
-    cudaFree(d_pts);
-    cudaFree(d_k);
-    cudaFree(d_proj);
+    c->gbig[cl->id] = (uint32_t*)big_b.release();
     return 0;
 }
 
@@ -594,7 +602,7 @@ int ecb200_kernel_timing_read(ecb200_ctx* c, double* total_ms, uint64_t* launche
 // ---- device-pointer entry points
 int ecb200_mul_gen_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_k, uint8_t* d_out, uint32_t flags, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
-    if (!cl || (n && (!d_k || !d_out))) return fail(c, ECB200_ERR_ARG, "mul_gen_dev: bad argument");
+    if (!cl || n > MAX_ROWS || (n && (!d_k || !d_out))) return fail(c, ECB200_ERR_ARG, "mul_gen_dev: bad argument");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return mul_gen_core(c, cl, n, d_k, d_out, flags, pick(c, stream));
@@ -602,14 +610,14 @@ int ecb200_mul_gen_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_k, u
 int ecb200_mul_var_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_pts, const uint8_t* d_inf, const uint8_t* d_k,
                        uint8_t* d_out, uint8_t* d_invalid, uint32_t flags, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
-    if (!cl || (n && (!d_pts || !d_k || !d_out))) return fail(c, ECB200_ERR_ARG, "mul_var_dev: bad argument");
+    if (!cl || n > MAX_ROWS || (n && (!d_pts || !d_k || !d_out))) return fail(c, ECB200_ERR_ARG, "mul_var_dev: bad argument");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return mul_var_core(c, cl, n, d_pts, d_inf, d_k, d_out, d_invalid, flags, pick(c, stream));
 }
 int ecb200_batch_normalize_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_xyz, uint8_t* d_xy, uint8_t* d_inf, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
-    if (!cl || (n && (!d_xyz || !d_xy))) return fail(c, ECB200_ERR_ARG, "batch_normalize_dev: bad argument");
+    if (!cl || n > MAX_ROWS || (n && (!d_xyz || !d_xy))) return fail(c, ECB200_ERR_ARG, "batch_normalize_dev: bad argument");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return batch_normalize_core(c, cl, n, d_xyz, d_xy, d_inf, pick(c, stream));
@@ -617,7 +625,7 @@ int ecb200_batch_normalize_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t
 int ecb200_ecdsa_verify_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_q, const uint8_t* d_z, const uint8_t* d_rs,
                             uint8_t* d_ok, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
-    if (!cl || (n && (!d_q || !d_z || !d_rs || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_verify_dev: bad argument");
+    if (!cl || n > MAX_ROWS || (n && (!d_q || !d_z || !d_rs || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_verify_dev: bad argument");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return verify_core(c, cl, n, d_q, d_z, d_rs, d_ok, pick(c, stream));
@@ -737,7 +745,7 @@ int ecb200_lincomb(ecb200_ctx* c, int curve, size_t n_terms, const uint8_t* pts,
 int ecb200_decode_points_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_enc, size_t stride, uint32_t mode, uint8_t* d_xy, uint8_t* d_status,
                              void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
-    if (!cl || mode > 1 || (n && (!d_enc || !d_xy || !d_status)) || stride < (size_t)cl->FB + (mode == DEC_SEC1 ? 1 : 0))
+    if (!cl || n > MAX_ROWS || mode > 1 || (n && (!d_enc || !d_xy || !d_status)) || stride < (size_t)cl->FB + (mode == DEC_SEC1 ? 1 : 0))
         return fail(c, ECB200_ERR_ARG, "decode_points_dev: bad argument");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
@@ -759,7 +767,7 @@ int ecb200_decode_points(ecb200_ctx* c, int curve, size_t n, const uint8_t* enc,
 int ecb200_ecdsa_verify_sec1_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_keys, size_t key_stride, const uint8_t* d_z, const uint8_t* d_rs,
                                  uint8_t* d_ok, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
-    if (!cl || (n && (!d_keys || !d_z || !d_rs || !d_ok)) || key_stride < (size_t)cl->FB + 1) return fail(c, ECB200_ERR_ARG, "ecdsa_verify_sec1_dev: bad argument");
+    if (!cl || n > MAX_ROWS || (n && (!d_keys || !d_z || !d_rs || !d_ok)) || key_stride < (size_t)cl->FB + 1) return fail(c, ECB200_ERR_ARG, "ecdsa_verify_sec1_dev: bad argument");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return verify_sec1_core(c, cl, n, d_keys, key_stride, d_z, d_rs, d_ok, pick(c, stream));
@@ -779,7 +787,7 @@ int ecb200_ecdsa_verify_sec1(ecb200_ctx* c, int curve, size_t n, const uint8_t* 
 int ecb200_ecdsa_recover_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_z, const uint8_t* d_rs, const uint8_t* d_recid, uint8_t* d_keys,
                              uint8_t* d_ok, uint32_t flags, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
-    if (!cl || (n && (!d_z || !d_rs || !d_recid || !d_keys || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_recover_dev: bad argument");
+    if (!cl || n > MAX_ROWS || (n && (!d_z || !d_rs || !d_recid || !d_keys || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_recover_dev: bad argument");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return recover_core(c, cl, n, d_z, d_rs, d_recid, d_keys, d_ok, flags, pick(c, stream));
@@ -799,7 +807,7 @@ int ecb200_ecdsa_recover(ecb200_ctx* c, int curve, size_t n, const uint8_t* z, c
 }
 int ecb200_schnorr_verify_dev(ecb200_ctx* c, size_t n, const uint8_t* d_pk, const uint8_t* d_e, const uint8_t* d_sig, uint8_t* d_ok, void* stream) {
     const CurveLaunch* cl = curve_of(c, ECB200_K256);
-    if (!cl || (n && (!d_pk || !d_e || !d_sig || !d_ok))) return fail(c, ECB200_ERR_ARG, "schnorr_verify_dev: bad argument");
+    if (!cl || n > MAX_ROWS || (n && (!d_pk || !d_e || !d_sig || !d_ok))) return fail(c, ECB200_ERR_ARG, "schnorr_verify_dev: bad argument");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return schnorr_core(c, cl, n, d_pk, d_e, d_sig, d_ok, pick(c, stream));
@@ -818,7 +826,7 @@ int ecb200_schnorr_verify(ecb200_ctx* c, size_t n, const uint8_t* pk, const uint
 }
 int ecb200_sm2dsa_verify_dev(ecb200_ctx* c, size_t n, const uint8_t* d_q, const uint8_t* d_e, const uint8_t* d_rs, uint8_t* d_ok, void* stream) {
     const CurveLaunch* cl = curve_of(c, ECB200_SM2);
-    if (!cl || (n && (!d_q || !d_e || !d_rs || !d_ok))) return fail(c, ECB200_ERR_ARG, "sm2dsa_verify_dev: bad argument");
+    if (!cl || n > MAX_ROWS || (n && (!d_q || !d_e || !d_rs || !d_ok))) return fail(c, ECB200_ERR_ARG, "sm2dsa_verify_dev: bad argument");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return verify_core(c, cl, n, d_q, d_e, d_rs, d_ok, pick(c, stream), VM_SM2DSA);
@@ -838,7 +846,7 @@ int ecb200_sm2dsa_verify(ecb200_ctx* c, size_t n, const uint8_t* q, const uint8_
 int ecb200_ecdsa_sign_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_d, const uint8_t* d_k, const uint8_t* d_z, uint8_t* d_rs, uint8_t* d_recid,
                           uint8_t* d_ok, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
-    if (!cl || (n && (!d_d || !d_k || !d_z || !d_rs || !d_recid || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_sign_dev: bad argument");
+    if (!cl || n > MAX_ROWS || (n && (!d_d || !d_k || !d_z || !d_rs || !d_recid || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_sign_dev: bad argument");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return sign_core(c, cl, n, d_d, d_k, d_z, d_rs, d_recid, d_ok, pick(c, stream));

@@ -510,8 +510,11 @@ def test_abi_error_behaviour_and_reuse(eng):
     assert lib.ecb200_decode_points(eng.h, 0, 1, buf, 8, 0, buf, buf) == -1         # stride too small
     assert lib.ecb200_decode_points(eng.h, 0, 1, buf, 33, 2, buf, buf) == -1        # unknown mode
     assert b"bad argument" in lib.ecb200_last_error(eng.h)
-    for name in ("mul_gen", "ecdsa_verify"):                                        # n = 0 is fine, even with null buffers
-        pass
+    # device-pointer calls index rows with int: more than 2^31 - 1 rows per call is refused, not truncated
+    assert lib.ecb200_mul_gen_dev(eng.h, 0, 1 << 31, buf, buf, 0, None) == -1
+    assert lib.ecb200_ecdsa_verify_dev(eng.h, 1, (1 << 31) + 5, buf, buf, buf, buf, None) == -1
+    assert lib.ecb200_mul_gen(eng.h, 5, 1, None, buf, 0) == -1 and lib.ecb200_mul_gen(eng.h, 6, 1, buf, buf, 0) == -1   # last curve id is 5
+    # n = 0 is fine, even with null buffers
     assert lib.ecb200_mul_gen(eng.h, 0, 0, None, None, 0) == 0
     assert lib.ecb200_ecdsa_verify(eng.h, 1, 0, None, None, None, None) == 0
     assert lib.ecb200_schnorr_verify(eng.h, 0, None, None, None, None) == 0
