@@ -125,9 +125,35 @@ template <class P, bool SQSPLIT = false> struct Mont {
         final_sub(r, h, top);
     }
 
+    // p = R - 2^(32e) + 1 (P-224, R = 2^224, e = 3; n0 = -1).  With Q' = t_lo * p^-1 mod R the reduced value is
+    // (t - Q' p) / R, in (-p, p).  p = 1 - 2^(32e) (mod R) makes Q' the fixed point of Q' = t_lo + (Q' << 32e) (mod R),
+    // found limb by limb with one ascending carry chain; then t - Q' p = t - Q' R + Q' 2^(32e) - Q', whose low half is
+    // (carry of that chain) * R, so  r = t_hi + (Q' >> 32(L-e)) + carry - Q',  plus p when negative.  No multiplier-pipe
+    // instruction and no final comparison against p.
+    template <class PP = P> ECB_DEV static void redc_negsparse(u32* r, u32* t) {
+        constexpr int e = PP::NE;
+        t[e] = add_cc(t[e], t[0]);
+        ECB_UNROLL
+        for (int i = e + 1; i < L; i++) t[i] = addc_cc(t[i], t[i - e]);
+        const u32 cs = addc(0u, 0u);                                   // t[0..L) is Q' now
+        u32 s[L], d[L];
+        add_cc(cs, 0xFFFFFFFFu);                                       // carry flag := cs
+        ECB_UNROLL
+        for (int j = 0; j < L; j++) s[j] = addc_cc(t[L + j], j < e ? t[L - e + j] : 0u);
+        const u32 sc = addc(0u, 0u);
+        d[0] = sub_cc(s[0], t[0]);
+        ECB_UNROLL
+        for (int j = 1; j < L; j++) d[j] = subc_cc(s[j], t[j]);
+        const u32 bw = subc(0u, 0u);                                   // all ones on borrow
+        const u32 m = bw & ~((u32)0 - sc);                             // negative: borrow not covered by the carry of s
+        r[0] = add_cc(d[0], PP::p(0) & m);
+        ECB_UNROLL
+        for (int j = 1; j < L; j++) r[j] = addc_cc(d[j], PP::p(j) & m);
+    }
     // Montgomery reduction of t[0..2L): r = t * R^-1 mod p   (t < p * R)
     ECB_DEV static void redc(u32* r, u32* t) {
         if constexpr (P::SPARSE) redc_sparse(r, t);
+        else if constexpr (P::NEGSPARSE) redc_negsparse(r, t);
         else redc_generic(r, t);
     }
     // odd limb counts (P-224): row by row with a 64-bit running carry; a row's carry-out (weight L + i) never feeds a later

@@ -104,6 +104,13 @@ def mont_params(name, m, L, comment, base_field=False):
         s += "    ECB_HD static constexpr int ts(int k) { constexpr int t[%d] = {%s}; return t[k]; }\n" % (len(terms), ", ".join(str(sg) for _, sg in terms))
     else:
         s += "    static constexpr bool SPARSE = false;\n"
+    # p = 2^(32L) - 2^(32e) + 1 (P-224): n0 = -1; reduction by one shifted addition chain and a subtraction (mont.cuh redc_negsparse)
+    ne = next((e for e in range(1, L) if m == R - (1 << (32 * e)) + 1), None)
+    if ne:
+        s += "    // p = 2^%d - 2^%d + 1: Montgomery reduction without multiplications (n0 = -1)\n" % (32 * L, 32 * ne)
+        s += "    static constexpr bool NEGSPARSE = true;\n    static constexpr int NE = %d;\n" % ne
+    else:
+        s += "    static constexpr bool NEGSPARSE = false;\n"
     if base_field and m % 4 == 1:
         # Tonelli-Shanks constants: m - 1 = 2^S * t, t odd; root = g^t in Montgomery form for the smallest non-residue g
         S, t = 0, m - 1
