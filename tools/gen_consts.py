@@ -102,6 +102,18 @@ def mont_params(name, m, L, comment, base_field=False):
             len(terms), "true" if asc else "false")
         s += "    ECB_HD static constexpr int te(int k) { constexpr int t[%d] = {%s}; return t[k]; }\n" % (len(terms), ", ".join(str(e) for e, _ in terms))
         s += "    ECB_HD static constexpr int ts(int k) { constexpr int t[%d] = {%s}; return t[k]; }\n" % (len(terms), ", ".join(str(sg) for _, sg in terms))
+        # -p folded into the first chain's high-half pass (mont.cuh redc_sparse): C = 2^(32(L+1)) - p = 1 (mod 2^(32 e0)); a '+'
+        # chain adds C's limbs from e0 up, a '-' chain subtracts the negation of C >> 32 e0; the 1 at limb 0 is a carry-in
+        e0, s0 = terms[0]
+        C = (1 << (32 * (L + 1))) - m
+        assert C % (1 << (32 * e0)) == 1
+        words = L - e0 + 1
+        V = C >> (32 * e0)
+        Wv = V if s0 > 0 else (-V) % (1 << (32 * words))
+        fold = [0] * e0 + [(Wv >> (32 * i)) & 0xFFFFFFFF for i in range(words)]
+        s += "    // -p for the sign-based final correction: constants of the first chain's upper limbs and of the top word\n"
+        s += "    ECB_HD static constexpr u32 foldc(int i) { constexpr u32 t[%d] = {%s}; return t[i]; }\n" % (L, ", ".join("0x%08Xu" % x for x in fold[:L]))
+        s += "    static constexpr u32 foldc_top = 0x%08Xu;\n" % fold[L]
     else:
         s += "    static constexpr bool SPARSE = false;\n"
     # p = 2^(32L) - 2^(32e) + 1 (P-224): n0 = -1; reduction by one shifted addition chain and a subtraction (mont.cuh redc_negsparse)
