@@ -32,7 +32,7 @@ def rand_scalars(n, fb, seed):
 
 
 # usage: quick_bench.py [curve,curve,...] [log2 n]   (default: every curve at its quick size)
-CASES = (("k256", 1 << 18), ("p256", 1 << 17), ("sm2", 1 << 17), ("p384", 1 << 16))
+CASES = (("k256", 1 << 18), ("p256", 1 << 17), ("sm2", 1 << 17), ("p384", 1 << 16), ("p192", 1 << 17), ("p224", 1 << 17))
 if len(sys.argv) > 1:
     CASES = tuple((c, (1 << int(sys.argv[2])) if len(sys.argv) > 2 else dict(CASES)[c]) for c in sys.argv[1].split(","))
 for cname, n in CASES:
