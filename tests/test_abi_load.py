@@ -21,6 +21,20 @@ def test_header_matches_python_mirror():
     assert header_symbols() == sorted(ecb200.ABI_SYMBOLS)
 
 
+def test_header_constants_match_python_and_cpp_mirrors():
+    """Curve ids, flags and decode modes: include/ecb200.h is the source; the ctypes layer and the C++ mirror must agree."""
+    text = open(os.path.join(ROOT, "include", "ecb200.h")).read()
+    enum = {k: int(v) for k, v in re.findall(r"ECB200_(K256|P256|P384|SM2|P192|P224) = (\d+)", text)}
+    assert enum == {"K256": ecb200.K256, "P256": ecb200.P256, "P384": ecb200.P384, "SM2": ecb200.SM2, "P192": ecb200.P192, "P224": ecb200.P224}
+    assert sorted(enum.values()) == list(range(6))
+    flags = {k: int(v) for k, v in re.findall(r"#define ECB200_FLAG_(\w+) (\d+)u", text)}
+    assert flags == {"CT": ecb200.FLAG_CT, "COMPRESSED": ecb200.FLAG_COMPRESSED, "UNCOMPRESSED": ecb200.FLAG_UNCOMPRESSED, "PROJ": ecb200.FLAG_PROJ}
+    hpp = open(os.path.join(ROOT, "include", "ecb200.hpp")).read()
+    for name, fb in (("K256", 32), ("P256", 32), ("P384", 48), ("SM2", 32), ("P192", 24), ("P224", 28)):
+        m = re.search(r"static constexpr int ID = ECB200_%s;\s*static constexpr size_t FB = (\d+);" % name, hpp)
+        assert m and int(m.group(1)) == fb == ecb200.field_bytes(enum[name]), name
+
+
 def test_library_exports_every_symbol():
     if not os.path.exists(ecb200.LIB_PATH):
         import __graft_entry__
