@@ -67,7 +67,16 @@ struct PinBuf {
     }
 };
 
-constexpr size_t CHUNK = (size_t)1 << 20;   // elements per pipelined chunk of the host entry points
+// Elements per pipelined piece of the host entry points.  One-row-per-thread kernels run 148 SMs x {6, 4, 3} resident CTAs x
+// 128 threads per wave (113 664 / 75 776 / 56 832 rows); pieces that are whole multiples of all three (148 x 1536 = 227 328)
+// do not end in a mostly empty last wave - a 2^20-row piece is 9.23 waves of the verify kernel.  ECB200_CHUNK overrides (tests).
+#ifndef ECB200_CHUNK
+#define ECB200_CHUNK (5 * 227328)
+#endif
+#ifndef ECB200_FIRST_CHUNK
+#define ECB200_FIRST_CHUNK 227328
+#endif
+constexpr size_t CHUNK = (size_t)ECB200_CHUNK;
 constexpr int NCURVE = 6;                   // K256, P256, P384, SM2, P192, P224 (ecb200_curve)
 constexpr size_t MAX_ROWS = 0x7FFFFFFF;      // rows per device-pointer call (kernels index rows with int); host entry points chunk
 constexpr int NSLOT = 2;                    // double buffering: H2D / kernel / D2H of adjacent chunks overlap
@@ -413,8 +422,7 @@ template <class Fn>
 int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, const size_t* in_sz, int n_out, uint8_t* const* out,
                  const size_t* out_sz, Fn&& enqueue) {
     if (n == 0) return 0;
-    // piece 0 is a quarter of the others, so the first (unoverlapped) H2D is short
-    const size_t FIRST = CHUNK / 4;
+    const size_t FIRST = (size_t)ECB200_FIRST_CHUNK;   // the first piece is short, so the (unoverlapped) first H2D is short
     auto piece = [&](size_t ch, size_t& off, size_t& cnt) {
         off = ch == 0 ? 0 : FIRST + (ch - 1) * CHUNK;
         cnt = std::min(ch == 0 ? FIRST : CHUNK, n - off);

@@ -476,9 +476,12 @@ def test_pinned_host_buffers(eng):
     assert eng.ecdsa_verify("k256", pq.numpy(), z, prs.numpy()) == ref
 
 
-@pytest.mark.parametrize("n", [(1 << 18) - 1, (1 << 18) + 1, (1 << 18) + (1 << 20) + 5, (1 << 18) + 2 * (1 << 20)])
+FIRST_PIECE, PIECE = 227328, 5 * 227328     # abi.cu ECB200_FIRST_CHUNK / ECB200_CHUNK (wave-aligned pieces of the host pipeline)
+
+
+@pytest.mark.parametrize("n", [FIRST_PIECE - 1, FIRST_PIECE + 1, FIRST_PIECE + PIECE + 5, FIRST_PIECE + 2 * PIECE, (1 << 18) + (1 << 20) + 5])
 def test_pipeline_chunk_boundaries(eng, n):
-    """Host pipeline pieces (2^18 then 2^20 rows): a periodic input must give the same periodic output at every
+    """Host pipeline pieces (227 328 then 1 136 640 rows): a periodic input must give the same periodic output at every
     position, whatever piece a row falls into."""
     c = o.K256
     per = 1009
