@@ -3,7 +3,7 @@
  * This is the drop-in boundary for the data-parallel hot path of the RustCrypto `elliptic-curves`
  * workspace (risc0 fork): independent scalar multiplications, batch normalisation, small linear
  * combinations and ECDSA verify_prehash over secp256k1 (k256) and the primeorder curves P-256,
- * P-384 and SM2.  The reference has no FFI of its own; its only accelerator precedent is the risc0
+ * P-384 and SM2 (and P-192 / P-224 through the same template).  The reference has no FFI of its own; its only accelerator precedent is the risc0
  * zkVM syscall `modmul_u256_denormalized(&U256,&U256,&U256)` (k256/src/arithmetic/field/
  * field_8x32_risc0.rs:177-193, k256/src/arithmetic/scalar.rs:114-134), which swaps ONE modular
  * multiplication.  Across PCIe that granularity is useless, so the boundary moves up to whole batches
