@@ -13,6 +13,9 @@
 //   * secp256k1: the per-element table {1..8}Q is brought to ONE common Z without any inversion by
 //     working on the isomorphic curve y^2 = x^3 + 7 Z^6 (the a = 0 doubling does not involve b), so all
 //     66 GLV additions are mixed additions; the true Z is restored with one multiplication at the end.
+//   * primeorder curves: the per-element table {1..8}Q is made AFFINE for the whole batch by a separate kernel (k_wintab:
+//     Jacobian multiples, one inversion per thread shared by 16 rows x 7 entries through Montgomery's trick), so the window
+//     loop runs on mixed additions too (mul_window_affine); recovery, whose point is derived in-kernel, keeps mul_window_signed.
 // Secret-scalar entry points (ECB200_FLAG_CT) never come here.
 #pragma once
 #include "ec.cuh"

@@ -9,7 +9,8 @@
 //   byte inputs / outputs: as the C ABI (include/ecb200.h) — big-endian, AoS, one element after another;
 //   internal projective points: 3L little-endian u32 limbs per element (X|Y|Z, field-internal form,
 //     i.e. Montgomery for the primeorder curves), AoS, 16-byte aligned;
-//   internal affine tables: 2L limbs per entry (x|y).
+//   internal affine tables: 2L limbs per entry (x|y);
+//   per-row window tables of the primeorder public-input path: 16L limbs per row ({1..8}Q affine) + 7L limbs of Z scratch.
 #pragma once
 #include "ec.cuh"
 #include "jac.cuh"
