@@ -10,7 +10,8 @@ constexpr int BLK = 128;   // threads per CTA of the arithmetic kernels (registe
 // Resident CTAs per SM the public-input kernels are compiled for (register cap 65536 / (128 N)).  Measured on the B200
 // (k256 verify at 2^22 rows / P-256 verify at 2^20, M rows/s): N = 3: 50.7 / 27.6, 4: 50.7 / 28.5, 5: 51.9 / 28.7,
 // 6: 52.7 / 28.9, 7: 53.0 / 29.1, 8: 52.7 / 29.1.  6 (80 registers, ~120 bytes of spills) is the knee for the 8-limb curves;
-// the 12-limb curve keeps 4 (3 was slower, see git history).
+// the 12-limb curve keeps 4 (3 was slower, see git history).  Re-measured on the final round-1 build at 2^22 rows (batch-affine window
+// tables, sign-driven reduction): 6 / 7 / 8 = 52.77 / 53.07 / 52.74 (k256), 32.72 / 32.66 / 32.91 (P-256); P-384 at 4 / 5 / 6 = 10.26 / 10.32 / 10.41.
 #ifndef ECB_FAST_MIN_CTAS
 #define ECB_FAST_MIN_CTAS 6
 #endif
