@@ -36,6 +36,15 @@ enum : int {
 enum : int { DEC_SEC1 = 0, DEC_COMPACT = 1 };
 enum : int { FIN_SCHNORR = 0, FIN_RECOVER = 1 };
 
+// How the Montgomery-trick bodies (normalise, verify prep, window tables, sign finish) invert the running product of
+// the rows a thread owns.  OwnInv: every thread runs its own inversion chain - what the host emulation runs.  The CUDA
+// wrappers pass BlockInv (kernels_impl.cuh), which continues the trick across the CTA (warp shuffles + shared memory)
+// so that ONE chain serves all 128 threads; a cooperative policy needs every thread of the CTA to reach run().
+struct OwnInv {
+    static constexpr bool COOPERATIVE = false;
+    template <class FF> ECB_DEV static void run(typename FF::E& r, const typename FF::E& a) { FF::inv(r, a); }
+};
+
 template <class C> struct Bodies {
     typedef EC<C> G;
     typedef typename G::Proj Proj;
@@ -136,6 +145,7 @@ template <class C> struct Bodies {
     // slot becomes IDENTITY.  One field inversion per thread, 3 mul per element for the trick,
     // 2 mul for (X*zinv, Y*zinv).
     static constexpr int EPT = 16;
+    template <class INV = OwnInv>
     ECB_DEV static void body_normalize(int tid, int nthreads, int n, const u32* proj, int mode, int compress,
                                        u8* out_bytes, u8* out_inf, u32* out_limbs) {
         E pref[EPT];
@@ -158,9 +168,9 @@ template <class C> struct Bodies {
             F::mul(acc, acc, z);
             cnt++;
         }
-        if (cnt == 0) return;
+        if (!INV::COOPERATIVE && cnt == 0) return;
         E inv;
-        F::inv(inv, acc);
+        INV::template run<F>(inv, acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -354,6 +364,7 @@ template <class C> struct Bodies {
         load_be<L>(v, rs_row + (mode == VM_RECOVER ? 0 : FB));
         if (!scalar_in_range(v)) { zero_n<L>(v); v[0] = 1; }
     }
+    template <class INV = OwnInv>
     ECB_DEV static void body_verify_prep(int tid, int nthreads, int n, int mode, const u8* z, const u8* rs, u32* scratch) {
         typename Fn::E pref[PREP_EPT];
         typename Fn::E acc, inv;
@@ -376,8 +387,8 @@ template <class C> struct Bodies {
             }
             cnt++;
         }
-        if (cnt == 0) return;
-        if (need_inv) Fn::inv(inv, acc);
+        if (!INV::COOPERATIVE && cnt == 0) return;
+        if (need_inv) INV::template run<Fn>(inv, acc);   // need_inv depends on the mode only: uniform across the CTA
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -666,6 +677,7 @@ template <class C> struct Bodies {
         select_n<L>(v, ok, v, one);
         return ok;
     }
+    template <class INV = OwnInv>
     ECB_DEV static void body_sign_finish(int tid, int nthreads, int n, const u8* d, const u8* k, const u8* z, const u32* aff,
                                          u8* rs_out, u8* recid_out, u8* ok_out) {
         typename Fn::E pref[PREP_EPT];
@@ -686,8 +698,8 @@ template <class C> struct Bodies {
             Fn::mul(acc, acc, km);
             cnt++;
         }
-        if (cnt == 0) return;
-        Fn::inv(inv, acc);
+        if (!INV::COOPERATIVE && cnt == 0) return;
+        INV::template run<Fn>(inv, acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -754,6 +766,7 @@ template <class C> struct Bodies {
 #define ECB_WT_EPT 16
 #endif
     static constexpr int WT_EPT = ECB_WT_EPT;
+    template <class INV = OwnInv>
     ECB_DEV static void body_wintab(int tid, int nthreads, int n, const u8* pts, const u32* aff_limbs, u32* wtab, u32* zbuf) {
         E pref[WT_EPT];
         E run;
@@ -789,9 +802,9 @@ template <class C> struct Bodies {
             F::mul(run, run, prod);
             cnt++;
         }
-        if (cnt == 0) return;
+        if (!INV::COOPERATIVE && cnt == 0) return;
         E inv;
-        F::inv(inv, run);
+        INV::template run<F>(inv, run);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif

@@ -34,6 +34,89 @@ template <class C> struct SplitSqr : C { typedef Mont<typename C::F::Params, tru
 template <class C> struct CtCurve { typedef C type; };
 template <> struct CtCurve<CurveP384> { typedef SplitSqr<CurveP384> type; };
 
+// One inversion chain per CTA for the Montgomery-trick kernels (normalise, verify prep, window tables, sign finish).
+// Lanes run in lockstep, so an inversion costs a warp the same ~270-330 multiplications whether one lane or all 32 run
+// it; sharing it only pays across warps.  Each thread brings the product a of its rows.  Inside a warp: inclusive prefix
+// and suffix products by shuffles (5 + 5 multiplications); the four warp products go through shared memory, thread 0
+// inverts their product and gives every warp the inverse of its own product (Montgomery's trick over four values); a
+// thread's result is (product of the lanes below) x (product of the lanes above) x (inverse of its warp's product).
+// While thread 0 runs the chain the other three warps wait at the barrier and the SM issues other CTAs: per thread the
+// kernels spend 12 + ~280/4 multiplications on inversion instead of ~280.  No secret-dependent branch or address (the
+// sign-finish kernel inverts secret nonces).  The product must be non-zero: every body substitutes 1 for a zero factor.
+// -DECB_BLOCK_INV=0 restores one chain per thread (A/B measurements).
+#ifndef ECB_BLOCK_INV
+#define ECB_BLOCK_INV 1
+#endif
+struct BlockInv {
+    static constexpr bool COOPERATIVE = true;
+    template <class E> __device__ __forceinline__ static void shfl_up(E& r, const E& a, int d) {
+#pragma unroll
+        for (int w = 0; w < (int)(sizeof(E) / sizeof(u32)); w++) r.v[w] = __shfl_up_sync(0xffffffffu, a.v[w], d);
+    }
+    template <class E> __device__ __forceinline__ static void shfl_down(E& r, const E& a, int d) {
+#pragma unroll
+        for (int w = 0; w < (int)(sizeof(E) / sizeof(u32)); w++) r.v[w] = __shfl_down_sync(0xffffffffu, a.v[w], d);
+    }
+    template <class FF> __device__ static void run(typename FF::E& r, const typename FF::E& a) {
+        typedef typename FF::E E;
+        constexpr int W = (int)(sizeof(E) / sizeof(u32));
+        constexpr int NW = BLK / 32;
+        __shared__ u32 sh[2 * NW * W];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        E pre = a, suf = a, t, m;
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {
+            shfl_up(t, pre, d);
+            FF::mul(m, pre, t);
+            FF::select(pre, lane >= d, m, pre);
+            shfl_down(t, suf, d);
+            FF::mul(m, suf, t);
+            FF::select(suf, lane + d < 32, m, suf);
+        }
+        E below, above, one;
+        FF::set_one(one);
+        shfl_up(t, pre, 1);
+        FF::select(below, lane == 0, one, t);
+        shfl_down(t, suf, 1);
+        FF::select(above, lane == 31, one, t);
+        if (lane == 31) {
+#pragma unroll
+            for (int w = 0; w < W; w++) sh[warp * W + w] = pre.v[w];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {   // warp products in sh[0 .. NW), running products before each warp in sh[NW .. 2 NW), overwritten by the result
+            E tot, inv;
+            FF::set_one(tot);
+#pragma unroll 1
+            for (int k = 0; k < NW; k++) {
+#pragma unroll
+                for (int w = 0; w < W; w++) { t.v[w] = sh[k * W + w]; sh[(NW + k) * W + w] = tot.v[w]; }
+                FF::mul(tot, tot, t);
+            }
+            FF::inv(inv, tot);
+#pragma unroll 1
+            for (int k = NW - 1; k >= 0; k--) {
+#pragma unroll
+                for (int w = 0; w < W; w++) { t.v[w] = sh[(NW + k) * W + w]; m.v[w] = sh[k * W + w]; }
+                FF::mul(t, inv, t);
+                FF::mul(inv, inv, m);
+#pragma unroll
+                for (int w = 0; w < W; w++) sh[(NW + k) * W + w] = t.v[w];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < W; w++) t.v[w] = sh[(NW + warp) * W + w];
+        FF::mul(m, below, above);
+        FF::mul(r, m, t);
+    }
+};
+#if ECB_BLOCK_INV
+typedef BlockInv TrickInv;
+#else
+typedef OwnInv TrickInv;
+#endif
+
 template <class C> __global__ void __launch_bounds__(BLK) k_field_op(int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
     Bodies<C>::body_field_op(blockIdx.x * BLK + threadIdx.x, n, which, op, a, b, out, ok);
 }
@@ -47,7 +130,7 @@ template <class C> __global__ void __launch_bounds__(BLK) k_load_proj(int n, con
     Bodies<C>::body_load_proj(blockIdx.x * BLK + threadIdx.x, n, xyz, proj, invalid);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_normalize(int n, const u32* proj, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
-    Bodies<typename CtCurve<C>::type>::body_normalize(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, proj, mode, compress, out_bytes, out_inf, out_limbs);
+    Bodies<typename CtCurve<C>::type>::template body_normalize<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, proj, mode, compress, out_bytes, out_inf, out_limbs);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_verify(int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok) {
     Bodies<C>::body_verify(blockIdx.x * BLK + threadIdx.x, n, q, z, rs, gtab, ok);
@@ -76,10 +159,10 @@ template <class C> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_
 #endif
 template <class C> constexpr int wt_min_ctas() { return C::L > 8 ? 3 : ECB_WT_MIN_CTAS; }
 template <class C> __global__ void __launch_bounds__(BLK, wt_min_ctas<C>()) k_wintab(int n, const u8* pts, const u32* aff_limbs, u32* wtab, u32* zbuf) {
-    Bodies<typename CtCurve<C>::type>::body_wintab(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, pts, aff_limbs, wtab, zbuf);
+    Bodies<typename CtCurve<C>::type>::template body_wintab<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, pts, aff_limbs, wtab, zbuf);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_verify_prep(int n, int mode, const u8* z, const u8* rs, u32* scratch) {
-    Bodies<C>::body_verify_prep(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, mode, z, rs, scratch);
+    Bodies<C>::template body_verify_prep<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, mode, z, rs, scratch);
 }
 // MODE is a template parameter: the ECDSA instance carries no decompression / projective-output code
 template <class C, int MODE> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_verify_main(int n, const u8* q, const u8* rs, const u8* z, const u8* aux, const u32* scratch, const u32* gbig, int gw, u8* ok, u32* proj_out,
@@ -94,7 +177,7 @@ template <class C> __global__ void __launch_bounds__(BLK) k_finish(int n, int ki
     Bodies<C>::body_finish(blockIdx.x * BLK + threadIdx.x, n, kind, a, stride, inf, rs, ok);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_sign_finish(int n, const u8* d, const u8* k, const u8* z, const u32* aff, u8* rs_out, u8* recid_out, u8* ok_out) {
-    Bodies<C>::body_sign_finish(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, d, k, z, aff, rs_out, recid_out, ok_out);
+    Bodies<C>::template body_sign_finish<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, d, k, z, aff, rs_out, recid_out, ok_out);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_proj_to_bytes(int n, const u32* proj, u8* xyz) {
     int tid = blockIdx.x * BLK + threadIdx.x;

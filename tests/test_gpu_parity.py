@@ -200,6 +200,33 @@ def test_batch_normalize(eng, cname):
     assert eng.batch_normalize(cname, b"") == (b"", b"")
 
 
+@pytest.mark.parametrize("cname", ["k256", "p256", "p384"])
+def test_batch_normalize_shared_inversion(eng, cname):
+    """Several rows per thread and a ragged last CTA: the CTA-wide inversion (kernels_impl.cuh BlockInv: warp prefix /
+    suffix products, one chain per CTA) must give every row its own 1/Z - including rows next to Z = 0 slots, which
+    enter the shared product as 1 (BatchInvert semantics, k256 projective.rs:350-379)."""
+    c = o.curve(cname)
+    fb = c.fb
+    rng = random.Random(52)
+    base = [o.mul_gen(c, rng.randrange(1, c.n)) for _ in range(8)]
+    n = 148 * 128 * 2 + 77                      # 3 rows per thread, last CTA partly idle
+    pts = []
+    for i in range(n):
+        P = base[i % 8]
+        lam = rng.randrange(1, c.p)
+        if i % 129 == 5 or i in (0, n - 1):     # identity slots in every lane position over the batch
+            pts.append((P[0] * lam % c.p, P[1] * lam % c.p, 0))
+        else:
+            pts.append((P[0] * lam % c.p, P[1] * lam % c.p, lam))
+    xy, inf = eng.batch_normalize(cname, b"".join(be(P, fb) for P in pts))
+    for i, P in enumerate(pts):
+        sl = xy[i * 2 * fb:(i + 1) * 2 * fb]
+        if P[2] == 0:
+            assert inf[i] == 1 and sl == bytes(2 * fb), i
+        else:
+            assert inf[i] == 0 and sl == be(base[i % 8], fb), i
+
+
 @pytest.mark.parametrize("cname", CUR)
 def test_lincomb(eng, cname):
     """lincomb == sum k_i P_i (k256 mul.rs:493-526), incl. cancellation to the identity."""
