@@ -23,7 +23,8 @@ WANT = [
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "sm__cycles_elapsed.avg",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "sm__cycles_elapsed.avg",
     "launch__local_memory_size" , "smsp__inst_executed_op_local_ld.sum",
 ]
 lines = ["# ncu --set full: %s" % title, "", "| metric | unit | value |", "|---|---|---|"]
