@@ -38,9 +38,9 @@ template <> struct CtCurve<CurveP384> { typedef SplitSqr<CurveP384> type; };
 // Lanes run in lockstep, so an inversion costs a warp the same ~270-330 multiplications whether one lane or all 32 run
 // it; sharing it only pays across warps.  Each thread brings the product a of its rows.  Inside a warp: inclusive prefix
 // and suffix products by shuffles (5 + 5 multiplications); the four warp products go through shared memory, thread 0
-// (of a warp picked per CTA, see below) inverts their product and gives every warp the inverse of its own product (Montgomery's trick over four values); a
+// inverts their product and gives every warp the inverse of its own product (Montgomery's trick over four values); a
 // thread's result is (product of the lanes below) x (product of the lanes above) x (inverse of its warp's product).
-// While that thread runs the chain the other three warps wait at the barrier and the SM issues other CTAs: per thread the
+// While thread 0 runs the chain the other three warps wait at the barrier and the SM issues other CTAs: per thread the
 // kernels spend 12 + ~280/4 multiplications on inversion instead of ~280.  No secret-dependent branch or address (the
 // sign-finish kernel inverts secret nonces).  The product must be non-zero: every body substitutes 1 for a zero factor.
 // -DECB_BLOCK_INV=0 restores one chain per thread (A/B measurements).
@@ -84,11 +84,12 @@ struct BlockInv {
             for (int w = 0; w < W; w++) sh[warp * W + w] = pre.v[w];
         }
         __syncthreads();
-        // The chain runs on lane 0 of ONE warp.  Warp w of a CTA sits on SM sub-partition w % 4, so a fixed choice would put
-        // the chains of every resident CTA on the same scheduler and leave three idle during that phase: pick the warp by a
-        // hash of the CTA index (CTAs i, i + 148, ... of one SM share i % 4, hence not a plain modulus).
+        // The chain runs on thread 0.  Picking the warp by a hash of the CTA index, so that the chains of the CTAs resident
+        // on one SM land on different sub-partitions (warp w sits on sub-partition w % 4), was measured and is SLOWER on the
+        // B200: k_verify_prep<K256> 1.74 -> 2.05 ms per 2^22 rows, <P256> 0.51 -> 0.57 ms per 2^20 (ncu launch lists, same box);
+        // per-sub-partition instruction counts differ by only 14 % with the fixed choice.  -DECB_BLOCK_INV_SPREAD=1 builds it.
 #ifndef ECB_BLOCK_INV_SPREAD
-#define ECB_BLOCK_INV_SPREAD 1
+#define ECB_BLOCK_INV_SPREAD 0
 #endif
         const int chain_thread = ECB_BLOCK_INV_SPREAD ? (int)((blockIdx.x * 0x9E3779B1u) >> 30) % NW * 32 : 0;
         if ((int)threadIdx.x == chain_thread) {   // warp products in sh[0 .. NW), running products before each warp in sh[NW .. 2 NW), overwritten by the result
