@@ -18,7 +18,13 @@ constexpr int BLK = 128;   // threads per CTA of the arithmetic kernels (registe
 #ifndef ECB_FAST_MIN_CTAS_WIDE
 #define ECB_FAST_MIN_CTAS_WIDE 4
 #endif
-template <class C> constexpr int fast_min_ctas() { return C::L > 8 ? ECB_FAST_MIN_CTAS_WIDE : ECB_FAST_MIN_CTAS; }
+// secp256k1 takes 7 (72 registers, 140 / 204 bytes of spill stores / loads in the verify kernel): three back-to-back A/B rounds on one
+// box at 2^22 rows, 6 vs 7: verify 53.19 / 53.19 / 53.20 vs 53.50 / 53.49 / 53.50 M/s (+0.6 %), P*k 57.85 vs 58.28 M/s (+0.7 %);
+// the earlier sweeps had shown the same +0.5 % twice.  P-256 / SM2 measured flat to slightly slower at 7 and stay at 6.
+#ifndef ECB_FAST_MIN_CTAS_K256
+#define ECB_FAST_MIN_CTAS_K256 7
+#endif
+template <class C> constexpr int fast_min_ctas() { return C::L > 8 ? ECB_FAST_MIN_CTAS_WIDE : (C::A_IS_ZERO ? ECB_FAST_MIN_CTAS_K256 : ECB_FAST_MIN_CTAS); }
 // same knob for the secret-scalar kernels (complete formulas, full table scans).  Measured (k256 G*k CT at 2^18 / k256 P*k CT /
 // P-256 G*k CT / P-256 P*k CT, M/s): unconstrained (146-154 registers, 3 CTAs) 93.5 / 37.7 / 70.5 / 15.6,
 // 4: 95.5 / 39.4 / 73.6 / 16.3, 5: 93.4 / 39.3 / 70.2 / 15.6, 6: 91.5 / 39.7 / 60.8 / 16.2.
