@@ -20,8 +20,11 @@
  *   - Return value: 0 on success, negative ecb200_status otherwise (ecb200_last_error gives text).
  *     Per-element failures are data, not status (ok[i] / invalid[i]), mirroring
  *     `Result<(), signature::Error>` and `CtOption`.
- *   - A context is bound to one CUDA device and is thread-compatible (one call at a time).
- *     One process per GPU creates one context; batches shard by index range across ranks.
+ *   - A context made by ecb200_init is bound to one CUDA device and is thread-compatible (one call at a time; two
+ *     contexts may be driven from two host threads concurrently).  A context made by ecb200_init_multi spans several
+ *     devices of the box: its host entry points cut [0, n) into contiguous index shards, one per device, and run them
+ *     concurrently on one host thread + streams + pinned staging per device - no collective on the data path.
+ *     The alternative deployment is one process per GPU with one single-device context each (bench.py under torchrun).
  *   - There is no CPU fallback: every entry point fails with ECB200_ERR_CUDA if no sm_100 device
  *     is usable.
  */
@@ -50,7 +53,9 @@ typedef enum {
     ECB200_OK = 0,
     ECB200_ERR_ARG = -1,   /* null pointer, bad curve id, negative count */
     ECB200_ERR_CUDA = -2,  /* CUDA runtime failure (no device, launch or copy error) */
-    ECB200_ERR_ALLOC = -3  /* out of device or pinned memory */
+    ECB200_ERR_ALLOC = -3, /* out of device or pinned memory */
+    ECB200_ERR_POINT = -4  /* ecb200_lincomb: a term is not a valid point (coordinate >= p or off the curve); the reference
+                              cannot even construct such a ProjectivePoint, so the sum is refused rather than computed without it */
 } ecb200_status;
 
 /* flags */
@@ -70,6 +75,15 @@ size_t ecb200_point_slot_bytes(int curve, uint32_t flags);
 
 /* Create / destroy a context on CUDA device `device`.  Builds the fixed-base tables on the device. */
 int ecb200_init(int device, ecb200_ctx** out);
+/* One context over n_dev devices ("one call shards [0, n) over the GPUs of the box").  devices = NULL
+ * means devices 0 .. n_dev-1; n_dev <= 0 (with devices = NULL) means every visible device; an ordinal may be listed
+ * twice (two shards on one device - how the single-GPU tests exercise the sharding).  Every host-pointer entry
+ * point below accepts such a context: rows [floor(i n / g), floor((i+1) n / g)) go to device i, each on its own host
+ * thread, streams and pinned staging; ecb200_lincomb reduces each shard to one projective partial on its device and
+ * adds the <= g partials on the first device.  `_dev` entry points (device pointers) need a single-device context. */
+int ecb200_init_multi(int n_dev, const int* devices, ecb200_ctx** out);
+/* Number of devices behind a context (1 for ecb200_init). */
+int ecb200_device_count(const ecb200_ctx* ctx);
 void ecb200_destroy(ecb200_ctx* ctx);
 const char* ecb200_last_error(const ecb200_ctx* ctx);
 const char* ecb200_version(void);
@@ -106,9 +120,18 @@ int ecb200_batch_normalize(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* 
 /* out_point = sum_i k[i] * P[i] (ONE point).  Replaces `LinearCombinationExt::lincomb_ext(&[(P, k)])`
  * and `LinearCombination::lincomb` (k256 mul.rs:313-393; primeorder/src/projective.rs:415-420).
  * pts as in ecb200_mul_var; with ECB200_FLAG_PROJ in `out_flags_proj` the result is written as
- * X||Y||Z (3FB bytes, a partial sum another rank can keep adding to), else as one SEC1 slot. */
+ * X||Y||Z (3FB bytes, a partial sum another rank can keep adding to), else as one SEC1 slot.
+ * A term that is not a valid point fails the whole call with ECB200_ERR_POINT (nothing is written). */
 int ecb200_lincomb(ecb200_ctx* ctx, int curve, size_t n_terms, const uint8_t* pts, const uint8_t* k, uint8_t* out_point,
                    uint32_t flags, uint32_t out_flags_proj);
+
+/* out[i] = SEC1(k1[i] * P1[i] + k2[i] * P2[i]) - one result PER ROW.  Replaces `LinearCombination::lincomb(&x, &k, &y, &l)`
+ * (k256/src/arithmetic/mul.rs:313-323 -> lincomb N=2; primeorder/src/projective.rs:415-420) called in a loop over
+ * slices.  p1, p2: n x 2FB affine x||y, or n x 3FB X||Y||Z with ECB200_FLAG_PROJ (Z = 0 is the identity); k1, k2: n x FB;
+ * invalid: optional n bytes, 1 where either point failed validation (that row's output is the identity slot).
+ * ECB200_FLAG_CT selects the secret-scalar kernels for both products. */
+int ecb200_lincomb2(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* p1, const uint8_t* k1, const uint8_t* p2,
+                    const uint8_t* k2, uint8_t* out, uint8_t* invalid, uint32_t flags);
 
 /* ok[i] = 1 iff the signature verifies.  Replaces `VerifyingKey::verify_prehash` after bits2field, i.e.
  * `<AffinePoint as VerifyPrimitive>::verify_prehashed(&Q, &z, &sig)` (k256/src/ecdsa.rs:200-209 with the
@@ -138,6 +161,9 @@ int ecb200_batch_normalize_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8
                                uint8_t* d_inf, void* stream);
 int ecb200_ecdsa_verify_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_q, const uint8_t* d_z,
                             const uint8_t* d_rs, uint8_t* d_ok, void* stream);
+int ecb200_lincomb2_dev(ecb200_ctx* ctx, int curve, size_t n, const uint8_t* d_p1, const uint8_t* d_k1,
+                        const uint8_t* d_p2, const uint8_t* d_k2, uint8_t* d_out, uint8_t* d_invalid, uint32_t flags,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Callers and data formats either side of the path.  Same conventions;

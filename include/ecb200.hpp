@@ -186,6 +186,15 @@ public:
             throw Error(rc, "ecb200_init(device=" + std::to_string(device) + ") failed with " + std::to_string(rc) +
                                 ": no usable CUDA device (there is no CPU fallback)");
     }
+    // one context over several GPUs of the box (ecb200_init_multi): every batch entry point shards its rows by contiguous
+    // index range over `devices` inside one call; an empty list means every visible device
+    explicit Engine(const std::vector<int>& devices) {
+        int rc = ecb200_init_multi((int)devices.size(), devices.empty() ? nullptr : devices.data(), &ctx_);
+        if (rc != 0 || !ctx_)
+            throw Error(rc, "ecb200_init_multi over " + std::to_string(devices.size()) + " devices failed with " + std::to_string(rc) +
+                                ": no usable CUDA device (there is no CPU fallback)");
+    }
+    int device_count() const { return ecb200_device_count(ctx_); }
     ~Engine() { if (ctx_) ecb200_destroy(ctx_); }
     Engine(const Engine&) = delete;
     Engine& operator=(const Engine&) = delete;
@@ -434,6 +443,22 @@ template <class C> struct ProjectivePoint {
     // LinearCombination::lincomb(x, k, y, l) = x*k + y*l
     static ProjectivePoint lincomb(Engine& eng, const ProjectivePoint& x, const Scalar<C>& k, const ProjectivePoint& y, const Scalar<C>& l) {
         return lincomb_ext(eng, {{x, k}, {y, l}});
+    }
+    // LinearCombination::lincomb(&x, &k, &y, &l) over slices: out[i] = x_i*k_i + y_i*l_i, one point per row (constant time
+    // like the reference; k256/src/arithmetic/mul.rs:313-323, primeorder/src/projective.rs:415-420)
+    struct LincombTerm { ProjectivePoint x; Scalar<C> k; ProjectivePoint y; Scalar<C> l; };
+    static std::vector<AffinePoint<C>> lincomb_batch(Engine& eng, const std::vector<LincombTerm>& terms, bool vartime = false) {
+        const size_t n = terms.size(), slot = 1 + 2 * C::FB;
+        std::vector<uint8_t> p1(n * 3 * C::FB + 1), p2(n * 3 * C::FB + 1), k1(n * C::FB + 1), k2(n * C::FB + 1), out(n * slot + 1);
+        for (size_t i = 0; i < n; i++) {
+            std::memcpy(&p1[i * 3 * C::FB], &terms[i].x, 3 * C::FB);
+            std::memcpy(&p2[i * 3 * C::FB], &terms[i].y, 3 * C::FB);
+            std::memcpy(&k1[i * C::FB], terms[i].k.to_repr().data(), C::FB);
+            std::memcpy(&k2[i * C::FB], terms[i].l.to_repr().data(), C::FB);
+        }
+        eng.check(ecb200_lincomb2(eng.raw(), C::ID, n, p1.data(), k1.data(), p2.data(), k2.data(), out.data(), nullptr,
+                                  (vartime ? 0u : ECB200_FLAG_CT) | ECB200_FLAG_PROJ | ECB200_FLAG_UNCOMPRESSED), "lincomb2");
+        return slots_to_affine(out, n);
     }
     // group::Curve::to_affine for one point (a batch of one)
     AffinePoint<C> to_affine(Engine& eng) const { return batch_normalize(eng, {*this})[0]; }

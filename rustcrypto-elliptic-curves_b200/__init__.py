@@ -47,6 +47,7 @@ ABI_SYMBOLS = [
     "ecb200_ecdsa_sign", "ecb200_decode_points_dev", "ecb200_ecdsa_verify_sec1_dev", "ecb200_ecdsa_recover_dev",
     "ecb200_schnorr_verify_dev", "ecb200_sm2dsa_verify_dev", "ecb200_ecdsa_sign_dev",
     "ecb200_kernel_timing", "ecb200_kernel_timing_read",
+    "ecb200_init_multi", "ecb200_device_count", "ecb200_lincomb2", "ecb200_lincomb2_dev",
 ]
 DECODE_SEC1, DECODE_COMPACT = 0, 1
 
@@ -73,6 +74,10 @@ def load_library() -> ctypes.CDLL:
     lib.ecb200_point_slot_bytes.restype = sz
     lib.ecb200_point_slot_bytes.argtypes = [ci, u32]
     lib.ecb200_init.argtypes = [ci, ctypes.POINTER(vp)]
+    lib.ecb200_init_multi.argtypes = [ci, ctypes.POINTER(ci), ctypes.POINTER(vp)]
+    lib.ecb200_device_count.argtypes = [vp]
+    lib.ecb200_lincomb2.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, u8p, u8p, u32]
+    lib.ecb200_lincomb2_dev.argtypes = [vp, ci, sz, u8p, u8p, u8p, u8p, u8p, u8p, u32, vp]
     lib.ecb200_destroy.argtypes = [vp]
     lib.ecb200_destroy.restype = None
     lib.ecb200_last_error.argtypes = [vp]
@@ -139,32 +144,66 @@ def _nbytes(b) -> int:
     return int(b.nbytes) if hasattr(b, "nbytes") else len(b)
 
 
-def _as_buf(b) -> Tuple[ctypes.c_void_p, object]:
-    """bytes / bytearray / numpy uint8 array -> (void*, keep-alive)"""
+def _as_buf(b, need: Optional[int] = None, what: str = "buffer") -> Tuple[ctypes.c_void_p, object]:
+    """bytes / bytearray / numpy uint8 array -> (void*, keep-alive).  The C ABI takes raw pointers and trusts the row
+    count, so the length is checked HERE: `need` is the exact byte size the call will read or write through the pointer
+    (a shorter buffer would be read past its end).  numpy arrays must be uint8 and C-contiguous - a strided view such as
+    a[:, :fb] would silently feed the wrong bytes."""
     if b is None:
         return None, None
     if isinstance(b, bytes):       # zero-copy view of the immutable buffer (inputs only)
-        return ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p), b
-    if isinstance(b, bytearray):
-        arr = (ctypes.c_uint8 * len(b)).from_buffer(b)
-        return ctypes.cast(arr, ctypes.c_void_p), arr
-    if hasattr(b, "ctypes"):      # numpy
-        return ctypes.c_void_p(b.ctypes.data), b
-    raise TypeError("unsupported buffer type %r" % type(b))
+        ptr, keep = ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p), b
+    elif isinstance(b, bytearray):
+        keep = (ctypes.c_uint8 * len(b)).from_buffer(b)
+        ptr = ctypes.cast(keep, ctypes.c_void_p)
+    elif hasattr(b, "ctypes") and hasattr(b, "flags"):      # numpy
+        if str(b.dtype) != "uint8":
+            raise ValueError("%s: numpy buffers must have dtype uint8, got %s" % (what, b.dtype))
+        if not b.flags.c_contiguous:
+            raise ValueError("%s: numpy buffers must be C-contiguous (use np.ascontiguousarray)" % what)
+        ptr, keep = ctypes.c_void_p(b.ctypes.data), b
+    else:
+        raise TypeError("%s: unsupported buffer type %r" % (what, type(b)))
+    if need is not None and _nbytes(b) != need:
+        raise ValueError("%s: expected %d bytes, got %d" % (what, need, _nbytes(b)))
+    return ptr, keep
+
+
+def _rows(b, elem: int, what: str) -> int:
+    """row count of the buffer that defines n; its size must be a whole number of rows"""
+    nb = _nbytes(b)
+    if elem <= 0 or nb % elem:
+        raise ValueError("%s: %d bytes is not a whole number of %d-byte rows" % (what, nb, elem))
+    return nb // elem
 
 
 class Engine:
-    """One context = one GPU (one process per GPU).  Thread-compatible, not thread-safe."""
+    """One context.  Engine(device) = one GPU (the one-process-per-GPU deployment); Engine(devices=[0, 1, ...]) or
+    Engine(devices="all") = one context over several GPUs of the box (ecb200_init_multi): the host-buffer methods shard
+    every batch by contiguous index range over the devices inside ONE call.  Thread-compatible, not thread-safe."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
         self.lib = load_library()
         h = ctypes.c_void_p()
-        rc = self.lib.ecb200_init(int(device), ctypes.byref(h))
+        if devices is None:
+            rc = self.lib.ecb200_init(int(device), ctypes.byref(h))
+            what = "ecb200_init(device=%d)" % device
+        elif isinstance(devices, str):
+            if devices != "all":
+                raise ValueError("devices must be a list of device ordinals or 'all'")
+            rc = self.lib.ecb200_init_multi(0, None, ctypes.byref(h))
+            what = "ecb200_init_multi(all devices)"
+        else:
+            devs = [int(d) for d in devices]
+            arr = (ctypes.c_int * len(devs))(*devs)
+            rc = self.lib.ecb200_init_multi(len(devs), arr, ctypes.byref(h))
+            what = "ecb200_init_multi(%r)" % (devs,)
         if rc != 0 or not h:
-            raise Ecb200Error("ecb200_init(device=%d) failed with %d: no usable CUDA device or kernel build mismatch "
-                              "(there is no CPU fallback)" % (device, rc))
+            raise Ecb200Error("%s failed with %d: no usable CUDA device or kernel build mismatch "
+                              "(there is no CPU fallback)" % (what, rc))
         self.h = h
         self.device = device
+        self.n_devices = int(self.lib.ecb200_device_count(h))
 
     def close(self):
         if getattr(self, "h", None):
@@ -198,12 +237,14 @@ class Engine:
         return float(ms.value), int(cnt.value)
 
     # ------------------------------------------------------------------ host-buffer API (bytes in, bytes out)
+    # Every method derives n from ONE buffer and checks every other buffer against it (ValueError on mismatch):
+    # the C ABI takes raw pointers and would read past a short buffer.
     def mul_by_generator_batch(self, curve, ks: bytes, flags: int = 0) -> bytes:
         """[k_i * G] as SEC1 slots.  ks = n x FB big-endian scalars."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = _nbytes(ks) // fb
+        n = _rows(ks, fb, "mul_gen: ks")
         out = bytearray(n * slot_bytes(cid, flags))
-        pk, k1 = _as_buf(ks)
+        pk, k1 = _as_buf(ks, n * fb, "mul_gen: ks")
         po, k2 = _as_buf(out)
         self._check(self.lib.ecb200_mul_gen(self.h, cid, n, pk, po, flags), "mul_gen")
         return bytes(out)
@@ -211,12 +252,12 @@ class Engine:
     def mul_batch(self, curve, points: bytes, ks: bytes, inf: Optional[bytes] = None, flags: int = 0) -> Tuple[bytes, bytes]:
         """[k_i * P_i] as SEC1 slots, plus the per-element invalid-point flags."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = _nbytes(ks) // fb
+        n = _rows(ks, fb, "mul_var: ks")
         out = bytearray(n * slot_bytes(cid, flags))
         invalid = bytearray(n)
-        pp, a = _as_buf(points)
-        pi, b = _as_buf(inf)
-        pk, c = _as_buf(ks)
+        pp, a = _as_buf(points, n * fb * (3 if flags & FLAG_PROJ else 2), "mul_var: points")
+        pi, b = _as_buf(inf, n, "mul_var: inf")
+        pk, c = _as_buf(ks, n * fb, "mul_var: ks")
         po, d = _as_buf(out)
         pv, e = _as_buf(invalid)
         self._check(self.lib.ecb200_mul_var(self.h, cid, n, pp, pi, pk, po, pv, flags), "mul_var")
@@ -224,10 +265,10 @@ class Engine:
 
     def batch_normalize(self, curve, xyz: bytes) -> Tuple[bytes, bytes]:
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = _nbytes(xyz) // (3 * fb)
+        n = _rows(xyz, 3 * fb, "batch_normalize: xyz")
         xy = bytearray(n * 2 * fb)
         inf = bytearray(n)
-        pi, a = _as_buf(xyz)
+        pi, a = _as_buf(xyz, n * 3 * fb, "batch_normalize: xyz")
         po, b = _as_buf(xy)
         pf, c = _as_buf(inf)
         self._check(self.lib.ecb200_batch_normalize(self.h, cid, n, pi, po, pf), "batch_normalize")
@@ -236,25 +277,43 @@ class Engine:
     def lincomb(self, curve, points: bytes, ks: bytes, flags: int = 0, out_proj: bool = False) -> bytes:
         """sum_i k_i * P_i as one SEC1 slot (or X||Y||Z when out_proj)."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = _nbytes(ks) // fb
+        n = _rows(ks, fb, "lincomb: ks")
         out = bytearray(3 * fb if out_proj else slot_bytes(cid, flags))
-        pp, a = _as_buf(points)
-        pk, b = _as_buf(ks)
+        pp, a = _as_buf(points, n * fb * (3 if flags & FLAG_PROJ else 2), "lincomb: points")
+        pk, b = _as_buf(ks, n * fb, "lincomb: ks")
         po, c = _as_buf(out)
         self._check(self.lib.ecb200_lincomb(self.h, cid, n, pp, pk, po, flags, FLAG_PROJ if out_proj else 0), "lincomb")
         return bytes(out)
+
+    def lincomb2_batch(self, curve, p1: bytes, k1: bytes, p2: bytes, k2: bytes, flags: int = 0) -> Tuple[bytes, bytes]:
+        """[k1_i * P1_i + k2_i * P2_i] as SEC1 slots, one result PER ROW, plus per-row invalid flags:
+        LinearCombination::lincomb(&x, &k, &y, &l) (k256 mul.rs:313-323, primeorder projective.rs:415-420) over slices.
+        Points are affine x||y (X||Y||Z with FLAG_PROJ); FLAG_CT selects the secret-scalar kernels."""
+        cid, fb = curve_id(curve), field_bytes(curve)
+        n = _rows(k1, fb, "lincomb2: k1")
+        pb = fb * (3 if flags & FLAG_PROJ else 2)
+        out = bytearray(n * slot_bytes(cid, flags))
+        invalid = bytearray(n)
+        a1, h1 = _as_buf(p1, n * pb, "lincomb2: p1")
+        a2, h2 = _as_buf(k1, n * fb, "lincomb2: k1")
+        a3, h3 = _as_buf(p2, n * pb, "lincomb2: p2")
+        a4, h4 = _as_buf(k2, n * fb, "lincomb2: k2")
+        po, h5 = _as_buf(out)
+        pv, h6 = _as_buf(invalid)
+        self._check(self.lib.ecb200_lincomb2(self.h, cid, n, a1, a2, a3, a4, po, pv, flags), "lincomb2")
+        return bytes(out), bytes(invalid)
 
     def ecdsa_verify(self, curve, q: bytes, z: bytes, rs: bytes, out=None) -> bytes:
         """ok bytes for n x (Q = x||y, z = bits2field(prehash), r||s).  Buffers may be bytes or numpy uint8 arrays;
         page-locked arrays (e.g. views of torch pinned tensors) are DMA'd directly, pageable ones are staged.
         out: optional n-byte numpy array that receives the result (returned as is)."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = _nbytes(z) // fb
+        n = _rows(z, fb, "ecdsa_verify: z")
         ok = out if out is not None else bytearray(n)
-        pq, a = _as_buf(q)
-        pz, b = _as_buf(z)
-        pr, c = _as_buf(rs)
-        po, d = _as_buf(ok)
+        pq, a = _as_buf(q, n * 2 * fb, "ecdsa_verify: q")
+        pz, b = _as_buf(z, n * fb, "ecdsa_verify: z")
+        pr, c = _as_buf(rs, n * 2 * fb, "ecdsa_verify: rs")
+        po, d = _as_buf(ok, n, "ecdsa_verify: out")
         self._check(self.lib.ecb200_ecdsa_verify(self.h, cid, n, pq, pz, pr, po), "ecdsa_verify")
         return ok if out is not None else bytes(ok)
 
@@ -262,6 +321,8 @@ class Engine:
                              sigs: Sequence[Tuple[int, int]]) -> List[bool]:
         """Vec<Result<(), Error>> of VerifyingKey::verify_prehash over slices (True = Ok(()))."""
         cid, fb = curve_id(curve), field_bytes(curve)
+        if not (len(keys) == len(prehashes) == len(sigs)):
+            raise ValueError("verify_prehash_batch: keys, prehashes and sigs must have the same length")
         lim = 1 << (8 * fb)
         idx, q, z, rs = [], bytearray(), bytearray(), bytearray()
         res = [False] * len(keys)
@@ -283,11 +344,11 @@ class Engine:
 
     def field_op(self, curve, which: int, op: int, a: bytes, b: Optional[bytes] = None) -> Tuple[bytes, bytes]:
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = _nbytes(a) // fb
+        n = _rows(a, fb, "field_op: a")
         out = bytearray(n * fb)
         ok = bytearray(n)
-        pa, k1 = _as_buf(a)
-        pb, k2 = _as_buf(b)
+        pa, k1 = _as_buf(a, n * fb, "field_op: a")
+        pb, k2 = _as_buf(b, n * fb, "field_op: b")
         po, k3 = _as_buf(out)
         pk, k4 = _as_buf(ok)
         self._check(self.lib.ecb200_field_op(self.h, cid, which, op, n, pa, pb, po, pk), "field_op")
@@ -297,9 +358,9 @@ class Engine:
     def decode_points(self, curve, enc: bytes, stride: int, mode: int = DECODE_SEC1) -> Tuple[bytes, bytes]:
         """from_encoded_point / decompress / decompact over n fixed-stride slots -> (x||y bytes, status bytes 1/2/0)."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = _nbytes(enc) // stride
+        n = _rows(enc, stride, "decode_points: enc")
         xy, st = bytearray(n * 2 * fb), bytearray(n)
-        pe, a = _as_buf(enc)
+        pe, a = _as_buf(enc, n * stride, "decode_points: enc")
         px, b = _as_buf(xy)
         ps, c = _as_buf(st)
         self._check(self.lib.ecb200_decode_points(self.h, cid, n, pe, stride, mode, px, ps), "decode_points")
@@ -308,11 +369,11 @@ class Engine:
     def ecdsa_verify_sec1(self, curve, keys: bytes, key_stride: int, z: bytes, rs: bytes) -> bytes:
         """verify_prehash with SEC1-encoded keys (VerifyingKey::from_sec1_bytes), keys decoded on the device."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = _nbytes(z) // fb
+        n = _rows(z, fb, "ecdsa_verify_sec1: z")
         ok = bytearray(n)
-        pk, a = _as_buf(keys)
-        pz, b = _as_buf(z)
-        pr, c = _as_buf(rs)
+        pk, a = _as_buf(keys, n * key_stride, "ecdsa_verify_sec1: keys")
+        pz, b = _as_buf(z, n * fb, "ecdsa_verify_sec1: z")
+        pr, c = _as_buf(rs, n * 2 * fb, "ecdsa_verify_sec1: rs")
         po, d = _as_buf(ok)
         self._check(self.lib.ecb200_ecdsa_verify_sec1(self.h, cid, n, pk, key_stride, pz, pr, po), "ecdsa_verify_sec1")
         return bytes(ok)
@@ -322,9 +383,9 @@ class Engine:
         cid, fb = curve_id(curve), field_bytes(curve)
         n = _nbytes(recid)
         keys, ok = bytearray(n * slot_bytes(cid, flags)), bytearray(n)
-        pz, a = _as_buf(z)
-        pr, b = _as_buf(rs)
-        pi, c = _as_buf(recid)
+        pz, a = _as_buf(z, n * fb, "ecdsa_recover: z")
+        pr, b = _as_buf(rs, n * 2 * fb, "ecdsa_recover: rs")
+        pi, c = _as_buf(recid, n, "ecdsa_recover: recid")
         pk, d = _as_buf(keys)
         po, e = _as_buf(ok)
         self._check(self.lib.ecb200_ecdsa_recover(self.h, cid, n, pz, pr, pi, pk, po, flags), "ecdsa_recover")
@@ -332,21 +393,21 @@ class Engine:
 
     def schnorr_verify(self, pk: bytes, e: bytes, sig: bytes) -> bytes:
         """BIP340 verification after hashing: pk n x 32, e n x 32 challenge digests, sig n x 64."""
-        n = _nbytes(pk) // 32
+        n = _rows(pk, 32, "schnorr_verify: pk")
         ok = bytearray(n)
-        pp, a = _as_buf(pk)
-        pe, b = _as_buf(e)
-        ps, c = _as_buf(sig)
+        pp, a = _as_buf(pk, n * 32, "schnorr_verify: pk")
+        pe, b = _as_buf(e, n * 32, "schnorr_verify: e")
+        ps, c = _as_buf(sig, n * 64, "schnorr_verify: sig")
         po, d = _as_buf(ok)
         self._check(self.lib.ecb200_schnorr_verify(self.h, n, pp, pe, ps, po), "schnorr_verify")
         return bytes(ok)
 
     def sm2dsa_verify(self, q: bytes, e: bytes, rs: bytes) -> bytes:
-        n = _nbytes(e) // 32
+        n = _rows(e, 32, "sm2dsa_verify: e")
         ok = bytearray(n)
-        pq, a = _as_buf(q)
-        pe, b = _as_buf(e)
-        pr, c = _as_buf(rs)
+        pq, a = _as_buf(q, n * 64, "sm2dsa_verify: q")
+        pe, b = _as_buf(e, n * 32, "sm2dsa_verify: e")
+        pr, c = _as_buf(rs, n * 64, "sm2dsa_verify: rs")
         po, d = _as_buf(ok)
         self._check(self.lib.ecb200_sm2dsa_verify(self.h, n, pq, pe, pr, po), "sm2dsa_verify")
         return bytes(ok)
@@ -354,11 +415,11 @@ class Engine:
     def ecdsa_sign(self, curve, d: bytes, k: bytes, z: bytes) -> Tuple[bytes, bytes, bytes]:
         """try_sign_prehashed with caller-supplied nonces -> (r||s, recovery ids, ok)."""
         cid, fb = curve_id(curve), field_bytes(curve)
-        n = _nbytes(z) // fb
+        n = _rows(z, fb, "ecdsa_sign: z")
         rs, rid, ok = bytearray(n * 2 * fb), bytearray(n), bytearray(n)
-        pd, a = _as_buf(d)
-        pk, b = _as_buf(k)
-        pz, c = _as_buf(z)
+        pd, a = _as_buf(d, n * fb, "ecdsa_sign: d")
+        pk, b = _as_buf(k, n * fb, "ecdsa_sign: k")
+        pz, c = _as_buf(z, n * fb, "ecdsa_sign: z")
         pr, e = _as_buf(rs)
         pi, f = _as_buf(rid)
         po, g = _as_buf(ok)
@@ -389,6 +450,11 @@ class Engine:
                                                      self._ptr(d_ok), ctypes.c_void_p(stream) if stream else None),
                     "ecdsa_verify_dev")
 
+
+    def lincomb2_dev(self, curve, n, d_p1, d_k1, d_p2, d_k2, d_out, d_invalid=None, flags=0, stream=None):
+        self._check(self.lib.ecb200_lincomb2_dev(self.h, curve_id(curve), n, self._ptr(d_p1), self._ptr(d_k1), self._ptr(d_p2), self._ptr(d_k2),
+                                                 self._ptr(d_out), self._ptr(d_invalid), flags, ctypes.c_void_p(stream) if stream else None),
+                    "lincomb2_dev")
 
     def ecdsa_verify_sec1_dev(self, curve, n, d_keys, key_stride, d_z, d_rs, d_ok, stream=None):
         self._check(self.lib.ecb200_ecdsa_verify_sec1_dev(self.h, curve_id(curve), n, self._ptr(d_keys), key_stride, self._ptr(d_z),

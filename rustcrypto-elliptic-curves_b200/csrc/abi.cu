@@ -8,12 +8,13 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <thread>
 
 #include "../../include/ecb200.h"
 #include "launch.h"
 
 namespace ecb {
-uint64_t g_launch_count = 0;
+thread_local uint64_t* tl_launch_counter = nullptr;
 }
 using namespace ecb;
 
@@ -102,8 +103,14 @@ struct ecb200_ctx {
     DevBuf partial, one_point;
     DevBuf d_in[NSLOT][4], d_out[NSLOT][3];  // staging for host-pointer entry points
     PinBuf h_in[NSLOT][4], h_out[NSLOT][3];
+    DevBuf proj2, inv2;                      // second product and its invalid flags (per-row two-term lincomb)
     std::string err;
-    uint64_t launches_base = 0;
+    uint64_t launches = 0;                   // kernels launched by this context (launch.h count_launch)
+    // ecb200_init_multi: the parent owns one child context per device and no device state of its own; host entry points
+    // shard [0, n) by contiguous index range over the children, one host thread per device
+    std::vector<ecb200_ctx*> kids;
+    bool held_secrets = false;               // a signing / FLAG_CT call staged secret scalars in this context
+    size_t in_used[NSLOT][4] = {};           // bytes of each staging buffer written by the current call (for wiping)
     // optional per-launch timing of the dominant kernel (verify_main) with CUDA events on its own stream
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -123,6 +130,12 @@ int fail(ecb200_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
         cudaError_t e_ = (call);                                              \
         if (e_ != cudaSuccess) return fail(ctx, ECB200_ERR_CUDA, #call, e_);  \
     } while (0)
+
+// points the launch counter of this host thread at the calling context for the duration of one entry point
+struct Enter {
+    explicit Enter(ecb200_ctx* c) { tl_launch_counter = c ? &c->launches : nullptr; }
+    ~Enter() { tl_launch_counter = nullptr; }
+};
 
 const CurveLaunch* curve_of(ecb200_ctx* c, int curve) {
     if (!c || curve < 0 || curve >= NCURVE) return nullptr;
@@ -456,6 +469,7 @@ int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, co
                     memcpy(c->h_in[slot][k].p, src, bytes);
                     src = c->h_in[slot][k].p;
                 }
+                c->in_used[slot][k] = std::max(c->in_used[slot][k], bytes);
                 CU(c, cudaMemcpyAsync(c->d_in[slot][k].p, src, bytes, cudaMemcpyHostToDevice, c->copy_in));
             }
             for (int k = 0; k < n_out; k++) {
@@ -495,6 +509,87 @@ int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, co
     return 0;
 }
 
+
+// Secret scalars (signing keys, nonces, FLAG_CT scalars) pass through the context's staging buffers, which live until
+// ecb200_destroy and are reused by later calls.  The reference zeroizes such values (Zeroizing / ZeroizeOnDrop on
+// SigningKey and the nonce); here the staged copies are overwritten as soon as the call that brought them has drained:
+// device staging by cudaMemsetAsync, pinned host staging by memset.  mask: bit k = input k of the pipeline is secret.
+int wipe_secret_inputs(ecb200_ctx* c, unsigned mask) {
+    c->held_secrets = true;
+    for (int slot = 0; slot < NSLOT; slot++)
+        for (int k = 0; k < 4; k++) {
+            const size_t used = c->in_used[slot][k];
+            c->in_used[slot][k] = 0;
+            if (!((mask >> k) & 1u) || !used) continue;
+            if (c->d_in[slot][k].p) CU(c, cudaMemsetAsync(c->d_in[slot][k].p, 0, std::min(used, c->d_in[slot][k].cap), c->stream));
+            if (c->h_in[slot][k].p) memset(c->h_in[slot][k].p, 0, std::min(used, c->h_in[slot][k].cap));
+        }
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+void forget_staged(ecb200_ctx* c) { memset(c->in_used, 0, sizeof(c->in_used)); }
+
+// ecb200_init_multi: contiguous index shards [floor(i n / g), floor((i+1) n / g)) over the g child contexts,
+// one host thread per device for the duration of the call; f(child, index, lo, count) runs the single-device entry point.
+template <class F> int multi_run(ecb200_ctx* c, size_t n, bool call_empty, F&& f) {
+    const size_t g = c->kids.size();
+    std::vector<int> rc(g, 0);
+    std::vector<std::thread> th;
+    th.reserve(g);
+    for (size_t i = 0; i < g; i++) {
+        const size_t lo = i * n / g, hi = (i + 1) * n / g;
+        if (hi == lo && !call_empty) continue;
+        th.emplace_back([&rc, &f, c, i, lo, hi] { rc[i] = f(c->kids[i], i, lo, hi - lo); });
+    }
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < g; i++)
+        if (rc[i]) {
+            c->err = "device " + std::to_string(c->kids[i]->device) + ": " + c->kids[i]->err;
+            return rc[i];
+        }
+    return 0;
+}
+template <class T> T* at(T* p, size_t bytes) { return p ? p + bytes : nullptr; }
+
+// per-row two-term linear combination: two products on the ordinary kernels, one complete addition, normalisation
+int lincomb2_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_p1, const uint8_t* d_k1, const uint8_t* d_p2, const uint8_t* d_k2,
+                  uint8_t* d_out, uint8_t* d_invalid, uint32_t flags, cudaStream_t s) {
+    CU(c, c->proj.reserve(n * 3 * (size_t)cl->L * 4));
+    CU(c, c->proj2.reserve(n * 3 * (size_t)cl->L * 4));
+    CU(c, c->inv2.reserve(2 * n));
+    uint32_t *pa = (uint32_t*)c->proj.p, *pb = (uint32_t*)c->proj2.p;
+    uint8_t* inv_a = d_invalid ? d_invalid : (uint8_t*)c->inv2.p + n;
+    uint8_t* inv_b = (uint8_t*)c->inv2.p;
+    const bool proj = (flags & ECB200_FLAG_PROJ) != 0;
+    const uint8_t* pts[2] = {d_p1, d_p2};
+    const uint8_t* ks[2] = {d_k1, d_k2};
+    uint32_t* dst[2] = {pa, pb};
+    uint8_t* inv[2] = {inv_a, inv_b};
+    for (int t = 0; t < 2; t++) {
+        if (flags & ECB200_FLAG_CT) {
+            cl->mul_var(s, true, (int)n, proj ? ECB200_FLAG_PROJ : 0, pts[t], nullptr, ks[t], dst[t], inv[t]);
+            continue;
+        }
+        // public scalars: the Jacobian fast path (projective inputs are normalised first, as in mul_var_core); the
+        // context's affine / window-table scratch is reused by the second product, stream-ordered after the first
+        const uint32_t* aff = nullptr;
+        if (proj) {
+            CU(c, c->aff.reserve(n * 2 * (size_t)cl->L * 4));
+            cl->load_proj(s, (int)n, pts[t], dst[t], nullptr);
+            cl->normalize(s, (int)n, dst[t], 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, (uint32_t*)c->aff.p);
+            aff = (const uint32_t*)c->aff.p;
+        }
+        uint32_t* wt = nullptr;
+        int r = window_tables(c, cl, n, proj ? nullptr : pts[t], aff, s, &wt);
+        if (r) return r;
+        cl->mul_var_fast(s, (int)n, proj ? nullptr : pts[t], aff, nullptr, ks[t], dst[t], inv[t], wt);
+    }
+    cl->add_proj(s, (int)n, pa, pb, pa, inv_a, inv_b);
+    cl->normalize(s, (int)n, pa, 0, resolve_compress(cl, flags) ? 1 : 0, d_out, nullptr, nullptr);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 // ===============================================================================================
@@ -509,7 +604,16 @@ size_t ecb200_point_slot_bytes(int curve, uint32_t flags) {
     bool comp = (flags & ECB200_FLAG_COMPRESSED) ? true : (flags & ECB200_FLAG_UNCOMPRESSED) ? false : (curve == ECB200_K256);
     return 1 + (comp ? fb : 2 * fb);
 }
-const char* ecb200_version(void) { return "ecb200 0.1 (sm_100a)"; }
+const char* ecb200_version(void) { return "ecb200 0.2 (sm_100a)"; }
+
+static void set_launchers(ecb200_ctx* c) {
+    c->cl[0] = launch_k256();
+    c->cl[1] = launch_p256();
+    c->cl[2] = launch_p384();
+    c->cl[3] = launch_sm2();
+    c->cl[4] = launch_p192();
+    c->cl[5] = launch_p224();
+}
 
 int ecb200_init(int device, ecb200_ctx** out) {
     if (!out) return ECB200_ERR_ARG;
@@ -518,13 +622,9 @@ int ecb200_init(int device, ecb200_ctx** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return ECB200_ERR_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return ECB200_ERR_CUDA;
     ecb200_ctx* c = new ecb200_ctx();
+    Enter enter_(c);
     c->device = device;
-    c->cl[0] = launch_k256();
-    c->cl[1] = launch_p256();
-    c->cl[2] = launch_p384();
-    c->cl[3] = launch_sm2();
-    c->cl[4] = launch_p192();
-    c->cl[5] = launch_p224();
+    set_launchers(c);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -540,15 +640,50 @@ int ecb200_init(int device, ecb200_ctx** out) {
         ecb200_destroy(c);
         return ECB200_ERR_CUDA;
     }
-    c->launches_base = g_launch_count;
+    c->launches = 0;     // table construction is not the caller's work
     *out = c;
     return 0;
 }
 
+int ecb200_init_multi(int n_dev, const int* devices, ecb200_ctx** out) {
+    if (!out) return ECB200_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return ECB200_ERR_CUDA;
+    if (n_dev <= 0) { if (devices) return ECB200_ERR_ARG; n_dev = ndev; }
+    if (n_dev > 64) return ECB200_ERR_ARG;
+    for (int i = 0; devices && i < n_dev; i++)     // an ordinal may repeat: two shards (two child contexts) on one device
+        if (devices[i] < 0 || devices[i] >= ndev) return ECB200_ERR_ARG;
+    if (!devices && n_dev > ndev) return ECB200_ERR_CUDA;
+    ecb200_ctx* c = new ecb200_ctx();
+    c->device = -1;
+    set_launchers(c);
+    for (int i = 0; i < n_dev; i++) {
+        ecb200_ctx* kid = nullptr;
+        int r = ecb200_init(devices ? devices[i] : i, &kid);
+        if (r) { ecb200_destroy(c); return r; }
+        c->kids.push_back(kid);
+    }
+    *out = c;
+    return 0;
+}
+int ecb200_device_count(const ecb200_ctx* c) { return !c ? 0 : c->kids.empty() ? 1 : (int)c->kids.size(); }
+
 void ecb200_destroy(ecb200_ctx* c) {
     if (!c) return;
+    if (!c->kids.empty() || c->device < 0) {
+        for (ecb200_ctx* k : c->kids) ecb200_destroy(k);
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->held_secrets)   // belt and braces: secret staging was wiped after each call (wipe_secret_inputs)
+        for (int s = 0; s < NSLOT; s++)
+            for (int k = 0; k < 4; k++) {
+                if (c->d_in[s][k].p) cudaMemset(c->d_in[s][k].p, 0, c->d_in[s][k].cap);
+                if (c->h_in[s][k].p) memset(c->h_in[s][k].p, 0, c->h_in[s][k].cap);
+            }
     for (int i = 0; i < NCURVE; i++) {
         if (c->gtab[i]) cudaFree(c->gtab[i]);
         if (c->gentab[i]) cudaFree(c->gentab[i]);
@@ -560,6 +695,8 @@ void ecb200_destroy(ecb200_ctx* c) {
     c->kxy.release();
     c->kst.release();
     c->proj.release();
+    c->proj2.release();
+    c->inv2.release();
     c->partial.release();
     c->one_point.release();
     for (int s = 0; s < NSLOT; s++) {
@@ -569,6 +706,7 @@ void ecb200_destroy(ecb200_ctx* c) {
         if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]);
         if (c->ev_out[s]) cudaEventDestroy(c->ev_out[s]);
     }
+    for (auto& pr : c->timed) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
@@ -576,9 +714,16 @@ void ecb200_destroy(ecb200_ctx* c) {
 }
 
 const char* ecb200_last_error(const ecb200_ctx* c) { return c ? c->err.c_str() : "null context"; }
-uint64_t ecb200_launch_count(const ecb200_ctx* c) { return c ? g_launch_count - c->launches_base : 0; }
+uint64_t ecb200_launch_count(const ecb200_ctx* c) {
+    if (!c) return 0;
+    uint64_t t = c->launches;
+    for (const ecb200_ctx* k : c->kids) t += k->launches;
+    return t;
+}
 int ecb200_sync(ecb200_ctx* c) {
     if (!c) return ECB200_ERR_ARG;
+    for (ecb200_ctx* k : c->kids) { int r = ecb200_sync(k); if (r) return r; }
+    if (!c->kids.empty()) return 0;
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
     return 0;
@@ -587,10 +732,21 @@ int ecb200_sync(ecb200_ctx* c) {
 int ecb200_kernel_timing(ecb200_ctx* c, int enable) {
     if (!c) return ECB200_ERR_ARG;
     c->timing = enable != 0;
+    for (ecb200_ctx* k : c->kids) k->timing = enable != 0;
     return 0;
 }
 int ecb200_kernel_timing_read(ecb200_ctx* c, double* total_ms, uint64_t* launches) {
     if (!c || !total_ms || !launches) return ECB200_ERR_ARG;
+    if (!c->kids.empty()) {   // sum over the devices (each device times its own launches)
+        *total_ms = 0; *launches = 0;
+        for (ecb200_ctx* k : c->kids) {
+            double ms = 0; uint64_t cnt = 0;
+            int r = ecb200_kernel_timing_read(k, &ms, &cnt);
+            if (r) return r;
+            *total_ms += ms; *launches += cnt;
+        }
+        return 0;
+    }
     CU(c, cudaSetDevice(c->device));
     double sum = 0;
     for (auto& pr : c->timed) {
@@ -607,10 +763,16 @@ int ecb200_kernel_timing_read(ecb200_ctx* c, double* total_ms, uint64_t* launche
     return 0;
 }
 
+// device pointers belong to one device: the _dev entry points refuse a multi-device context
+#define DEV_ENTER(c, name)                                                                                     \
+    if ((c) && !(c)->kids.empty()) return fail(c, ECB200_ERR_ARG, name ": device-pointer calls need a single-device context"); \
+    Enter enter_(c)
+
 // ---- device-pointer entry points
 int ecb200_mul_gen_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_k, uint8_t* d_out, uint32_t flags, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || n > MAX_ROWS || (n && (!d_k || !d_out))) return fail(c, ECB200_ERR_ARG, "mul_gen_dev: bad argument");
+    DEV_ENTER(c, "mul_gen_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return mul_gen_core(c, cl, n, d_k, d_out, flags, pick(c, stream));
@@ -619,6 +781,7 @@ int ecb200_mul_var_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_pts,
                        uint8_t* d_out, uint8_t* d_invalid, uint32_t flags, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || n > MAX_ROWS || (n && (!d_pts || !d_k || !d_out))) return fail(c, ECB200_ERR_ARG, "mul_var_dev: bad argument");
+    DEV_ENTER(c, "mul_var_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return mul_var_core(c, cl, n, d_pts, d_inf, d_k, d_out, d_invalid, flags, pick(c, stream));
@@ -626,6 +789,7 @@ int ecb200_mul_var_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_pts,
 int ecb200_batch_normalize_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_xyz, uint8_t* d_xy, uint8_t* d_inf, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || n > MAX_ROWS || (n && (!d_xyz || !d_xy))) return fail(c, ECB200_ERR_ARG, "batch_normalize_dev: bad argument");
+    DEV_ENTER(c, "batch_normalize_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return batch_normalize_core(c, cl, n, d_xyz, d_xy, d_inf, pick(c, stream));
@@ -634,46 +798,81 @@ int ecb200_ecdsa_verify_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d
                             uint8_t* d_ok, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || n > MAX_ROWS || (n && (!d_q || !d_z || !d_rs || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_verify_dev: bad argument");
+    DEV_ENTER(c, "ecdsa_verify_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return verify_core(c, cl, n, d_q, d_z, d_rs, d_ok, pick(c, stream));
+}
+int ecb200_lincomb2_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_p1, const uint8_t* d_k1, const uint8_t* d_p2, const uint8_t* d_k2,
+                        uint8_t* d_out, uint8_t* d_invalid, uint32_t flags, void* stream) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || n > MAX_ROWS || (n && (!d_p1 || !d_k1 || !d_p2 || !d_k2 || !d_out)))
+        return fail(c, ECB200_ERR_ARG, "lincomb2_dev: bad argument");
+    DEV_ENTER(c, "lincomb2_dev");
+    if (!n) return 0;
+    CU(c, cudaSetDevice(c->device));
+    return lincomb2_core(c, cl, n, d_p1, d_k1, d_p2, d_k2, d_out, d_invalid, flags, pick(c, stream));
 }
 
 // ---- host-pointer entry points
 int ecb200_mul_gen(ecb200_ctx* c, int curve, size_t n, const uint8_t* k, uint8_t* out, uint32_t flags) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || (n && (!k || !out))) return fail(c, ECB200_ERR_ARG, "mul_gen: bad argument");
+    const size_t FB = cl->FB, SB = slot_bytes(cl, flags);
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_mul_gen(kid, curve, cnt, k + lo * FB, out + lo * SB, flags);
+        });
+    Enter enter_(c);
     CU(c, cudaSetDevice(c->device));
     const uint8_t* in[1] = {k};
-    size_t in_sz[1] = {(size_t)cl->FB};
+    size_t in_sz[1] = {FB};
     uint8_t* o[1] = {out};
-    size_t o_sz[1] = {slot_bytes(cl, flags)};
-    return run_pipeline(c, n, 1, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+    size_t o_sz[1] = {SB};
+    forget_staged(c);
+    int r = run_pipeline(c, n, 1, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
         return mul_gen_core(c, cl, cnt, di[0], dout[0], flags, s);
     });
+    if ((flags & ECB200_FLAG_CT) && n) { int w = wipe_secret_inputs(c, 1u); if (!r) r = w; }
+    return r;
 }
 int ecb200_mul_var(ecb200_ctx* c, int curve, size_t n, const uint8_t* pts, const uint8_t* inf, const uint8_t* k, uint8_t* out,
                    uint8_t* invalid, uint32_t flags) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || (n && (!pts || !k || !out))) return fail(c, ECB200_ERR_ARG, "mul_var: bad argument");
-    CU(c, cudaSetDevice(c->device));
     const bool proj = (flags & ECB200_FLAG_PROJ) != 0;
+    const size_t FB = cl->FB, PB = FB * (proj ? 3 : 2), SB = slot_bytes(cl, flags);
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_mul_var(kid, curve, cnt, pts + lo * PB, at(inf, lo), k + lo * FB, out + lo * SB, at(invalid, lo), flags);
+        });
+    Enter enter_(c);
+    CU(c, cudaSetDevice(c->device));
     const uint8_t* in[3] = {pts, k, proj ? nullptr : inf};
-    size_t in_sz[3] = {(size_t)cl->FB * (proj ? 3 : 2), (size_t)cl->FB, 1};
+    size_t in_sz[3] = {PB, FB, 1};
     uint8_t* o[2] = {out, invalid};
-    size_t o_sz[2] = {slot_bytes(cl, flags), 1};
-    return run_pipeline(c, n, 3, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+    size_t o_sz[2] = {SB, 1};
+    forget_staged(c);
+    int r = run_pipeline(c, n, 3, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
         return mul_var_core(c, cl, cnt, di[0], di[2], di[1], dout[0], dout[1], flags, s);
     });
+    if ((flags & ECB200_FLAG_CT) && n) { int w = wipe_secret_inputs(c, 2u); if (!r) r = w; }
+    return r;
 }
 int ecb200_batch_normalize(ecb200_ctx* c, int curve, size_t n, const uint8_t* xyz, uint8_t* xy, uint8_t* inf) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || (n && (!xyz || !xy))) return fail(c, ECB200_ERR_ARG, "batch_normalize: bad argument");
+    const size_t FB = cl->FB;
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_batch_normalize(kid, curve, cnt, xyz + lo * 3 * FB, xy + lo * 2 * FB, at(inf, lo));
+        });
+    Enter enter_(c);
     CU(c, cudaSetDevice(c->device));
     const uint8_t* in[1] = {xyz};
-    size_t in_sz[1] = {(size_t)cl->FB * 3};
+    size_t in_sz[1] = {FB * 3};
     uint8_t* o[2] = {xy, inf};
-    size_t o_sz[2] = {(size_t)cl->FB * 2, 1};
+    size_t o_sz[2] = {FB * 2, 1};
     return run_pipeline(c, n, 1, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
         return batch_normalize_core(c, cl, cnt, di[0], dout[0], dout[1], s);
     });
@@ -681,9 +880,15 @@ int ecb200_batch_normalize(ecb200_ctx* c, int curve, size_t n, const uint8_t* xy
 int ecb200_ecdsa_verify(ecb200_ctx* c, int curve, size_t n, const uint8_t* q, const uint8_t* z, const uint8_t* rs, uint8_t* ok) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || (n && (!q || !z || !rs || !ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_verify: bad argument");
+    const size_t FB = cl->FB;
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_ecdsa_verify(kid, curve, cnt, q + lo * 2 * FB, z + lo * FB, rs + lo * 2 * FB, ok + lo);
+        });
+    Enter enter_(c);
     CU(c, cudaSetDevice(c->device));
     const uint8_t* in[3] = {q, z, rs};
-    size_t in_sz[3] = {(size_t)cl->FB * 2, (size_t)cl->FB, (size_t)cl->FB * 2};
+    size_t in_sz[3] = {FB * 2, FB, FB * 2};
     uint8_t* o[1] = {ok};
     size_t o_sz[1] = {1};
     return run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
@@ -693,29 +898,73 @@ int ecb200_ecdsa_verify(ecb200_ctx* c, int curve, size_t n, const uint8_t* q, co
 int ecb200_field_op(ecb200_ctx* c, int curve, int which, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* ok) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || which < 0 || which > 1 || op < 0 || op > 6 || (n && (!a || !out || !ok))) return fail(c, ECB200_ERR_ARG, "field_op: bad argument");
+    const size_t FB = cl->FB;
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_field_op(kid, curve, which, op, cnt, a + lo * FB, at(b, lo * FB), out + lo * FB, ok + lo);
+        });
+    Enter enter_(c);
     CU(c, cudaSetDevice(c->device));
     const uint8_t* in[2] = {a, b};
-    size_t in_sz[2] = {(size_t)cl->FB, (size_t)cl->FB};
+    size_t in_sz[2] = {FB, FB};
     uint8_t* o[2] = {out, ok};
-    size_t o_sz[2] = {(size_t)cl->FB, 1};
+    size_t o_sz[2] = {FB, 1};
     return run_pipeline(c, n, 2, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
         cl->field_op(s, (int)cnt, which, op, di[0], di[1], dout[0], dout[1]);
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? 0 : fail(c, ECB200_ERR_CUDA, "field_op launch", e);
     });
 }
+int ecb200_lincomb2(ecb200_ctx* c, int curve, size_t n, const uint8_t* p1, const uint8_t* k1, const uint8_t* p2, const uint8_t* k2, uint8_t* out,
+                    uint8_t* invalid, uint32_t flags) {
+    const CurveLaunch* cl = curve_of(c, curve);
+    if (!cl || (n && (!p1 || !k1 || !p2 || !k2 || !out))) return fail(c, ECB200_ERR_ARG, "lincomb2: bad argument");
+    const size_t FB = cl->FB, SB = slot_bytes(cl, flags), PB = FB * ((flags & ECB200_FLAG_PROJ) ? 3 : 2);
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_lincomb2(kid, curve, cnt, p1 + lo * PB, k1 + lo * FB, p2 + lo * PB, k2 + lo * FB, out + lo * SB, at(invalid, lo), flags);
+        });
+    Enter enter_(c);
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* in[4] = {p1, k1, p2, k2};
+    size_t in_sz[4] = {PB, FB, PB, FB};
+    uint8_t* o[2] = {out, invalid};
+    size_t o_sz[2] = {SB, 1};
+    forget_staged(c);
+    int r = run_pipeline(c, n, 4, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+        return lincomb2_core(c, cl, cnt, di[0], di[1], di[2], di[3], dout[0], dout[1], flags, s);
+    });
+    if ((flags & ECB200_FLAG_CT) && n) { int w = wipe_secret_inputs(c, 2u | 8u); if (!r) r = w; }
+    return r;
+}
 int ecb200_lincomb(ecb200_ctx* c, int curve, size_t n_terms, const uint8_t* pts, const uint8_t* k, uint8_t* out_point, uint32_t flags,
                    uint32_t out_flags_proj) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || !out_point || (n_terms && (!pts || !k))) return fail(c, ECB200_ERR_ARG, "lincomb: bad argument");
-    CU(c, cudaSetDevice(c->device));
     const int L = cl->L, FB = cl->FB;
     const bool proj = (flags & ECB200_FLAG_PROJ) != 0;
     const size_t psz = (size_t)FB * (proj ? 3 : 2);
+    if (!c->kids.empty()) {
+        // every device reduces its index shard of the terms to ONE projective partial; the <= 8 partials (3 FB bytes each)
+        // come back to the host and the first device adds them (scalars = 1) - the only exchange on this path
+        const size_t g = c->kids.size();
+        std::vector<uint8_t> partials(g * 3 * FB), ones(g * FB, 0);
+        for (size_t i = 0; i < g; i++) ones[i * FB + FB - 1] = 1;
+        int r = multi_run(c, n_terms, true, [&](ecb200_ctx* kid, size_t i, size_t lo, size_t cnt) {
+            return ecb200_lincomb(kid, curve, cnt, at(pts, lo * psz), at(k, lo * FB), &partials[i * 3 * FB], flags, ECB200_FLAG_PROJ);
+        });
+        if (r) return r;
+        r = ecb200_lincomb(c->kids[0], curve, g, partials.data(), ones.data(), out_point, (flags & ~ECB200_FLAG_CT) | ECB200_FLAG_PROJ, out_flags_proj);
+        if (r) c->err = c->kids[0]->err;
+        return r;
+    }
+    Enter enter_(c);
+    CU(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     CU(c, c->proj.reserve(std::max<size_t>(n_terms, 1) * 3 * L * 4));
     CU(c, c->partial.reserve((size_t)cl->sum_blocks * 3 * L * 4));
     CU(c, c->one_point.reserve((size_t)3 * L * 4 + 3 * FB + 256));
+    CU(c, c->inv2.reserve(std::max<size_t>(n_terms, 1)));
     // terms are processed in CHUNK pieces; each piece's products land in c->proj at its offset
     for (size_t off = 0; off < n_terms; off += CHUNK) {
         size_t cnt = std::min(CHUNK, n_terms - off);
@@ -723,13 +972,24 @@ int ecb200_lincomb(ecb200_ctx* c, int curve, size_t n_terms, const uint8_t* pts,
         CU(c, c->d_in[0][1].reserve(cnt * FB));
         CU(c, cudaMemcpyAsync(c->d_in[0][0].p, pts + off * psz, cnt * psz, cudaMemcpyHostToDevice, s));
         CU(c, cudaMemcpyAsync(c->d_in[0][1].p, k + off * FB, cnt * FB, cudaMemcpyHostToDevice, s));
+        uint8_t* inv = (uint8_t*)c->inv2.p + off;
         if ((flags & ECB200_FLAG_CT) || proj)
             cl->mul_var(s, (flags & ECB200_FLAG_CT) != 0, (int)cnt, flags, (const uint8_t*)c->d_in[0][0].p, nullptr,
-                        (const uint8_t*)c->d_in[0][1].p, (uint32_t*)c->proj.p + off * 3 * L, nullptr);
+                        (const uint8_t*)c->d_in[0][1].p, (uint32_t*)c->proj.p + off * 3 * L, inv);
         else
             cl->mul_var_fast(s, (int)cnt, (const uint8_t*)c->d_in[0][0].p, nullptr, nullptr, (const uint8_t*)c->d_in[0][1].p,
-                             (uint32_t*)c->proj.p + off * 3 * L, nullptr, nullptr);
+                             (uint32_t*)c->proj.p + off * 3 * L, inv, nullptr);
+        if (flags & ECB200_FLAG_CT) CU(c, cudaMemsetAsync(c->d_in[0][1].p, 0, cnt * FB, s));   // secret scalars do not outlive their piece
         CU(c, cudaStreamSynchronize(s));   // staging buffers are reused by the next piece
+    }
+    // A term that fails validation (coordinate >= p, affine point off the curve) cannot be represented in the reference at
+    // all; dropping it silently would return a wrong sum with status 0, so the whole call fails instead.
+    if (n_terms) {
+        std::vector<uint8_t> inv(n_terms);
+        CU(c, cudaMemcpyAsync(inv.data(), c->inv2.p, n_terms, cudaMemcpyDeviceToHost, s));
+        CU(c, cudaStreamSynchronize(s));
+        for (size_t i = 0; i < n_terms; i++)
+            if (inv[i]) return fail(c, ECB200_ERR_POINT, ("lincomb: term " + std::to_string(i) + " is not a valid point").c_str());
     }
     uint32_t* d_sum = (uint32_t*)c->one_point.p;
     uint8_t* d_bytes = (uint8_t*)c->one_point.p + 3 * L * 4;
@@ -755,6 +1015,7 @@ int ecb200_decode_points_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* 
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || n > MAX_ROWS || mode > 1 || (n && (!d_enc || !d_xy || !d_status)) || stride < (size_t)cl->FB + (mode == DEC_SEC1 ? 1 : 0))
         return fail(c, ECB200_ERR_ARG, "decode_points_dev: bad argument");
+    DEV_ENTER(c, "decode_points_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return decode_core(c, cl, n, d_enc, stride, (int)mode, d_xy, d_status, pick(c, stream));
@@ -763,11 +1024,17 @@ int ecb200_decode_points(ecb200_ctx* c, int curve, size_t n, const uint8_t* enc,
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || mode > 1 || (n && (!enc || !xy || !status)) || stride < (size_t)cl->FB + (mode == DEC_SEC1 ? 1 : 0))
         return fail(c, ECB200_ERR_ARG, "decode_points: bad argument");
+    const size_t FB = cl->FB;
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_decode_points(kid, curve, cnt, enc + lo * stride, stride, mode, xy + lo * 2 * FB, status + lo);
+        });
+    Enter enter_(c);
     CU(c, cudaSetDevice(c->device));
     const uint8_t* in[1] = {enc};
     size_t in_sz[1] = {stride};
     uint8_t* o[2] = {xy, status};
-    size_t o_sz[2] = {(size_t)cl->FB * 2, 1};
+    size_t o_sz[2] = {FB * 2, 1};
     return run_pipeline(c, n, 1, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
         return decode_core(c, cl, cnt, di[0], stride, (int)mode, dout[0], dout[1], s);
     });
@@ -776,6 +1043,7 @@ int ecb200_ecdsa_verify_sec1_dev(ecb200_ctx* c, int curve, size_t n, const uint8
                                  uint8_t* d_ok, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || n > MAX_ROWS || (n && (!d_keys || !d_z || !d_rs || !d_ok)) || key_stride < (size_t)cl->FB + 1) return fail(c, ECB200_ERR_ARG, "ecdsa_verify_sec1_dev: bad argument");
+    DEV_ENTER(c, "ecdsa_verify_sec1_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return verify_sec1_core(c, cl, n, d_keys, key_stride, d_z, d_rs, d_ok, pick(c, stream));
@@ -783,9 +1051,15 @@ int ecb200_ecdsa_verify_sec1_dev(ecb200_ctx* c, int curve, size_t n, const uint8
 int ecb200_ecdsa_verify_sec1(ecb200_ctx* c, int curve, size_t n, const uint8_t* keys, size_t key_stride, const uint8_t* z, const uint8_t* rs, uint8_t* ok) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || (n && (!keys || !z || !rs || !ok)) || key_stride < (size_t)cl->FB + 1) return fail(c, ECB200_ERR_ARG, "ecdsa_verify_sec1: bad argument");
+    const size_t FB = cl->FB;
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_ecdsa_verify_sec1(kid, curve, cnt, keys + lo * key_stride, key_stride, z + lo * FB, rs + lo * 2 * FB, ok + lo);
+        });
+    Enter enter_(c);
     CU(c, cudaSetDevice(c->device));
     const uint8_t* in[3] = {keys, z, rs};
-    size_t in_sz[3] = {key_stride, (size_t)cl->FB, (size_t)cl->FB * 2};
+    size_t in_sz[3] = {key_stride, FB, FB * 2};
     uint8_t* o[1] = {ok};
     size_t o_sz[1] = {1};
     return run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
@@ -796,6 +1070,7 @@ int ecb200_ecdsa_recover_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* 
                              uint8_t* d_ok, uint32_t flags, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || n > MAX_ROWS || (n && (!d_z || !d_rs || !d_recid || !d_keys || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_recover_dev: bad argument");
+    DEV_ENTER(c, "ecdsa_recover_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return recover_core(c, cl, n, d_z, d_rs, d_recid, d_keys, d_ok, flags, pick(c, stream));
@@ -804,11 +1079,17 @@ int ecb200_ecdsa_recover(ecb200_ctx* c, int curve, size_t n, const uint8_t* z, c
                          uint32_t flags) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || (n && (!z || !rs || !recid || !keys || !ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_recover: bad argument");
+    const size_t FB = cl->FB, SB = slot_bytes(cl, flags);
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_ecdsa_recover(kid, curve, cnt, z + lo * FB, rs + lo * 2 * FB, recid + lo, keys + lo * SB, ok + lo, flags);
+        });
+    Enter enter_(c);
     CU(c, cudaSetDevice(c->device));
     const uint8_t* in[3] = {z, rs, recid};
-    size_t in_sz[3] = {(size_t)cl->FB, (size_t)cl->FB * 2, 1};
+    size_t in_sz[3] = {FB, FB * 2, 1};
     uint8_t* o[2] = {keys, ok};
-    size_t o_sz[2] = {slot_bytes(cl, flags), 1};
+    size_t o_sz[2] = {SB, 1};
     return run_pipeline(c, n, 3, in, in_sz, 2, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
         return recover_core(c, cl, cnt, di[0], di[1], di[2], dout[0], dout[1], flags, s);
     });
@@ -816,6 +1097,7 @@ int ecb200_ecdsa_recover(ecb200_ctx* c, int curve, size_t n, const uint8_t* z, c
 int ecb200_schnorr_verify_dev(ecb200_ctx* c, size_t n, const uint8_t* d_pk, const uint8_t* d_e, const uint8_t* d_sig, uint8_t* d_ok, void* stream) {
     const CurveLaunch* cl = curve_of(c, ECB200_K256);
     if (!cl || n > MAX_ROWS || (n && (!d_pk || !d_e || !d_sig || !d_ok))) return fail(c, ECB200_ERR_ARG, "schnorr_verify_dev: bad argument");
+    DEV_ENTER(c, "schnorr_verify_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return schnorr_core(c, cl, n, d_pk, d_e, d_sig, d_ok, pick(c, stream));
@@ -823,6 +1105,11 @@ int ecb200_schnorr_verify_dev(ecb200_ctx* c, size_t n, const uint8_t* d_pk, cons
 int ecb200_schnorr_verify(ecb200_ctx* c, size_t n, const uint8_t* pk, const uint8_t* e, const uint8_t* sig, uint8_t* ok) {
     const CurveLaunch* cl = curve_of(c, ECB200_K256);
     if (!cl || (n && (!pk || !e || !sig || !ok))) return fail(c, ECB200_ERR_ARG, "schnorr_verify: bad argument");
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_schnorr_verify(kid, cnt, pk + lo * 32, e + lo * 32, sig + lo * 64, ok + lo);
+        });
+    Enter enter_(c);
     CU(c, cudaSetDevice(c->device));
     const uint8_t* in[3] = {pk, e, sig};
     size_t in_sz[3] = {32, 32, 64};
@@ -835,6 +1122,7 @@ int ecb200_schnorr_verify(ecb200_ctx* c, size_t n, const uint8_t* pk, const uint
 int ecb200_sm2dsa_verify_dev(ecb200_ctx* c, size_t n, const uint8_t* d_q, const uint8_t* d_e, const uint8_t* d_rs, uint8_t* d_ok, void* stream) {
     const CurveLaunch* cl = curve_of(c, ECB200_SM2);
     if (!cl || n > MAX_ROWS || (n && (!d_q || !d_e || !d_rs || !d_ok))) return fail(c, ECB200_ERR_ARG, "sm2dsa_verify_dev: bad argument");
+    DEV_ENTER(c, "sm2dsa_verify_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return verify_core(c, cl, n, d_q, d_e, d_rs, d_ok, pick(c, stream), VM_SM2DSA);
@@ -842,6 +1130,11 @@ int ecb200_sm2dsa_verify_dev(ecb200_ctx* c, size_t n, const uint8_t* d_q, const 
 int ecb200_sm2dsa_verify(ecb200_ctx* c, size_t n, const uint8_t* q, const uint8_t* e, const uint8_t* rs, uint8_t* ok) {
     const CurveLaunch* cl = curve_of(c, ECB200_SM2);
     if (!cl || (n && (!q || !e || !rs || !ok))) return fail(c, ECB200_ERR_ARG, "sm2dsa_verify: bad argument");
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_sm2dsa_verify(kid, cnt, q + lo * 64, e + lo * 32, rs + lo * 64, ok + lo);
+        });
+    Enter enter_(c);
     CU(c, cudaSetDevice(c->device));
     const uint8_t* in[3] = {q, e, rs};
     size_t in_sz[3] = {64, 32, 64};
@@ -855,6 +1148,7 @@ int ecb200_ecdsa_sign_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_d
                           uint8_t* d_ok, void* stream) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || n > MAX_ROWS || (n && (!d_d || !d_k || !d_z || !d_rs || !d_recid || !d_ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_sign_dev: bad argument");
+    DEV_ENTER(c, "ecdsa_sign_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
     return sign_core(c, cl, n, d_d, d_k, d_z, d_rs, d_recid, d_ok, pick(c, stream));
@@ -862,14 +1156,23 @@ int ecb200_ecdsa_sign_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_d
 int ecb200_ecdsa_sign(ecb200_ctx* c, int curve, size_t n, const uint8_t* d, const uint8_t* k, const uint8_t* z, uint8_t* rs, uint8_t* recid, uint8_t* ok) {
     const CurveLaunch* cl = curve_of(c, curve);
     if (!cl || (n && (!d || !k || !z || !rs || !recid || !ok))) return fail(c, ECB200_ERR_ARG, "ecdsa_sign: bad argument");
+    const size_t FB = cl->FB;
+    if (!c->kids.empty())
+        return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {
+            return ecb200_ecdsa_sign(kid, curve, cnt, d + lo * FB, k + lo * FB, z + lo * FB, rs + lo * 2 * FB, recid + lo, ok + lo);
+        });
+    Enter enter_(c);
     CU(c, cudaSetDevice(c->device));
     const uint8_t* in[3] = {d, k, z};
-    size_t in_sz[3] = {(size_t)cl->FB, (size_t)cl->FB, (size_t)cl->FB};
+    size_t in_sz[3] = {FB, FB, FB};
     uint8_t* o[3] = {rs, recid, ok};
-    size_t o_sz[3] = {(size_t)cl->FB * 2, 1, 1};
-    return run_pipeline(c, n, 3, in, in_sz, 3, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+    size_t o_sz[3] = {FB * 2, 1, 1};
+    forget_staged(c);
+    int r = run_pipeline(c, n, 3, in, in_sz, 3, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
         return sign_core(c, cl, cnt, di[0], di[1], di[2], dout[0], dout[1], dout[2], s);
     });
+    if (n) { int w = wipe_secret_inputs(c, 1u | 2u); if (!r) r = w; }   // d and k (Zeroizing / ZeroizeOnDrop in the reference)
+    return r;
 }
 
 }  // extern "C"

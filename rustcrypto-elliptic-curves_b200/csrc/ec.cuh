@@ -228,8 +228,13 @@ template <class C> struct EC {
 #pragma unroll 1
 #endif
         for (int j = 2; j < N; j++) {
-            if ((j & 1) == 0) dbl(t.e[j], t.e[j >> 1]);
-            else add(t.e[j], t.e[j - 1], p);
+            // operands and result go through named temporaries: a dynamically indexed element of a local array passed by
+            // reference to the non-inlined point functions once produced wrong results (kernels.cuh lincomb_g_q, nvcc 12.9
+            // for sm_100a; root cause not isolated), so no call here ever sees such a reference
+            Proj src = t.e[(j & 1) == 0 ? (j >> 1) : (j - 1)], dst;
+            if ((j & 1) == 0) dbl(dst, src);
+            else add(dst, src, p);
+            t.e[j] = dst;
         }
     }
     // constant-time |idx| lookup: scan every entry, masked move (k256 mul.rs:92-127,

@@ -3,6 +3,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "launch.h"
+#include <atomic>
 
 namespace ecb {
 
@@ -204,6 +205,20 @@ template <class C> __global__ void __launch_bounds__(BLK) k_proj_to_bytes(int n,
     C::F::to_limbs(t, p.Y); store_be<C::L>(xyz + (size_t)tid * 3 * C::FB + C::FB, t);
     C::F::to_limbs(t, p.Z); store_be<C::L>(xyz + (size_t)tid * 3 * C::FB + 2 * C::FB, t);
 }
+// out[i] = a[i] + b[i] (complete addition on internal projective limbs): the tail of the per-row two-term lincomb
+template <class C> __global__ void __launch_bounds__(BLK) k_add_proj(int n, const u32* a, const u32* b, u32* out, u8* invalid, const u8* invalid_b) {
+    int tid = blockIdx.x * BLK + threadIdx.x;
+    if (tid >= n) return;
+    typedef Bodies<C> B;
+    typename B::Proj p, q, r;
+    B::load_proj_limbs(p, a + (size_t)tid * 3 * C::L);
+    B::load_proj_limbs(q, b + (size_t)tid * 3 * C::L);
+    EC<C>::add(r, p, q);
+    u32 bad = (invalid ? invalid[tid] : 0u) | (invalid_b ? invalid_b[tid] : 0u);
+    if (bad) EC<C>::set_identity(r);          // an invalid term voids the row (the reference cannot represent such a point)
+    B::store_proj(out + (size_t)tid * 3 * C::L, r);
+    if (invalid) invalid[tid] = bad ? 1 : 0;
+}
 // block-level sum of projective points: thread-strided partials, then a shared-memory tree
 template <class C> __global__ void __launch_bounds__(BLK) k_sum(int n, const u32* proj, u32* out) {
     typedef Bodies<C> B;
@@ -259,42 +274,41 @@ template <class C> struct Launch {
     static int grid(int n) { return (n + BLK - 1) / BLK; }
     // The opt-in for > 48 KB of dynamic shared memory is per function AND per device: remember it per device, so a process
     // that drives several GPUs (one context each) sets it on every one of them.
-    static bool first_use_on_device(bool (&seen)[64]) {
+    // (atomic: under ecb200_init_multi one host thread per device runs these launchers concurrently)
+    static bool first_use_on_device(std::atomic<bool> (&seen)[64]) {
         int dev = 0;
         cudaGetDevice(&dev);
         if (dev < 0 || dev >= 64) return true;
-        if (seen[dev]) return false;
-        seen[dev] = true;
-        return true;
+        return !seen[dev].exchange(true);
     }
 
     static void field_op(cudaStream_t s, int n, int which, int op, const u8* a, const u8* b, u8* out, u8* ok) {
         if (n <= 0) return;
         k_field_op<C><<<grid(n), BLK, 0, s>>>(n, which, op, a, b, out, ok);
-        g_launch_count++;
+        count_launch();
     }
     static void mul_var(cudaStream_t s, bool ct, int n, u32 flags, const u8* pts, const u8* inf, const u8* k, u32* proj, u8* invalid) {
         if (n <= 0) return;
         if (ct) k_mul_var<C, true><<<grid(n), BLK, 0, s>>>(n, flags, pts, inf, k, proj, invalid);
         else k_mul_var<C, false><<<grid(n), BLK, 0, s>>>(n, flags, pts, inf, k, proj, invalid);
-        g_launch_count++;
+        count_launch();
     }
     static void mul_gen(cudaStream_t s, bool ct, int n, const u8* k, const u32* tab, u32* proj) {
         if (n <= 0) return;
         const u32 bytes = (u32)Bodies<C>::GEN_WINDOWS * 8u * 2u * C::L * 4u;   // 33 KB (L = 8), 74.5 KB (L = 12)
-        static bool seen[64] = {};
+        static std::atomic<bool> seen[64] = {};
         if (first_use_on_device(seen)) {
             cudaFuncSetAttribute(k_mul_gen_smem<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
             cudaFuncSetAttribute(k_mul_gen_smem<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         }
         if (ct) k_mul_gen_smem<C, true><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
         else k_mul_gen_smem<C, false><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
-        g_launch_count++;
+        count_launch();
     }
     static void load_proj(cudaStream_t s, int n, const u8* xyz, u32* proj, u8* invalid) {
         if (n <= 0) return;
         k_load_proj<C><<<grid(n), BLK, 0, s>>>(n, xyz, proj, invalid);
-        g_launch_count++;
+        count_launch();
     }
     static void normalize(cudaStream_t s, int n, const u32* proj, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
         if (n <= 0) return;
@@ -307,7 +321,7 @@ template <class C> struct Launch {
         if (ept > Bodies<C>::EPT) ept = Bodies<C>::EPT;
         int threads = (n + ept - 1) / ept;
         k_normalize<C><<<grid(threads), BLK, 0, s>>>(n, proj, mode, compress, out_bytes, out_inf, out_limbs);
-        g_launch_count++;
+        count_launch();
     }
     static constexpr int SUM_BLOCKS = 148;
     static void sum(cudaStream_t s, int n, const u32* proj, u32* partial, u32* out) {
@@ -316,22 +330,27 @@ template <class C> struct Launch {
         if (blocks < 1) blocks = 1;
         if (blocks == 1) {
             k_sum<C><<<1, BLK, 0, s>>>(n, proj, out);
-            g_launch_count++;
+            count_launch();
         } else {
             k_sum<C><<<blocks, BLK, 0, s>>>(n, proj, partial);
             k_sum<C><<<1, BLK, 0, s>>>(blocks, partial, out);
-            g_launch_count += 2;
+            count_launch(2);
         }
+    }
+    static void add_proj(cudaStream_t s, int n, const u32* a, const u32* b, u32* out, u8* invalid, const u8* invalid_b) {
+        if (n <= 0) return;
+        k_add_proj<C><<<grid(n), BLK, 0, s>>>(n, a, b, out, invalid, invalid_b);
+        count_launch();
     }
     static void proj_to_bytes(cudaStream_t s, int n, const u32* proj, u8* xyz) {
         if (n <= 0) return;
         k_proj_to_bytes<C><<<grid(n), BLK, 0, s>>>(n, proj, xyz);
-        g_launch_count++;
+        count_launch();
     }
     static void verify(cudaStream_t s, int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok) {
         if (n <= 0) return;
         k_verify<C><<<grid(n), BLK, 0, s>>>(n, q, z, rs, gtab, ok);
-        g_launch_count++;
+        count_launch();
     }
     // Affine window tables for n rows (primeorder curves only; a no-op on secp256k1, whose shared-Z table needs no inversion).
     // wtab: n x 16L words of tables followed by n x 7L words of scratch for the Z coordinates (wintab_words(n) in all).
@@ -351,17 +370,17 @@ template <class C> struct Launch {
             const int threads = (cnt + ept - 1) / ept;
             k_wintab<C><<<grid(threads), BLK, 0, s>>>(cnt, pts ? pts + (size_t)off * 2 * C::FB : nullptr, aff_limbs ? aff_limbs + (size_t)off * 2 * C::L : nullptr,
                                                       wtab + (size_t)off * 16 * C::L, zbuf + (size_t)off * 7 * C::L);
-            g_launch_count++;
+            count_launch();
         }
     }
     static void mul_var_fast(cudaStream_t s, int n, const u8* pts, const u32* aff_limbs, const u8* inf, const u8* k, u32* proj, u8* invalid,
                              const u32* wtab) {
         if (n <= 0) return;
-        static bool seen[64] = {};
+        static std::atomic<bool> seen[64] = {};
         if (win_smem_bytes<C>() > 0 && first_use_on_device(seen))
             cudaFuncSetAttribute(k_mul_var_fast<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem_bytes<C>());
         k_mul_var_fast<C><<<grid(n), BLK, win_smem_bytes<C>(), s>>>(n, pts, aff_limbs, inf, k, proj, invalid, C::A_IS_ZERO ? nullptr : wtab);
-        g_launch_count++;
+        count_launch();
     }
     static int ept_threads(int n) {   // threads for the Montgomery-trick kernels: rows per thread that keep ~1 CTA per SM busy (latency-bound below that, see normalize)
         int ept = (n + 148 * 1 * BLK - 1) / (148 * 1 * BLK);
@@ -372,14 +391,14 @@ template <class C> struct Launch {
     static void verify_prep(cudaStream_t s, int n, int mode, const u8* z, const u8* rs, u32* scratch) {
         if (n <= 0) return;
         k_verify_prep<C><<<grid(ept_threads(n)), BLK, 0, s>>>(n, mode, z, rs, scratch);
-        g_launch_count++;
+        count_launch();
     }
     static void verify_main(cudaStream_t s, int n, int mode, const u8* q, const u8* rs, const u8* z, const u8* aux, const u32* scratch,
                             const u32* gbig, int gw, u8* ok, u32* proj_out, const u32* wtab) {
         if (n <= 0) return;
         // Schnorr exists for secp256k1 only, SM2DSA for SM2 only (abi.cu rejects other combinations before launching)
         const u32 sm = win_smem_bytes<C>();
-        static bool seen[64] = {};
+        static std::atomic<bool> seen[64] = {};
         if (sm > 0 && first_use_on_device(seen)) {
             cudaFuncSetAttribute(k_verify_main<C, VM_ECDSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             cudaFuncSetAttribute(k_verify_main<C, VM_RECOVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -393,37 +412,37 @@ template <class C> struct Launch {
         } else if (mode == VM_SM2DSA) {
             if constexpr (C::ID == 3) k_verify_main<C, VM_SM2DSA><<<grid(n), BLK, sm, s>>>(n, q, rs, z, aux, scratch, gbig, gw, ok, proj_out, wtab);
         }
-        g_launch_count++;
+        count_launch();
     }
     static void decode(cudaStream_t s, int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
         if (n <= 0) return;
         k_decode<C><<<grid(n), BLK, 0, s>>>(n, mode, enc, stride, xy, status);
-        g_launch_count++;
+        count_launch();
     }
     static void finish(cudaStream_t s, int n, int kind, const u8* a, int stride, const u8* inf, const u8* rs, u8* ok) {
         if (n <= 0) return;
         k_finish<C><<<grid(n), BLK, 0, s>>>(n, kind, a, stride, inf, rs, ok);
-        g_launch_count++;
+        count_launch();
     }
     static void sign_finish(cudaStream_t s, int n, const u8* d, const u8* k, const u8* z, const u32* aff, u8* rs_out, u8* recid_out, u8* ok_out) {
         if (n <= 0) return;
         k_sign_finish<C><<<grid(ept_threads(n)), BLK, 0, s>>>(n, d, k, z, aff, rs_out, recid_out, ok_out);
-        g_launch_count++;
+        count_launch();
     }
-    static const CurveLaunch* table() {
-        static CurveLaunch t = {
+    static CurveLaunch make_table() {
+        CurveLaunch t = {
             C::ID, C::L, C::FB, C::A_IS_ZERO ? 8 : 15, Bodies<C>::GEN_WINDOWS, 8, C::COMPRESS_DEFAULT, {0},
             &field_op, &mul_var, &mul_gen, &load_proj, &normalize, &sum, &proj_to_bytes, &verify,
-            &mul_var_fast, &verify_prep, &verify_main, &decode, &finish, &sign_finish, &wintab, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
-        static bool init = false;
-        if (!init) {   // R mod n (the Montgomery "one" of the scalar field) as big-endian bytes
-            for (int i = 0; i < C::L; i++) {
-                const u32 w = C::Fn::Params::one(i);
-                t.r_mod_n[C::FB - 4 * i - 1] = (u8)w; t.r_mod_n[C::FB - 4 * i - 2] = (u8)(w >> 8);
-                t.r_mod_n[C::FB - 4 * i - 3] = (u8)(w >> 16); t.r_mod_n[C::FB - 4 * i - 4] = (u8)(w >> 24);
-            }
-            init = true;
+            &mul_var_fast, &verify_prep, &verify_main, &decode, &finish, &sign_finish, &wintab, &add_proj, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
+        for (int i = 0; i < C::L; i++) {   // R mod n (the Montgomery "one" of the scalar field) as big-endian bytes
+            const u32 w = C::Fn::Params::one(i);
+            t.r_mod_n[C::FB - 4 * i - 1] = (u8)w; t.r_mod_n[C::FB - 4 * i - 2] = (u8)(w >> 8);
+            t.r_mod_n[C::FB - 4 * i - 3] = (u8)(w >> 16); t.r_mod_n[C::FB - 4 * i - 4] = (u8)(w >> 24);
         }
+        return t;
+    }
+    static const CurveLaunch* table() {
+        static const CurveLaunch t = make_table();   // initialised once, thread-safe (C++11 magic static)
         return &t;
     }
 };

@@ -42,6 +42,8 @@ struct CurveLaunch {
     // affine window tables {1..8}Q of n points (x||y bytes or field-internal limbs) into wtab (23 L words per row: 16 L of
     // table, 7 L of scratch); no-op on secp256k1
     void (*wintab)(cudaStream_t s, int n, const uint8_t* pts, const uint32_t* aff_limbs, uint32_t* wtab);
+    // out[i] = a[i] + b[i] on projective limbs (complete addition), invalid[i] |= invalid_b[i]: tail of the per-row 2-term lincomb
+    void (*add_proj)(cudaStream_t s, int n, const uint32_t* a, const uint32_t* b, uint32_t* out, uint8_t* invalid, const uint8_t* invalid_b);
     int prep_words;   // u32 words of scratch per row between verify_prep and verify_main
     int sum_blocks;
 };
@@ -53,7 +55,10 @@ const CurveLaunch* launch_sm2();
 const CurveLaunch* launch_p192();
 const CurveLaunch* launch_p224();
 
-// incremented by every kernel launch issued through the launchers (host side, not thread safe)
-extern uint64_t g_launch_count;
+// Launch accounting (bench.py's gpu_launches evidence).  Every entry point of abi.cu points this thread-local at the
+// calling context's own counter before it enqueues anything, so two contexts driven from two host threads (one per
+// device under ecb200_init_multi) never share a counter.
+extern thread_local uint64_t* tl_launch_counter;
+inline void count_launch(int k = 1) { if (tl_launch_counter) *tl_launch_counter += (uint64_t)k; }
 
 }  // namespace ecb

@@ -1,0 +1,267 @@
+"""-m gpu tests of the round-2 boundary additions, through the C ABI: the per-row two-term linear combination
+(ecb200_lincomb2), one context over several devices (ecb200_init_multi), rejected lincomb terms, host-buffer validation of
+the Python layer, and every index of the secret-scalar window table."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from oracle import ecoracle as o
+
+pytestmark = pytest.mark.gpu
+CUR = ["k256", "p256", "p384", "sm2", "p192", "p224"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import ecb200
+    e = ecb200.Engine(0)
+    yield e
+    e.close()
+
+
+def be(vals, fb):
+    if isinstance(vals, int):
+        vals = [vals]
+    return b"".join(int(v).to_bytes(fb, "big") for v in vals)
+
+
+def _pt(c, P):
+    return be(P, c.fb)
+
+
+@pytest.mark.parametrize("cname", CUR)
+@pytest.mark.parametrize("ct", [0, 1])
+def test_lincomb2_batch_vs_oracle(eng, cname, ct):
+    """LinearCombination::lincomb(&x, &k, &y, &l) per row (k256 mul.rs:313-323, primeorder projective.rs:415-420; the
+    reference's own test is mul.rs:493-507: lincomb == x*k + y*l).  Edge rows: cancellation (x*k + (-x)*k), y = x, zero
+    scalars, k = n - 1, generator terms."""
+    import ecb200
+    c = o.curve(cname)
+    fb = c.fb
+    rng = random.Random(71 + c.cid)
+    n = 150 if fb <= 32 else 60
+    rows = []
+    for i in range(n):
+        x, y = o.mul_gen(c, rng.randrange(1, c.n)), o.mul_gen(c, rng.randrange(1, c.n))
+        k, l = rng.randrange(c.n), rng.randrange(c.n)
+        if i == 0: y, l = o.pt_neg(c, x), k                  # sum = identity
+        if i == 1: y = x                                    # x*k + x*l
+        if i == 2: k = 0
+        if i == 3: k, l = 0, 0
+        if i == 4: k, l = c.n - 1, 1
+        if i == 5: x, y = c.G, c.G
+        if i == 6: y, l = x, (c.n - k) % c.n                # x*k + x*(n-k) = identity
+        rows.append((x, k, y, l))
+    p1 = b"".join(_pt(c, r[0]) for r in rows); k1 = be([r[1] for r in rows], fb)
+    p2 = b"".join(_pt(c, r[2]) for r in rows); k2 = be([r[3] for r in rows], fb)
+    exp = b"".join(o.slot_encode(c, o.pt_lincomb(c, [(r[0], r[1]), (r[2], r[3])])) for r in rows)
+    out, inv = eng.lincomb2_batch(cname, p1, k1, p2, k2, ct)
+    assert out == exp and not any(inv)
+    st = len(exp) // n
+    assert out[:st] == bytes(st) and out[6 * st:7 * st] == bytes(st)
+    # projective inputs with random Z
+    def proj(P):
+        lam = rng.randrange(1, c.p)
+        return be((P[0] * lam % c.p, P[1] * lam % c.p, lam), fb)
+    q1 = b"".join(proj(r[0]) for r in rows); q2 = b"".join(proj(r[2]) for r in rows)
+    out, inv = eng.lincomb2_batch(cname, q1, k1, q2, k2, ct | ecb200.FLAG_PROJ)
+    assert out == exp
+    # an invalid point in either position voids that row only
+    bad1 = be((1, 1), fb) + p1[2 * fb:6 * fb]
+    bad2 = p2[:2 * fb] + be((c.p, 0), fb) + p2[4 * fb:6 * fb]
+    out, inv = eng.lincomb2_batch(cname, bad1, k1[:3 * fb], bad2, k2[:3 * fb], ct)
+    assert list(inv) == [1, 1, 0] and out[:2 * st] == bytes(2 * st) and out[2 * st:] == exp[2 * st:3 * st]
+    assert eng.lincomb2_batch(cname, b"", b"", b"", b"", ct) == (b"", b"")
+
+
+def test_lincomb2_matches_verify_construction(eng):
+    """u1*G + u2*Q through lincomb2 equals the point ECDSA verification accepts on: R.x mod n == r for signed rows."""
+    import ecb200
+    c = o.K256
+    rng = np.random.default_rng(5)
+    n = 2000
+    def scal():
+        a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); a[:, 0] &= 0x7F; a[:, -1] |= 1
+        return a
+    d, k, z = scal(), scal(), rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    rs, rid, ok = eng.ecdsa_sign("k256", d, k, z)
+    assert ok == b"\x01" * n
+    pub = np.frombuffer(eng.mul_by_generator_batch("k256", d, ecb200.FLAG_UNCOMPRESSED), np.uint8).reshape(n, 65)[:, 1:].copy()
+    rsa = np.frombuffer(rs, np.uint8).reshape(n, 64)
+    r, s = np.ascontiguousarray(rsa[:, :32]), np.ascontiguousarray(rsa[:, 32:])
+    w, _ = eng.field_op("k256", 1, 5, s)
+    zr, _ = eng.field_op("k256", 1, 0, z, bytes(n * 32))
+    u1, _ = eng.field_op("k256", 1, 2, zr, w)
+    u2, _ = eng.field_op("k256", 1, 2, r, w)
+    g = np.tile(np.frombuffer(be(c.G, 32), np.uint8), (n, 1))
+    out, inv = eng.lincomb2_batch("k256", g, u1, pub, u2, ecb200.FLAG_UNCOMPRESSED)
+    x = np.frombuffer(out, np.uint8).reshape(n, 65)[:, 1:33]
+    xr, _ = eng.field_op("k256", 1, 0, np.ascontiguousarray(x), bytes(n * 32))
+    assert xr == r.tobytes()
+
+
+@pytest.mark.parametrize("cname", ["k256", "p256"])
+def test_lincomb_rejects_invalid_term(eng, cname):
+    import ecb200
+    c = o.curve(cname)
+    fb = c.fb
+    good = [o.mul_gen(c, 5), o.mul_gen(c, 9)]
+    ks = be([3, 4], fb)
+    assert eng.lincomb(cname, b"".join(_pt(c, P) for P in good), ks) == o.slot_encode(c, o.mul_gen(c, 51))
+    for flags in (0, ecb200.FLAG_CT):
+        with pytest.raises(ecb200.Ecb200Error, match="not a valid point"):
+            eng.lincomb(cname, _pt(c, good[0]) + be((1, 1), fb), ks, flags)
+    assert eng.lib.ecb200_lincomb(eng.h, c.cid, 2, ctypes.c_char_p(_pt(c, good[0]) + be((c.p, 0), fb)), ctypes.c_char_p(ks),
+                                  ctypes.create_string_buffer(200), 0, 0) == -4
+
+
+def _multi(devs):
+    import ecb200
+    return ecb200.Engine(devices=devs)
+
+
+def test_init_multi_shards_inside_one_call(eng):
+    """ecb200_init_multi: one context, several shards; every host entry point must return exactly what the single-device
+    context returns, for sizes that split unevenly (and for n smaller than the number of shards).  On a one-GPU box the
+    shards are child contexts on the same device; with >= 2 GPUs a second engine spans two devices."""
+    import ecb200
+    import torch
+    c = o.K256
+    rng = np.random.default_rng(11)
+    cases = [[0, 0, 0]]
+    if torch.cuda.device_count() >= 2:
+        cases.append([0, 1])
+    for devs in cases:
+        m = _multi(devs)
+        assert m.n_devices == len(devs)
+        for n in (0, 1, 2, 1001, 70001):
+            ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            a = eng.mul_by_generator_batch("k256", ks, ecb200.FLAG_UNCOMPRESSED)
+            assert m.mul_by_generator_batch("k256", ks, ecb200.FLAG_UNCOMPRESSED) == a
+            if n == 0:
+                continue
+            pts = np.frombuffer(a, np.uint8).reshape(n, 65)[:, 1:].copy()
+            k2 = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            inf = np.zeros(n, np.uint8); inf[::7] = 1
+            for fl in (0, ecb200.FLAG_CT):
+                assert m.mul_batch("k256", pts, k2, inf, fl) == eng.mul_batch("k256", pts, k2, inf, fl)
+            z = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            d = ks.copy(); d[:, 0] &= 0x7F; d[:, -1] |= 1
+            kk = k2.copy(); kk[:, 0] &= 0x7F; kk[:, -1] |= 1
+            sig = eng.ecdsa_sign("k256", d, kk, z)
+            assert m.ecdsa_sign("k256", d, kk, z) == sig
+            pub = np.frombuffer(eng.mul_by_generator_batch("k256", d, ecb200.FLAG_UNCOMPRESSED), np.uint8).reshape(n, 65)[:, 1:].copy()
+            rs = np.frombuffer(sig[0], np.uint8).reshape(n, 64).copy()
+            rs[::5, 40] ^= 1
+            okm = m.ecdsa_verify("k256", pub, z, rs)
+            assert okm == eng.ecdsa_verify("k256", pub, z, rs)
+            assert n < 5 or 0 < sum(okm) < n
+            assert m.ecdsa_recover("k256", z, rs, sig[1]) == eng.ecdsa_recover("k256", z, rs, sig[1])
+            assert m.lincomb2_batch("k256", pts, k2, pub, kk) == eng.lincomb2_batch("k256", pts, k2, pub, kk)
+            xyz = np.concatenate([pts, z], axis=1); xyz[:, 64] &= 0x7F
+            assert m.batch_normalize("k256", xyz) == eng.batch_normalize("k256", xyz)
+            assert m.field_op("k256", 0, 2, z, kk) == eng.field_op("k256", 0, 2, z, kk)
+            comp = eng.mul_by_generator_batch("k256", d)
+            assert m.decode_points("k256", comp, 33) == eng.decode_points("k256", comp, 33)
+            assert m.ecdsa_verify_sec1("k256", comp, 33, z, rs) == okm
+            # many-term lincomb: per-device partials, summed on the first device
+            if n <= 1001:
+                assert m.lincomb("k256", pts, k2) == eng.lincomb("k256", pts, k2)
+                assert m.lincomb("k256", pts, k2, ecb200.FLAG_CT) == eng.lincomb("k256", pts, k2)
+        assert m.launch_count > 0
+        # device pointers belong to one device
+        t = torch.zeros(64, dtype=torch.uint8, device="cuda:0")
+        with pytest.raises(ecb200.Ecb200Error, match="single-device"):
+            m.mul_gen_dev("k256", 1, t, t)
+        m.close()
+    # other curves through the sharded path
+    m = _multi([0, 0])
+    for cname in ("p256", "p384", "sm2"):
+        cc = o.curve(cname)
+        n = 333
+        ks = rng.integers(0, 256, size=(n, cc.fb), dtype=np.uint8)
+        assert m.mul_by_generator_batch(cname, ks) == eng.mul_by_generator_batch(cname, ks)
+    q = np.frombuffer(eng.mul_by_generator_batch("sm2", ks, ecb200.FLAG_UNCOMPRESSED), np.uint8).reshape(n, 65)[:, 1:].copy()
+    e = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    rs = rng.integers(0, 256, size=(n, 64), dtype=np.uint8); rs[:, 0] &= 0x7F; rs[:, 32] &= 0x7F
+    assert m.sm2dsa_verify(q, e, rs) == eng.sm2dsa_verify(q, e, rs)
+    pk = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    assert m.schnorr_verify(pk, e, rs) == eng.schnorr_verify(pk, e, rs)
+    m.close()
+    assert eng.lib.ecb200_init_multi(1, (ctypes.c_int * 1)(99), ctypes.byref(ctypes.c_void_p())) == -1
+    assert eng.lib.ecb200_device_count(eng.h) == 1
+
+
+def test_two_contexts_two_host_threads(eng):
+    """Two single-device contexts driven concurrently from two host threads: results and per-context launch counts are
+    independent (launch counters are per context, the per-function attribute flags atomic)."""
+    import threading
+    import ecb200
+    e2 = ecb200.Engine(0)
+    rng = np.random.default_rng(3)
+    ks = rng.integers(0, 256, size=(20000, 32), dtype=np.uint8)
+    exp = eng.mul_by_generator_batch("k256", ks, ecb200.FLAG_CT)
+    base = (eng.launch_count, e2.launch_count)
+    res = {}
+    def work(name, e, reps):
+        for _ in range(reps):
+            res[name] = e.mul_by_generator_batch("k256", ks, ecb200.FLAG_CT)
+    ts = [threading.Thread(target=work, args=("a", eng, 6)), threading.Thread(target=work, args=("b", e2, 3))]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert res["a"] == exp and res["b"] == exp
+    da, db = eng.launch_count - base[0], e2.launch_count - base[1]
+    assert da == 2 * db and db > 0          # 6 vs 3 identical calls: counts are not shared between contexts
+    e2.close()
+
+
+def test_python_layer_validates_buffers(eng):
+    """a short or strided buffer must raise before the C ABI is handed a raw pointer."""
+    z = np.zeros((10, 32), np.uint8)
+    q = np.zeros((10, 64), np.uint8)
+    with pytest.raises(ValueError):
+        eng.ecdsa_verify("k256", q[:9], z, q)                      # q shorter than n rows
+    with pytest.raises(ValueError):
+        eng.ecdsa_verify("k256", q, z, q[:, :63])                  # rs short and strided
+    with pytest.raises(ValueError):
+        eng.ecdsa_verify("k256", q[:, ::2], z[:, :16], q)          # strided views
+    with pytest.raises(ValueError):
+        eng.ecdsa_verify("k256", q.astype(np.uint16), z, q)        # wrong dtype
+    with pytest.raises(ValueError):
+        eng.mul_batch("k256", bytes(64 * 3), bytes(32 * 4))
+    with pytest.raises(ValueError):
+        eng.mul_batch("k256", bytes(64 * 4), bytes(32 * 4), inf=bytes(3))
+    with pytest.raises(ValueError):
+        eng.mul_by_generator_batch("p384", bytes(47))
+    with pytest.raises(ValueError):
+        eng.ecdsa_sign("k256", bytes(32), bytes(64), bytes(64))
+    with pytest.raises(ValueError):
+        eng.ecdsa_recover("k256", bytes(64), bytes(64), bytes(2))
+    with pytest.raises(ValueError):
+        eng.schnorr_verify(bytes(64), bytes(32), bytes(128))
+    with pytest.raises(ValueError):
+        eng.batch_normalize("k256", bytes(95))
+    with pytest.raises(ValueError):
+        eng.ecdsa_verify("k256", q, z, q, out=np.zeros(9, np.uint8))
+
+
+@pytest.mark.parametrize("cname", CUR)
+def test_every_window_table_index_secret_path(eng, cname):
+    """ADVICE r1 (build_table): the constant-time multiplication with scalars whose signed radix-16 digits take every
+    magnitude 0..8 and both signs in every window position - each entry of the 9-entry table is selected and used."""
+    import ecb200
+    c = o.curve(cname)
+    fb = c.fb
+    P = o.mul_gen(c, 0xABCDEF)
+    ks = []
+    for d in range(16):
+        ks.append(int(("%x" % d) * (2 * fb), 16) % c.n)            # the same nibble in every window
+        ks.append(d << (8 * fb - 8))
+        ks.append(d)
+    ks += [(c.n - 1) >> s for s in range(8)]
+    pb = _pt(c, P) * len(ks)
+    out, inv = eng.mul_batch(cname, pb, be(ks, fb), None, ecb200.FLAG_CT)
+    assert out == o.batch_mul_var_affine(c, pb, None, be(ks, fb)) and not any(inv)
+    out2, _ = eng.mul_batch(cname, pb, be(ks, fb), None, 0)
+    assert out2 == out
