@@ -3,20 +3,25 @@
 
     python bench.py --gpus N --steps K --warmup W          # our arm (one process per GPU; torchrun for N > 1)
     python bench.py --impl reference --gpus N ...           # the reference's CPU algorithms (C++ port) on host cores
+    python bench.py --op mul_var --curve p384 ...           # the other BASELINE configs as headline lines
+    python bench.py --scaling strong ...                    # ONE global batch, each rank takes its index shard
 
 Headline workload (BASELINE.json configs[2], the config the metric "ECDSA verify/s at 1/2/4/8 B200" is quoted
 on; it fits one GPU): secp256k1 ECDSA verify_prehash over 2^22 synthetic signatures per GPU, 2^16 distinct
-keys, 1/16 of the rows corrupted, sharded by index range with no collective on the data path (weak scaling:
-every rank verifies its own 2^22 rows).  A "step" is one pass over the rank's batch.
-  value  = whole-job verifies/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks)
-  e2e    = the same through the host-pointer C-ABI call (H2D of 160 B/row and D2H of 1 B/row inside the timing)
-  roofline: INT32 multiply-add issue rate — achieved = rows/s x W_elem (reference-algorithm
-            32x32->64 products per row) / the dominant kernel's launch duration (CUDA events inside the library) against
-            the measured whole-chip IMAD.WIDE rate (peaks_int.json);
-            an HBM figure (algorithmic bytes / time vs MEASURED_PEAKS.json) is reported beside it; executed_frac /
-            fmaheavy_pipe_pct (ncu, profiles/summary.json) are the hardware-utilisation view.
-  cpu_baseline: oracle/ecport.cpp (C++ port of the reference algorithms, OpenMP) on a bounded sample.
-The other BASELINE configs are measured in the same run at N = 1 and reported under "others".
+keys, 1/16 of the rows corrupted, sharded by index range with no collective on the data path (default = weak
+scaling: every rank verifies its own 2^22 rows; --scaling strong shards one 2^22-row batch).  A "step" is one pass
+over the rank's rows.
+  value  = whole-job rows/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks)
+  e2e    = the same through the host-pointer C-ABI call (H2D of the inputs and D2H of the result inside the timing)
+  roofline: INT32 multiply-add issue rate.  `frac` is the HARDWARE fraction of the dominant kernel:
+            IMAD.WIDE multiply-accumulates it executes per row (counted by ncu on this build, profiles/summary.json) x
+            rows per launch / its launch duration (CUDA events inside the library, ecb200_kernel_timing) against the
+            measured whole-chip IMAD.WIDE rate (peaks_int.json; the nominal 32 lanes/clk/SM figure is printed beside it).
+            `frac_ref_normalised` is SURVEY §8d's throughput-normalised companion (the REFERENCE algorithm's
+            multiplications per row, M_ref x W_per_M; it exceeds 1 when the device needs fewer multiplications).
+  cpu_baseline: oracle/ecport.cpp (C++ port of the reference algorithms, OpenMP) on a bounded sample of the same rows.
+The other BASELINE configs are measured in the same run at N = 1 and reported under "others", each with an output check,
+an end-to-end figure and its hardware fraction.
 """
 import argparse
 import ctypes
@@ -32,10 +37,27 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W_PER_M = {"k256": 73, "p256": 136, "sm2": 136, "p384": 300}
-M_REF = {"verify_k256": 3218, "verify_p256": 9005, "mul_gen_k256": 817, "mul_var_k256": 1990,
-         "mul_var_p384": 6478, "mul_var_sm2": 4366, "mul_var_p256": 4366}
-IO_BYTES = {"verify": lambda fb: 5 * fb + 1, "mul_gen": lambda fb: fb + 1 + fb, "mul_var": lambda fb: 4 * fb + 1 + fb}
+W_PER_M = {"k256": 73, "p256": 136, "sm2": 136, "p384": 300, "p192": 78, "p224": 105}     # SURVEY.md §8d (2L^2 + L for the last two)
+FB = {"k256": 32, "p256": 32, "sm2": 32, "p384": 48, "p192": 24, "p224": 28}
+# (op, curve) -> BASELINE config, reference-algorithm multiplications per row, default size, seed, dominant kernel
+CASES = {
+    ("verify", "k256"): dict(cfg="configs[2]", m_ref=3218, log2=22, seed=0xB2000003, unit="verifies/s",
+                             metric="secp256k1 ECDSA verify_prehash throughput", kernel="k_verify_main<CurveK256, VM_ECDSA>"),
+    ("verify", "p256"): dict(cfg="configs[3]", m_ref=9005, log2=22, seed=0xB2000004, unit="verifies/s",
+                             metric="P-256 ECDSA verify_prehash throughput", kernel="k_verify_main<CurveP256, VM_ECDSA> (k_wintab<CurveP256> before it)"),
+    ("mul_var", "k256"): dict(cfg="configs[1]", m_ref=1990, log2=20, seed=0xB2000002, unit="scalar-mul/s", projective=True,
+                              metric="secp256k1 variable-base P*k + batch_normalize throughput", kernel="k_mul_var_fast<CurveK256>"),
+    ("mul_var", "p384"): dict(cfg="configs[4]", m_ref=6478, log2=20, seed=0xB2000005, unit="scalar-mul/s", projective=False,
+                              metric="P-384 variable-base P*k throughput", kernel="k_mul_var_fast<CurveP384> (k_wintab<CurveP384> before it)"),
+    ("mul_var", "sm2"): dict(cfg="configs[4]", m_ref=4366, log2=20, seed=0xB2000006, unit="scalar-mul/s", projective=False,
+                             metric="SM2 variable-base P*k throughput", kernel="k_mul_var_fast<CurveSM2> (k_wintab<CurveSM2> before it)"),
+    ("mul_var", "p256"): dict(cfg="configs[4] shape on P-256", m_ref=4366, log2=20, seed=0xB2000009, unit="scalar-mul/s", projective=False,
+                              metric="P-256 variable-base P*k throughput", kernel="k_mul_var_fast<CurveP256> (k_wintab<CurveP256> before it)"),
+    ("mul_gen", "k256"): dict(cfg="configs[0]", m_ref=817, log2=16, seed=0xB2000001, unit="scalar-mul/s",
+                              metric="secp256k1 fixed-base G*k throughput (constant-time path)", kernel="k_mul_gen_smem<CurveK256, true>"),
+}
+IO_BYTES = {"verify": lambda fb, slot: (5 * fb, 1), "mul_gen": lambda fb, slot: (fb, slot),
+            "mul_var": lambda fb, slot: (3 * fb, slot), "mul_var_proj": lambda fb, slot: (4 * fb, slot)}
 
 
 def load_json(path, default=None):
@@ -88,47 +110,68 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def imad_peak_gmacs(sm_mhz):
-    """Measured IMAD.WIDE issue peak: whole-chip multiply-accumulates per second of IMAD.WIDE.U32.X carry chains
-    (bench/imad_peak.cu, event-timed on this pool's B200 at 1965 MHz -> peaks_int.json), scaled by the SM clock seen
-    during the timed region when that is lower."""
+def imad_peaks(sm_mhz):
+    """(measured, nominal) whole-chip IMAD.WIDE multiply-accumulates per second in Gmac/s.  Measured: IMAD.WIDE.U32.X carry
+    chains, bench/imad_peak.cu, event-timed on this pool's B200 at 1965 MHz (peaks_int.json; builder-measured - the driver's
+    MEASURED_PEAKS.json has no integer figure), scaled by the SM clock seen during the timed region when that is lower.
+    Nominal: one warp-wide IMAD.WIDE per 4 cycles per SM sub-partition = 32 lanes/clk/SM x 148 SMs x the SM clock."""
     pk = load_json(os.path.join(ROOT, "peaks_int.json"), {})
     g = pk.get("imad_wide_chip_gmacs")
-    src = "measured (peaks_int.json: IMAD.WIDE.U32.X carry chains, whole chip, CUDA events)"
-    if not g:
-        g, src = 32.0 * 148 * 1965e6 / 1e9, "fallback: 32 IMAD.WIDE/clk/SM x 148 SMs x 1965 MHz"
+    src = "measured by bench/imad_peak.cu (peaks_int.json: IMAD.WIDE.U32.X carry chains, whole chip, CUDA events, 29.9/clk/SM)"
     ref_mhz = pk.get("sm_mhz_during_measurement", 1965.0)
-    mhz = sm_mhz or ref_mhz
-    return g * min(1.0, mhz / ref_mhz), src
+    mhz = min(sm_mhz or ref_mhz, ref_mhz)
+    nominal = 32.0 * 148 * mhz * 1e6 / 1e9
+    if not g:
+        return nominal, nominal, "fallback: nominal 32 IMAD.WIDE lanes/clk/SM x 148 SMs x SM clock"
+    return g * mhz / ref_mhz, nominal, src
 
 
-def roofline(kind, curve, rows_per_s, ms_kernel, n_rows, sm_mhz, kernel_ms=None, kernel_name=None):
-    """achieved = algorithmic multiply-accumulates of one launch (reference-algorithm field
-    multiplications x schoolbook 32x32 products each) / launch duration; kernel_ms (CUDA events around the dominant
-    kernel, ecb200_kernel_timing) is used when available, else the whole step."""
-    fb = 48 if curve == "p384" else 32
-    w_elem = M_REF[f"{kind}_{curve}"] * W_PER_M[curve]
-    peak, src = imad_peak_gmacs(sm_mhz)
-    dur = kernel_ms if kernel_ms else ms_kernel
-    ach = n_rows * w_elem / (dur * 1e-3) / 1e9
-    peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), {})
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_ach = n_rows * IO_BYTES[kind](fb) / (ms_kernel * 1e-3) / 1e9
-    prof = load_json(os.path.join(ROOT, "profiles", "summary.json"), {}).get(f"{kind}_{curve}", {})
-    out = {"bound": "imad", "achieved": round(ach, 1), "peak": round(peak, 1), "unit": "Gmac/s (32x32->64 multiply-accumulates)",
-           "frac": round(ach / peak, 4), "w_elem": w_elem, "peak_source": src,
-           "kernel": kernel_name, "kernel_ms_per_launch": round(dur, 4), "rows_per_launch": n_rows,
-           "note": "achieved counts the REFERENCE algorithm's multiplications (M_ref x W_per_M); the device executes fewer, "
-                   "so this throughput-normalised fraction can exceed 1 - executed_frac and fmaheavy_pipe_pct are the hardware view",
-           "traffic": prof.get("dram_bytes_per_launch"), "traffic_rows": prof.get("n_rows"),
-           "hbm": {"achieved": round(hbm_ach, 2), "peak": hbm_peak, "unit": "GB/s", "frac": round(hbm_ach / hbm_peak, 5),
-                   "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"}}
-    if prof.get("wide_macs_per_row"):
-        ex = n_rows * prof["wide_macs_per_row"] / (dur * 1e-3) / 1e9
-        out["executed"] = round(ex, 1)
-        out["executed_frac"] = round(ex / peak, 4)
-        out["fmaheavy_pipe_pct"] = prof.get("pipe_fmaheavy_pct")
-        out["executed_source"] = prof.get("source")
+def prof_key(op, curve, ct=False):
+    return f"{op}_{curve}" + ("_ct" if ct and op == "mul_var" else "")
+
+
+def roofline(op, curve, n_rows, step_ms, sm_mhz, kernel_ms=None, ct=False, io=None):
+    """Hardware view first: the dominant kernel's executed IMAD.WIDE multiply-accumulates (ncu opcode counts of this build,
+    profiles/summary.json) / its launch duration, against the measured IMAD.WIDE peak.  step_executed_frac covers every
+    kernel of the step.  frac_ref_normalised = SURVEY §8d's M_ref x W_per_M figure over the same duration."""
+    case = CASES.get((op, curve), {})
+    peak, nominal, src = imad_peaks(sm_mhz)
+    dur = kernel_ms if kernel_ms else step_ms
+    out = {"bound": "imad", "unit": "Gmac/s (32x32->64 multiply-accumulates)", "achieved": None, "peak": round(peak, 1), "frac": None,
+           "peak_nominal": round(nominal, 1), "peak_source": src + "; peak_nominal = 32 lanes/clk/SM x 148 x SM clock",
+           "kernel": case.get("kernel"), "kernel_ms_per_launch": round(dur, 4), "rows_per_launch": n_rows, "traffic": None}
+    prof = load_json(os.path.join(ROOT, "profiles", "summary.json"), {}).get(prof_key(op, curve, ct), {})
+    ks = prof.get("kernels") or []
+    if ks and prof.get("n_rows"):
+        dom = max(ks, key=lambda k: k["ms"])
+        macs_dom = dom["wide_warp_inst"] * 32.0 / prof["n_rows"]
+        ach = n_rows * macs_dom / (dur * 1e-3) / 1e9
+        step = n_rows * prof["wide_macs_per_row"] / (step_ms * 1e-3) / 1e9
+        out.update({"achieved": round(ach, 1), "frac": round(ach / peak, 4), "frac_of_nominal": round(ach / nominal, 4),
+                    "macs_per_row_dominant_kernel": round(macs_dom, 1), "macs_per_row_step": prof["wide_macs_per_row"],
+                    "step_executed": round(step, 1), "step_executed_frac": round(step / peak, 4),
+                    "fmaheavy_pipe_pct": dom.get("fmaheavy_pct"), "issue_active_pct": dom.get("issue_active_pct"),
+                    "registers": dom.get("registers"), "traffic": prof.get("dram_bytes_per_launch"), "traffic_rows": prof["n_rows"],
+                    "executed_source": prof.get("source")})
+    elif prof.get("wide_macs_per_row"):      # round-1 style entry: one kernel only
+        ach = n_rows * prof["wide_macs_per_row"] / (dur * 1e-3) / 1e9
+        out.update({"achieved": round(ach, 1), "frac": round(ach / peak, 4), "frac_of_nominal": round(ach / nominal, 4),
+                    "macs_per_row_dominant_kernel": prof["wide_macs_per_row"], "fmaheavy_pipe_pct": prof.get("pipe_fmaheavy_pct"),
+                    "traffic": prof.get("dram_bytes_per_launch"), "traffic_rows": prof.get("n_rows"), "executed_source": prof.get("source")})
+    else:
+        out["note"] = "no ncu opcode count of this kernel in profiles/summary.json: only the reference-normalised figure is available"
+    if case.get("m_ref"):
+        w_elem = case["m_ref"] * W_PER_M[curve]
+        refn = n_rows * w_elem / (dur * 1e-3) / 1e9
+        out.update({"frac_ref_normalised": round(refn / peak, 4), "w_elem_ref": w_elem,
+                    "ref_normalised_note": "REFERENCE-algorithm multiplications (M_ref x W_per_M, SURVEY 8d) per row over the same duration; "
+                                           "not a utilisation - the device executes fewer multiplications than the reference algorithm"})
+    if io:
+        peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), {})
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm = n_rows * sum(io) / (step_ms * 1e-3) / 1e9
+        out["hbm"] = {"achieved": round(hbm, 2), "peak": hbm_peak, "unit": "GB/s", "frac": round(hbm / hbm_peak, 5), "algorithmic_bytes_per_row": sum(io),
+                      "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"}
     return out
 
 
@@ -158,6 +201,10 @@ class PyBackend:
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path on the host cores: oracle/ecport.cpp (C++ port of the reference
+    algorithms incl. the variable-time Stein inversion verify calls; the Rust crates cannot be built here), every host
+    thread, on the FIRST rows of the same seeded batch our arm verifies (make_verify_batch is prefix-stable: the rows of a
+    2^k-row batch are the first 2^k rows of the 2^22-row batch with the same seed - tests/test_workloads_cpu.py)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -166,36 +213,67 @@ def run_reference(args):
     lib = port_lib.load()
     lib.port_set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     cores = lib.port_threads()
-    curve = "k256"
-    # bounded sample: sized for roughly 2 s per step on this host
-    n0 = 4096
-    q, z, rs, exp = wl.make_verify_batch(PyBackend(curve), curve, n0, 0xB2000003)
-    ok = (ctypes.c_uint8 * n0)()
+    op, curve = args.op, args.curve
+    case = CASES[(op, curve)]
+    cid = {"k256": 0, "p256": 1, "p384": 2, "sm2": 3}[curve]
+    fb = FB[curve]
+    # calibrate on 2^12 rows, then size one step for about 2.5 s of CPU work (a power of two of rows, at most the config size)
+    be = PyBackend(curve)
+    seed = case["seed"]
+
+    def make(n):
+        if op == "verify":
+            q, z, rs, exp = wl.make_verify_batch(be, curve, n, seed)
+            return (q.tobytes(), z.tobytes(), rs.tobytes()), exp
+        base = wl.random_scalars(n, fb, seed)
+        k = wl.random_scalars(n, fb, seed + 1)
+        if op == "mul_gen":
+            return (k.tobytes(),), None
+        return (np.ascontiguousarray(be.mul_gen_xy(base)).tobytes(), k.tobytes()), None
+
+    slot = 1 + (fb if curve == "k256" else 2 * fb)
+
+    def run(n, bufs, out):
+        if op == "verify":
+            lib.port_verify(cid, n, bufs[0], bufs[1], bufs[2], out)
+        elif op == "mul_gen":
+            lib.port_mul_gen(cid, n, bufs[0], out, 1 if curve == "k256" else 0)
+        else:
+            lib.port_mul_var(cid, n, bufs[0], bufs[1], out, 1 if curve == "k256" else 0)
+
+    n0 = 1 << 12
+    bufs, exp = make(n0)
+    out = (ctypes.c_uint8 * (n0 * (1 if op == "verify" else slot)))()
+    run(n0, bufs, out)          # first call builds the port's fixed-base tables and spins up the OpenMP team
     t = time.time()
-    lib.port_verify(0, n0, q.tobytes(), z.tobytes(), rs.tobytes(), ok)
+    run(n0, bufs, out)
     rate = n0 / max(time.time() - t, 1e-6)
-    assert bytes(ok) == exp.tobytes(), "C++ port disagrees with the constructed mask"
-    n = int(min(1 << 20, max(n0, rate * 2.0)))
-    reps = (n + n0 - 1) // n0
-    qq, zz, rr = np.tile(q, (reps, 1))[:n], np.tile(z, (reps, 1))[:n], np.tile(rs, (reps, 1))[:n]
-    qb, zb, rb = qq.tobytes(), zz.tobytes(), rr.tobytes()
-    okn = (ctypes.c_uint8 * n)()
+    if exp is not None:
+        assert bytes(out) == exp.tobytes(), "C++ port disagrees with the constructed mask"
+    lg = max(12, min(case["log2"], 19, int(np.floor(np.log2(max(rate * 2.5, n0))))))
+    n = 1 << lg
+    bufs, exp = make(n)
+    out = (ctypes.c_uint8 * (n * (1 if op == "verify" else slot)))()
     for _ in range(args.warmup):
-        lib.port_verify(0, n, qb, zb, rb, okn)
+        run(n, bufs, out)
     t = time.time()
     for _ in range(args.steps):
-        lib.port_verify(0, n, qb, zb, rb, okn)
+        run(n, bufs, out)
     dt = time.time() - t
+    if exp is not None:
+        assert bytes(out) == exp.tobytes(), "C++ port disagrees with the constructed mask"
     value = n * args.steps / dt
-    sample = f"{n} rows per step ({n0} distinct signatures tiled), {args.steps} steps"
+    sample = f"the first 2^{lg} = {n} rows of the same seeded batch ({case['cfg']}, seed {seed:#x}; all rows distinct), {args.steps} steps"
     emit({
-        "impl": "reference", "metric": "secp256k1 ECDSA verify_prehash throughput", "value": round(value, 1), "unit": "verifies/s",
+        "impl": "reference", "metric": case["metric"], "value": round(value, 1), "unit": case["unit"],
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (5x52 field, u128 accumulators)",
-        "data": "synthetic", "config": config_block(args.gpus, bounded=sample),
-        "cpu_baseline": {"value": round(value, 1), "unit": "verifies/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": round(value, 1), "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference = C++ port of the reference's CPU algorithms (oracle/ecport.cpp, OpenMP); the Rust reference cannot be built here (no cargo/rustc)"})
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u64 limbs (5x52 field with u128 accumulators; 4x64 / 6x64 Montgomery)",
+        "data": "synthetic", "config": config_block(args, args.gpus, bounded=sample),
+        "cpu_baseline": {"value": round(value, 1), "unit": case["unit"], "cores": cores, "kind": "port", "sample": sample,
+                         "per_core": round(value / max(cores, 1), 1)},
+        "e2e": {"value": round(value, 1), "unit": case["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = C++ port of the reference's CPU algorithms (oracle/ecport.cpp, OpenMP, Stein invert_vartime as in "
+                "k256/src/arithmetic/scalar.rs:467-516); the Rust reference cannot be built here (no cargo/rustc)"})
 
 
 def importlib_pkg():
@@ -205,15 +283,21 @@ def importlib_pkg():
     return pkg
 
 
-def config_block(n_gpus, bounded=None, curve="k256", log2_rows=22):
-    rows = 1 << log2_rows
-    if curve == "k256":
-        what = "BASELINE configs[2]: secp256k1 ECDSA verify_prehash, 2^%d signatures per GPU" % log2_rows
-    else:   # --curve p256: BASELINE configs[3] (P-256 verify via the primeorder path), same construction, same sharding
-        what = "BASELINE configs[3]: p256 ECDSA verify_prehash, 2^%d signatures per GPU" % log2_rows
-    c = {"workload": what + " (2^16 distinct keys, 1/16 rows corrupted), sharded by index range, no collective",
-         "rows_per_gpu": rows, "global_rows": rows * n_gpus, "curve": curve,
-         "l2_policy": "inputs (%d MB per step) larger than L2 (126 MB)" % (rows * 160 // 1000000), "parallelism": f"index-shard x{n_gpus}"}
+def config_block(args, n_gpus, bounded=None):
+    case = CASES[(args.op, args.curve)]
+    lg = args.log2_rows or case["log2"]
+    rows = 1 << lg
+    what = {"verify": "%s ECDSA verify_prehash (2^16 distinct keys, 1/16 rows corrupted)", "mul_var": "%s variable-base P*k + normalisation to SEC1",
+            "mul_gen": "%s fixed-base G*k, constant-time path, SEC1 output"}[args.op] % args.curve
+    strong = args.scaling == "strong"
+    fb = FB[args.curve]
+    c = {"workload": "BASELINE %s: %s, 2^%d rows %s, sharded by index range, no collective" % (case["cfg"], what, lg, "in ONE global batch" if strong else "per GPU"),
+         "op": args.op, "curve": args.curve, "rows_per_gpu": rows // n_gpus if strong else rows, "global_rows": rows if strong else rows * n_gpus,
+         "l2_policy": "inputs (%d MB per step per GPU) %s L2 (126 MB)" % ((rows // (n_gpus if strong else 1)) * 5 * fb // 1000000,
+                                                                          "larger than" if (rows // (n_gpus if strong else 1)) * 5 * fb > 126e6 else "NOT larger than; successive steps re-read them from"),
+         "parallelism": f"index-shard x{n_gpus}"}
+    if args.op == "mul_gen":
+        c["l2_policy"] = "inputs are 2 MB: a 256 MB buffer is written between timed steps (L2 flush); the kernel is compute-bound either way"
     if bounded:
         c["bounded_sample"] = bounded
     return c
@@ -239,6 +323,96 @@ def emit(obj):
     out.flush()
 
 
+class Work:
+    """One BASELINE workload on one GPU: device-resident and host-pointer invocations of the same rows, plus its check."""
+
+    def __init__(self, pkg, eng, dev, stream, op, curve, rows, seed, lo=0, hi=None, ct=False, projective=None):
+        import torch
+        self.pkg, self.eng, self.op, self.curve, self.st, self.ct = pkg, eng, op, curve, stream, ct
+        wl = pkg.workloads
+        fb = self.fb = FB[curve]
+        hi = rows if hi is None else hi
+        self.n = hi - lo
+        self.flags = (pkg.FLAG_CT if ct else 0)
+        be = wl.EngineBackend(eng, curve)
+        if op == "verify":
+            q, z, rs, exp = wl.make_verify_batch(be, curve, rows, seed)
+            self.host_in = [np.ascontiguousarray(a[lo:hi]) for a in (q, z, rs)]
+            self.exp = exp[lo:hi]
+            self.out_bytes = 1
+        elif op == "mul_gen":
+            self.flags = pkg.FLAG_CT          # config 1 is the signing / keygen shape: always the constant-time kernel
+            self.ct = True
+            self.host_in = [np.ascontiguousarray(wl.random_scalars(rows, fb, seed)[lo:hi])]
+            self.slot = pkg.slot_bytes(curve, 0)
+            self.out_bytes = self.slot
+        else:
+            self.projective = CASES.get((op, curve), {}).get("projective", False) if projective is None else projective
+            pts, k = wl.make_mul_var_batch(be, curve, rows, seed, projective=self.projective)
+            self.host_in = [np.ascontiguousarray(pts[lo:hi]), np.ascontiguousarray(k[lo:hi])]
+            if self.projective:
+                self.flags |= pkg.FLAG_PROJ
+            self.slot = pkg.slot_bytes(curve, 0)
+            self.out_bytes = self.slot
+        self.dev_in = [torch.from_numpy(a).to(dev) for a in self.host_in]
+        self.dev_out = torch.empty(self.n * self.out_bytes, dtype=torch.uint8, device=dev)
+        self.h2d = sum(a.nbytes for a in self.host_in)
+        self.d2h = self.n * self.out_bytes
+        self.pin_in = self.pin_out = None
+
+    def dev(self):
+        e, n, di, st = self.eng, self.n, self.dev_in, self.st
+        if self.op == "verify":
+            e.ecdsa_verify_dev(self.curve, n, di[0], di[1], di[2], self.dev_out, st)
+        elif self.op == "mul_gen":
+            e.mul_gen_dev(self.curve, n, di[0], self.dev_out, self.flags, st)
+        else:
+            e.mul_var_dev(self.curve, n, di[0], None, di[1], self.dev_out, None, self.flags, st)
+
+    def pin(self):
+        import torch
+        if self.pin_in is None:      # page-locked host buffers (the contract's "from pinned host memory"): DMA'd directly by the library
+            self.pin_t = [torch.from_numpy(a).pin_memory() for a in self.host_in]
+            self.pin_in = [t.numpy() for t in self.pin_t]
+            self.pin_out_t = torch.empty(self.n * self.out_bytes, dtype=torch.uint8).pin_memory()
+            self.pin_out = self.pin_out_t.numpy()
+
+    def host(self):
+        """the call a user makes: host pointers in, results in a host buffer when it returns"""
+        self.pin()
+        lib, h, cid, n = self.eng.lib, self.eng.h, self.pkg.curve_id(self.curve), self.n
+        p = [ctypes.c_void_p(a.ctypes.data) for a in self.pin_in]
+        o = ctypes.c_void_p(self.pin_out.ctypes.data)
+        if self.op == "verify":
+            rc = lib.ecb200_ecdsa_verify(h, cid, n, p[0], p[1], p[2], o)
+        elif self.op == "mul_gen":
+            rc = lib.ecb200_mul_gen(h, cid, n, p[0], o, self.flags)
+        else:
+            rc = lib.ecb200_mul_var(h, cid, n, p[0], None, p[1], o, None, self.flags)
+        if rc != 0:
+            raise RuntimeError("host call failed: %d %s" % (rc, lib.ecb200_last_error(h).decode()))
+
+    def check(self, sample_log2=12):
+        """verify: the whole mask against the constructed expectation.  scalar multiplication: the first 2^sample_log2 rows
+        against OpenSSL libcrypto (independent of the engine, the oracle and the port); BASELINE-size 100 % comparisons live in
+        tests/test_gpu_fullsize.py."""
+        got = self.dev_out.cpu().numpy()
+        if self.op == "verify":
+            return {"check": "accept mask == mask implied by construction, all %d rows" % self.n, "ok": bool(np.array_equal(got, self.exp))}
+        from oracle import libcrypto_ref as lc
+        m = min(self.n, 1 << sample_log2)
+        k = self.host_in[-1][:m]
+        if self.op == "mul_gen":
+            exp = lc.mul_batch(self.curve, k.tobytes(), None, None)
+        else:
+            pts = self.host_in[0][:m]
+            if self.projective:     # libcrypto takes affine points: normalise the projective inputs with the engine (checked in tests)
+                xy, _ = self.eng.batch_normalize(self.curve, pts)
+                pts = np.frombuffer(xy, np.uint8)
+            exp = lc.mul_batch(self.curve, k.tobytes(), pts.tobytes(), None)
+        return {"check": "first %d rows == OpenSSL libcrypto EC_POINT_mul" % m, "ok": bool(got[:m * self.slot].tobytes() == exp)}
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -246,11 +420,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--log2-rows", type=int, default=22, help="rows per GPU (default 2^22 = the BASELINE config)")
-    ap.add_argument("--curve", default="k256", choices=["k256", "p256"], help="k256 = BASELINE configs[2] (the headline), p256 = configs[3]")
+    ap.add_argument("--op", default="verify", choices=["verify", "mul_var", "mul_gen"], help="verify = BASELINE configs[2]/[3]; mul_var = configs[1]/[4]; mul_gen = configs[0]")
+    ap.add_argument("--curve", default="k256", choices=["k256", "p256", "p384", "sm2"])
+    ap.add_argument("--ct", action="store_true", help="mul_var: the secret-scalar (constant-time) kernels instead of the public-input path")
+    ap.add_argument("--log2-rows", type=int, default=0, help="rows per GPU (weak) or in the global batch (strong); default = the BASELINE config's size")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: every rank processes its own 2^L rows; strong: ONE 2^L-row batch, each rank takes shard_range(rank)")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if (args.op, args.curve) not in CASES:
+        raise SystemExit("no BASELINE config for --op %s --curve %s" % (args.op, args.curve))
     if args.impl == "reference":
         return run_reference(args)
 
@@ -265,21 +444,24 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib_pkg()
-    wl = pkg.workloads
     eng = pkg.Engine(local)
     dev = torch.device("cuda", local)
     ts = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(ts)
     st = ts.cuda_stream
-    curve, n = args.curve, 1 << args.log2_rows
-    fb = 32
-    seed = 0xB2000003 if curve == "k256" else 0xB2000004
+    op, curve = args.op, args.curve
+    case = CASES[(op, curve)]
+    rows = 1 << (args.log2_rows or case["log2"])
+    steps, warmup = args.steps, max(args.warmup, 3)
 
-    # ---- inputs (synthetic, generated by the engine; not timed)
-    q, z, rs, exp = wl.make_verify_batch(wl.EngineBackend(eng, curve), curve, n, seed + 1000 * rank)
-    d_q, d_z, d_rs = torch.from_numpy(q).to(dev), torch.from_numpy(z).to(dev), torch.from_numpy(rs).to(dev)
-    d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
-    h_ok = np.empty(n, np.uint8)
+    # ---- inputs (synthetic, generated by the engine; not timed).  strong: the same global batch on every rank, own shard only
+    if args.scaling == "strong":
+        lo, hi = pkg.shard_range(rows, rank, world)
+        w = Work(pkg, eng, dev, st, op, curve, rows, case["seed"], lo, hi, ct=args.ct)
+    else:
+        w = Work(pkg, eng, dev, st, op, curve, rows, case["seed"] + 1000 * rank, ct=args.ct)
+    n = w.n
+    n_global = rows if args.scaling == "strong" else rows * world
 
     def barrier():
         torch.cuda.synchronize()
@@ -287,26 +469,27 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
+    def max_over_ranks(v):
         if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     # ---- kernel-resident timing
-    for _ in range(max(args.warmup, 3)):
-        eng.ecdsa_verify_dev(curve, n, d_q, d_z, d_rs, d_ok, st)
+    for _ in range(warmup):
+        w.dev()
     barrier()
-    assert np.array_equal(d_ok.cpu().numpy(), exp), "verify mask differs from the constructed expectation"
+    chk = w.check()
+    assert chk["ok"], "output check failed: " + chk["check"]
     l0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     eng.kernel_timing(True)
     with ClockSampler(local) as clk:
         barrier()
         e0.record(ts)
-        for _ in range(args.steps):
-            eng.ecdsa_verify_dev(curve, n, d_q, d_z, d_rs, d_ok, st)
+        for _ in range(steps):
+            w.dev()
         e1.record(ts)
         barrier()
     eng.kernel_timing(False)
@@ -314,46 +497,43 @@ def main():
     kernel_ms = max_over_ranks(k_ms / max(k_cnt, 1))
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count - l0
-    ms_step = ms_total / args.steps
-    value = n * world / (ms_step * 1e-3)
+    ms_step = ms_total / steps
+    value = n_global / (ms_step * 1e-3)
     clocks = clk.summary()
 
     # ---- end to end through the host-pointer C ABI (H2D + kernels + D2H per step)
-    # inputs and the result live in page-locked host memory (the contract's "from pinned host memory"); the library
-    # copies chunk i+1 H2D and chunk i-1 D2H on side streams while chunk i computes
-    pq, pz, prs = (torch.from_numpy(a).pin_memory() for a in (q, z, rs))
-    pok = torch.empty(n, dtype=torch.uint8).pin_memory()
-    hq, hz, hrs, hok = pq.numpy(), pz.numpy(), prs.numpy(), pok.numpy()
+    # inputs and the result live in page-locked host memory; the library copies chunk i+1 H2D and chunk i-1 D2H on side
+    # streams while chunk i computes
     for _ in range(2):
-        eng.ecdsa_verify(curve, hq, hz, hrs, out=hok)
-    assert np.array_equal(hok, exp)
+        w.host()
+    if op == "verify":
+        assert np.array_equal(w.pin_out, w.exp)
+    else:
+        assert np.array_equal(w.pin_out, w.dev_out.cpu().numpy()), "host-pointer call and device-pointer call disagree"
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.ecdsa_verify(curve, hq, hz, hrs, out=hok)
+    for _ in range(steps):
+        w.host()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e_value = n * world * args.steps / dt
+    dt = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n_global * steps / dt
 
+    io = IO_BYTES["mul_var_proj" if (op == "mul_var" and w.projective) else op](w.fb, getattr(w, "slot", 1))
     out = {
-        "metric": ("secp256k1" if curve == "k256" else "P-256") + " ECDSA verify_prehash throughput", "value": round(value, 1), "unit": "verifies/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (8x32, IMAD.WIDE carry chains)", "data": "synthetic",
-        "config": config_block(world, None, curve, args.log2_rows), "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": round(e2e_value, 1), "unit": "verifies/s", "h2d_bytes_per_step": int(n * 5 * fb), "d2h_bytes_per_step": int(n),
-                "ms_per_step": round(dt / args.steps * 1e3, 3), "api": "ecb200_ecdsa_verify (host pointers to page-locked buffers; chunked H2D / compute / D2H overlap inside the call)"},
-        "roofline": roofline("verify", curve, value / world, ms_step, n, clocks.get("sm_mhz"), kernel_ms,
-                             "k_verify_main<CurveK256, VM_ECDSA>" if curve == "k256" else "k_verify_main<CurveP256, VM_ECDSA> (+ k_wintab<CurveP256> before it)"),
+        "metric": case["metric"], "value": round(value, 1), "unit": case["unit"], "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "u32 limbs (%dx32, IMAD.WIDE carry chains)" % (w.fb // 4), "data": "synthetic",
+        "config": config_block(args, world), "clocks": clocks, "gpu_launches": int(launches), "output_check": chk,
+        "e2e": {"value": round(e2e_value, 1), "unit": case["unit"], "h2d_bytes_per_step": int(w.h2d), "d2h_bytes_per_step": int(w.d2h),
+                "ms_per_step": round(dt / steps * 1e3, 3),
+                "api": "ecb200_%s (host pointers to page-locked buffers; chunked H2D / compute / D2H overlap inside the call)" % {"verify": "ecdsa_verify", "mul_var": "mul_var", "mul_gen": "mul_gen"}[op]},
+        "roofline": roofline(op, curve, n, ms_step, clocks.get("sm_mhz"), kernel_ms, ct=args.ct, io=io),
     }
 
-    if rank == 0 and world == 1 and not args.no_others and curve == "k256":
-        out["others"] = other_configs(pkg, eng, dev, ts)
-    if rank == 0 and world == 1 and not args.no_cpu and curve == "k256":
-        out["cpu_baseline"] = cpu_baseline(q, z, rs, exp)
+    if rank == 0 and world == 1 and not args.no_others and (op, curve) == ("verify", "k256"):
+        out["others"] = other_configs(pkg, eng, dev, ts, clocks.get("sm_mhz"))
+    if rank == 0 and world == 1 and not args.no_cpu and op == "verify":
+        out["cpu_baseline"] = cpu_baseline(curve, *w.host_in, w.exp)
     if rank == 0:
         emit(out)
     if world > 1:
@@ -361,33 +541,35 @@ def main():
         dist.destroy_process_group()
 
 
-def cpu_baseline(q, z, rs, exp):
+def cpu_baseline(curve, q, z, rs, exp):
     """C++ port of the reference algorithms on the host cores, bounded sample of the same batch."""
     from tests import port_lib
     lib = port_lib.load()
+    cid = {"k256": 0, "p256": 1, "p384": 2, "sm2": 3}[curve]
     n0 = 1 << 12
     ok = (ctypes.c_uint8 * n0)()
     t = time.time()
-    lib.port_verify(0, n0, q[:n0].tobytes(), z[:n0].tobytes(), rs[:n0].tobytes(), ok)
+    lib.port_verify(cid, n0, q[:n0].tobytes(), z[:n0].tobytes(), rs[:n0].tobytes(), ok)
     rate = n0 / max(time.time() - t, 1e-6)
     n = int(min(q.shape[0], max(n0, rate * 8.0)))
     ok = (ctypes.c_uint8 * n)()
     qb, zb, rb = q[:n].tobytes(), z[:n].tobytes(), rs[:n].tobytes()
     t = time.time()
-    lib.port_verify(0, n, qb, zb, rb, ok)
+    lib.port_verify(cid, n, qb, zb, rb, ok)
     dt = time.time() - t
     agree = bytes(ok) == exp[:n].tobytes()
-    out = {"value": round(n / dt, 1), "unit": "verifies/s", "cores": lib.port_threads(), "kind": "port",
+    cores = lib.port_threads()
+    out = {"value": round(n / dt, 1), "unit": "verifies/s", "cores": cores, "kind": "port", "per_core": round(n / dt / max(cores, 1), 1),
            "sample": f"first {n} rows of the same batch, one pass ({dt:.1f} s)", "matches_gpu_mask": bool(agree)}
     try:   # second CPU figure: OpenSSL libcrypto (ECDSA_do_verify + low-s rule) on the same cores (BASELINE.md §3 item 2)
         from oracle import libcrypto_ref as lc
         m = 1 << 13
         t = time.time()
-        lc.verify_batch("k256", q[:m].tobytes(), z[:m].tobytes(), rs[:m].tobytes())
+        lc.verify_batch(curve, q[:m].tobytes(), z[:m].tobytes(), rs[:m].tobytes())
         rate = m / max(time.time() - t, 1e-6)
         m = int(min(q.shape[0], max(m, rate * 5.0)))
         t = time.time()
-        okl = lc.verify_batch("k256", q[:m].tobytes(), z[:m].tobytes(), rs[:m].tobytes())
+        okl = lc.verify_batch(curve, q[:m].tobytes(), z[:m].tobytes(), rs[:m].tobytes())
         dt2 = time.time() - t
         out["openssl"] = {"value": round(m / dt2, 1), "unit": "verifies/s", "cores": lc.threads_used(), "version": lc.lib().OpenSSL_version(0).decode()
                           if hasattr(lc.lib(), "OpenSSL_version") else "libcrypto", "sample": f"first {m} rows ({dt2:.1f} s), oracle/osslref.c (OpenMP)" if lc.driver() else f"first {m} rows ({dt2:.1f} s), ctypes + thread pool",
@@ -397,60 +579,71 @@ def cpu_baseline(q, z, rs, exp):
     return out
 
 
-def other_configs(pkg, eng, dev, ts):
-    """BASELINE configs 1, 2, 4, 5 at their own sizes, kernel-resident (CUDA events, 1 warm-up + 2 timed)."""
+def other_configs(pkg, eng, dev, ts, sm_mhz):
+    """BASELINE configs 1, 2, 4, 5 at their own sizes: kernel-resident rate (CUDA events, 1 warm-up + timed repetitions), the
+    end-to-end rate through the host-pointer call, an output check, and the hardware roofline fraction of the step."""
     import torch
     wl = pkg.workloads
     st = ts.cuda_stream
     res = []
 
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2 (126 MB): written between timed repetitions
+
     def timed(fn, reps=2):
+        """mean device time per repetition; L2 is flushed before each one (outside its event pair): some of these inputs fit L2"""
         fn()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(ts)
+        tot = 0.0
         for _ in range(reps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
             fn()
-        e1.record(ts)
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
+            e1.record(ts)
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps
 
-    # config 1: k256 fixed-base, 2^16 scalars, constant-time path, compressed SEC1
-    n = 1 << 16
-    k = torch.from_numpy(wl.random_scalars(n, 32, 0xB2000001)).to(dev)
-    o = torch.empty(n * 33, dtype=torch.uint8, device=dev)
-    ms = timed(lambda: eng.mul_gen_dev("k256", n, k, o, pkg.FLAG_CT, st), 5)
-    res.append({"config": "1: k256 G*k, 2^16 scalars, CT path, 33-B SEC1", "value": round(n / ms * 1e3, 1), "unit": "scalar-mul/s", "ms": round(ms, 4),
-                "roofline_frac": roofline("mul_gen", "k256", n / ms * 1e3, ms, n, None)["frac"]})
-    # config 2: k256 variable-base + batch_normalize, 2^20 projective inputs with random Z
-    n = 1 << 20
-    be = wl.EngineBackend(eng, "k256")
-    xyz, kk = wl.make_mul_var_batch(be, "k256", n, 0xB2000002, projective=True)
-    d_p, d_k = torch.from_numpy(xyz).to(dev), torch.from_numpy(kk).to(dev)
-    o = torch.empty(n * 33, dtype=torch.uint8, device=dev)
-    for name, fl in (("CT", pkg.FLAG_CT), ("VARTIME", 0)):
-        ms = timed(lambda: eng.mul_var_dev("k256", n, d_p, None, d_k, o, None, fl | pkg.FLAG_PROJ, st))
-        res.append({"config": f"2: k256 P*k + batch_normalize, 2^20 (X:Y:Z) inputs, {name}", "value": round(n / ms * 1e3, 1), "unit": "scalar-mul/s",
-                    "ms": round(ms, 4), "roofline_frac": roofline("mul_var", "k256", n / ms * 1e3, ms, n, None)["frac"]})
-    # config 4: p256 verify, 2^22 rows on this GPU (BASELINE quotes the same batch spread over 8 GPUs)
-    n = 1 << 22
-    q, z, rs, exp = wl.make_verify_batch(wl.EngineBackend(eng, "p256"), "p256", n, 0xB2000004)
-    d_q, d_z, d_rs = torch.from_numpy(q).to(dev), torch.from_numpy(z).to(dev), torch.from_numpy(rs).to(dev)
-    d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
-    ms = timed(lambda: eng.ecdsa_verify_dev("p256", n, d_q, d_z, d_rs, d_ok, st))
-    res.append({"config": "4: p256 ECDSA verify_prehash, 2^22 rows on 1 GPU", "value": round(n / ms * 1e3, 1), "unit": "verifies/s", "ms": round(ms, 4),
-                "mask_ok": bool(np.array_equal(d_ok.cpu().numpy(), exp)),
-                "roofline_frac": roofline("verify", "p256", n / ms * 1e3, ms, n, None)["frac"]})
-    # config 5: p384 and sm2 variable-base, 2^20 each on this GPU (BASELINE quotes the same batches on 8 GPUs)
-    for cname in ("p384", "sm2"):
-        n = 1 << 20
-        fb = 48 if cname == "p384" else 32
-        pts, kk = wl.make_mul_var_batch(wl.EngineBackend(eng, cname), cname, n, 0xB2000005)
-        d_p, d_k = torch.from_numpy(pts).to(dev), torch.from_numpy(kk).to(dev)
-        o = torch.empty(n * (1 + 2 * fb), dtype=torch.uint8, device=dev)
-        ms = timed(lambda: eng.mul_var_dev(cname, n, d_p, None, d_k, o, None, 0, st))
-        res.append({"config": f"5: {cname} P*k, 2^20 on 1 GPU, uncompressed SEC1", "value": round(n / ms * 1e3, 1), "unit": "scalar-mul/s",
-                    "ms": round(ms, 4), "roofline_frac": roofline("mul_var", cname, n / ms * 1e3, ms, n, None)["frac"]})
+    def host_timed(fn, reps=2):
+        fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(reps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            tot += time.perf_counter() - t0
+        return tot / reps * 1e3
+
+    def config(label, op, curve, ct=False, reps=2, log2=None, projective=None):
+        case = CASES[(op, curve)]
+        n = 1 << (log2 or case["log2"])
+        w = Work(pkg, eng, dev, st, op, curve, n, case["seed"], ct=ct, projective=projective)
+        eng.kernel_timing(True)
+        ms = timed(w.dev, reps)
+        eng.kernel_timing(False)
+        k_ms, k_cnt = eng.kernel_timing_read()
+        chk = w.check()
+        hms = host_timed(w.host, reps)
+        io = IO_BYTES["mul_var_proj" if (op == "mul_var" and w.projective) else op](w.fb, getattr(w, "slot", 1))
+        rf = roofline(op, curve, n, ms, sm_mhz, k_ms / max(k_cnt, 1), ct=ct, io=io)
+        res.append({"config": label, "value": round(n / ms * 1e3, 1), "unit": case["unit"], "ms": round(ms, 4),
+                    "e2e": {"value": round(n / hms * 1e3, 1), "ms": round(hms, 4), "h2d_bytes": int(w.h2d), "d2h_bytes": int(w.d2h)},
+                    "output_check": chk,
+                    "roofline": {k: rf.get(k) for k in ("kernel", "kernel_ms_per_launch", "achieved", "peak", "frac", "frac_of_nominal", "step_executed_frac",
+                                                        "fmaheavy_pipe_pct", "frac_ref_normalised", "traffic", "executed_source", "note") if rf.get(k) is not None}})
+        del w
+        torch.cuda.empty_cache()
+
+    config("1: k256 G*k, 2^16 scalars, CT path, 33-B SEC1", "mul_gen", "k256", ct=True, reps=5)
+    config("2: k256 P*k + batch_normalize, 2^20 (X:Y:Z) inputs, VARTIME (public scalars)", "mul_var", "k256")
+    config("2: k256 P*k + batch_normalize, 2^20 (X:Y:Z) inputs, CT (secret scalars)", "mul_var", "k256", ct=True)
+    config("4: p256 ECDSA verify_prehash, 2^22 rows on 1 GPU", "verify", "p256")
+    config("5: p384 P*k, 2^20 on 1 GPU, uncompressed SEC1", "mul_var", "p384")
+    config("5: sm2 P*k, 2^20 on 1 GPU, uncompressed SEC1", "mul_var", "sm2")
+
     # SURVEY §8 f4 tail: the primeorder template on 24-byte fields (P-192), verify at 2^20
     n = 1 << 20
     q, z, rs, exp = wl.make_verify_batch(wl.EngineBackend(eng, "p192"), "p192", n, 0xB2000008)
@@ -458,9 +651,8 @@ def other_configs(pkg, eng, dev, ts):
     d_ok = torch.empty(n, dtype=torch.uint8, device=dev)
     ms = timed(lambda: eng.ecdsa_verify_dev("p192", n, d_q, d_z, d_rs, d_ok, st))
     res.append({"config": "f4: p192 ECDSA verify_prehash, 2^20 rows", "value": round(n / ms * 1e3, 1), "unit": "verifies/s", "ms": round(ms, 4),
-                "mask_ok": bool(np.array_equal(d_ok.cpu().numpy(), exp))})
+                "output_check": {"check": "accept mask == mask implied by construction", "ok": bool(np.array_equal(d_ok.cpu().numpy(), exp))}})
     # SURVEY §8f rows at 2^20 (k256): compressed-key verify, recovery, BIP340 (inputs made by the engine's own signer)
-    n = 1 << 20
     rng = np.random.default_rng(0xB2000007)
 
     def scal():
@@ -477,20 +669,30 @@ def other_configs(pkg, eng, dev, ts):
     ms = timed(lambda: eng.ecdsa_sign_dev("k256", n, d_d, d_k, d_z, d_rs, d_id, d_ok, st))
     all_ok = bool(d_ok.all().item())
     res.append({"config": "f4: k256 ECDSA sign (CT fixed-base k*G + batched k^-1), 2^20", "value": round(n / ms * 1e3, 1), "unit": "signatures/s",
-                "ms": round(ms, 4), "all_ok": all_ok})
+                "ms": round(ms, 4), "output_check": {"check": "every row signs; the signatures verify and recover below", "ok": all_ok}})
     eng.mul_gen_dev("k256", n, d_d, d_pub, pkg.FLAG_CT, st)
     ms = timed(lambda: eng.ecdsa_verify_sec1_dev("k256", n, d_pub, 33, d_z, d_rs, d_ok, st))
     res.append({"config": "f1: k256 verify_prehash with compressed SEC1 keys (on-device decompression), 2^20", "value": round(n / ms * 1e3, 1),
-                "unit": "verifies/s", "ms": round(ms, 4), "all_ok": bool(d_ok.all().item())})
+                "unit": "verifies/s", "ms": round(ms, 4), "output_check": {"check": "all device-made signatures accepted", "ok": bool(d_ok.all().item())}})
     d_keys = torch.empty(n * 33, dtype=torch.uint8, device=dev)
     ms = timed(lambda: eng.ecdsa_recover_dev("k256", n, d_z, d_rs, d_id, d_keys, d_ok, 0, st))
     res.append({"config": "f2: k256 recover_from_prehash, 2^20", "value": round(n / ms * 1e3, 1), "unit": "recoveries/s", "ms": round(ms, 4),
-                "all_ok": bool(d_ok.all().item()) and bool(torch.equal(d_keys, d_pub))})
+                "output_check": {"check": "recovered keys == signing keys' public points", "ok": bool(d_ok.all().item()) and bool(torch.equal(d_keys, d_pub))}})
     # BIP340: random (invalid) signatures over valid x-only keys exercise the full arithmetic path
     d_pkx = d_pub.view(n, 33)[:, 1:].contiguous()
     ms = timed(lambda: eng.schnorr_verify_dev(n, d_pkx, d_z, d_rs, d_ok, st))
     res.append({"config": "f2: k256 BIP340 Schnorr verify (random signatures over valid keys), 2^20", "value": round(n / ms * 1e3, 1),
-                "unit": "verifies/s", "ms": round(ms, 4)})
+                "unit": "verifies/s", "ms": round(ms, 4), "output_check": {"check": "random signatures all rejected", "ok": not bool(d_ok.any().item())}})
+    # per-row two-term lincomb (LinearCombination::lincomb over slices), public scalars
+    d_out = torch.empty(n * 33, dtype=torch.uint8, device=dev)
+    d_xy = torch.empty(n * 65, dtype=torch.uint8, device=dev)
+    eng.mul_gen_dev("k256", n, d_d, d_xy, pkg.FLAG_UNCOMPRESSED, st)
+    d_p1 = d_xy.view(n, 65)[:, 1:].contiguous()
+    eng.mul_gen_dev("k256", n, d_k, d_xy, pkg.FLAG_UNCOMPRESSED, st)
+    d_p2 = d_xy.view(n, 65)[:, 1:].contiguous()
+    ms = timed(lambda: eng.lincomb2_dev("k256", n, d_p1, d_z, d_p2, d_k, d_out, None, 0, st))
+    res.append({"config": "a4: k256 per-row lincomb x*k + y*l (ecb200_lincomb2, public scalars), 2^20", "value": round(n / ms * 1e3, 1),
+                "unit": "lincombs/s", "ms": round(ms, 4)})
     return res
 
 

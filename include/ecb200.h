@@ -91,9 +91,10 @@ const char* ecb200_version(void);
 uint64_t ecb200_launch_count(const ecb200_ctx* ctx);
 /* Block until everything enqueued on the context's stream has finished. */
 int ecb200_sync(ecb200_ctx* ctx);
-/* Measurement hook (bench.py roofline): while enabled, every launch of the dominant kernel (the main kernel of
- * ecb200_ecdsa_verify*) is bracketed by CUDA events on the stream it is launched on; _read waits for them and
- * returns the summed duration and the number of launches since the last read. */
+/* Measurement hook (bench.py roofline): while enabled, every launch of the dominant kernel of an operation (the main
+ * kernel of ecb200_ecdsa_verify*, the scalar-multiplication kernel of ecb200_mul_var* / ecb200_mul_gen*) is bracketed by
+ * CUDA events on the stream it is launched on; _read waits for them and returns the summed duration and the number of
+ * launches since the last read. */
 int ecb200_kernel_timing(ecb200_ctx* ctx, int enable);
 int ecb200_kernel_timing_read(ecb200_ctx* ctx, double* total_ms, uint64_t* launches);
 

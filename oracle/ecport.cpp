@@ -21,9 +21,9 @@
 //   ecdsa            hazmat::verify_prehashed semantics, k256 low-s rule
 //                    (k256/src/ecdsa.rs:201-208)
 // Deviations (cost-neutral or stated): scalar-field arithmetic uses a generic Montgomery multiplier
-// for every curve and Fermat inversion (the reference's constant-time `invert`, k256 scalar.rs:161-209)
-// instead of the variable-time Stein inversion verify uses (scalar.rs:467-516) — about +8 % on a k256
-// verify; to_affine uses the Fermat chain as the reference does.
+// for every curve; s^-1 in verification is the variable-time Stein inversion the reference calls
+// (Scalar::invert_vartime, k256 scalar.rs:467-516, p256 scalar.rs:365-409); to_affine uses the Fermat
+// chain as the reference does.
 //
 //   g++ -O3 -march=native -fopenmp -shared -fPIC -o oracle/libecport.so oracle/ecport.cpp
 #include <cstdint>
@@ -134,6 +134,40 @@ template <int N, const MontCtx<N>* CTX> struct MF {
         e[0] -= 2;   // p is odd and > 2: no borrow
         return pow(e);
     }
+    // Scalar::invert_vartime - Stein's binary extended GCD on plain values, the schedule of
+    // k256/src/arithmetic/scalar.rs:467-516 and p256/src/arithmetic/scalar.rs:365-409 (u-loop, v-loop, sub-step; halving
+    // an odd A as (A >> 1) + (m >> 1) + 1).  This is what hazmat::verify_prehashed calls for s^-1.  0 -> 0.
+    MF inv_vartime() const {
+        const u64* m = C().p;
+        u64 u[N], v[N], A[N] = {1}, Cc[N] = {0}, half[N];
+        to_plain(u);
+        memcpy(v, m, sizeof v);
+        for (int j = 0; j < N; j++) half[j] = (m[j] >> 1) | (j + 1 < N ? m[j + 1] << 63 : 0);   // FRAC_MODULUS_2
+        auto shr1 = [](u64* x) { for (int j = 0; j < N; j++) x[j] = (x[j] >> 1) | (j + 1 < N ? x[j + 1] << 63 : 0); };
+        auto halve_mod = [&](u64* x) {
+            const bool odd = x[0] & 1;
+            shr1(x);
+            if (odd) {   // + (m - 1) / 2 + 1: stays below m
+                u64 c = 1;
+                for (int j = 0; j < N; j++) { u128 t = (u128)x[j] + half[j] + c; x[j] = (u64)t; c = (u64)(t >> 64); }
+            }
+        };
+        if (is_zero<N>(u)) return zero();
+        while (!is_zero<N>(u)) {
+            while (!(u[0] & 1)) { shr1(u); halve_mod(A); }
+            while (!(v[0] & 1)) { shr1(v); halve_mod(Cc); }
+            if (geq<N>(u, v)) {
+                u64 bw = 0;
+                for (int j = 0; j < N; j++) { u128 t = (u128)u[j] - v[j] - bw; u[j] = (u64)t; bw = (u64)(t >> 64) & 1; }
+                mod_sub<N>(A, A, Cc, m);
+            } else {
+                u64 bw = 0;
+                for (int j = 0; j < N; j++) { u128 t = (u128)v[j] - u[j] - bw; v[j] = (u64)t; bw = (u64)(t >> 64) & 1; }
+                mod_sub<N>(Cc, Cc, A, m);
+            }
+        }
+        return from_plain(Cc);
+    }
 };
 
 // =============================================================================================
@@ -234,7 +268,7 @@ template <int N, const MontCtx<N>* FP, const MontCtx<N>* FN> struct PrimeOrder {
         F X = F::from_plain(qx), Y = F::from_plain(qy);
         if (!on_curve(X, Y)) return false;
         reduce_scalar(z);
-        S w = S::from_plain(s).inv();
+        S w = S::from_plain(s).inv_vartime();   // hazmat::verify_prehashed: s.invert_vartime()
         u64 u1[N], u2[N];
         (S::from_plain(z) * w).to_plain(u1);
         (S::from_plain(r) * w).to_plain(u2);
@@ -519,7 +553,7 @@ static bool k_verify(const u8* q, const u8* zb, const u8* rs) {
     KPt Q;
     if (!k_load_affine(Q, q)) return false;
     k_reduce_scalar(z);
-    KS w = KS::from_plain(s).inv();
+    KS w = KS::from_plain(s).inv_vartime();   // hazmat::verify_prehashed: s.invert_vartime() (k256 scalar.rs:467-516)
     u64 u[2][4];
     (KS::from_plain(z) * w).to_plain(u[0]);
     (KS::from_plain(r) * w).to_plain(u[1]);

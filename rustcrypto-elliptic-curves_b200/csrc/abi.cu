@@ -291,9 +291,29 @@ int ensure_gbig(ecb200_ctx* c, const CurveLaunch* cl) {
 // -------------------------------------------------------------------------------------------
 // device-pointer cores (enqueue only)
 
+// ecb200_kernel_timing: bracket the dominant kernel of an operation with CUDA events on the stream it is launched on
+struct TimedLaunch {
+    ecb200_ctx* c;
+    cudaStream_t s;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    TimedLaunch(ecb200_ctx* c_, cudaStream_t s_) : c(c_), s(s_) {
+        if (!c->timing) return;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+        cudaEventRecord(e0, s);
+    }
+    ~TimedLaunch() {
+        if (!e0) return;
+        cudaEventRecord(e1, s);
+        c->timed.emplace_back(e0, e1);
+    }
+};
+
 int mul_gen_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_k, uint8_t* d_out, uint32_t flags, cudaStream_t s) {
     CU(c, c->proj.reserve(n * 3 * cl->L * 4));
-    cl->mul_gen(s, (flags & ECB200_FLAG_CT) != 0, (int)n, d_k, c->gentab[cl->id], (uint32_t*)c->proj.p);
+    {
+        TimedLaunch t(c, s);
+        cl->mul_gen(s, (flags & ECB200_FLAG_CT) != 0, (int)n, d_k, c->gentab[cl->id], (uint32_t*)c->proj.p);
+    }
     cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 0, resolve_compress(cl, flags) ? 1 : 0, d_out, nullptr, nullptr);
     CU(c, cudaGetLastError());
     return 0;
@@ -315,6 +335,7 @@ int mul_var_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* 
     uint32_t* proj = (uint32_t*)c->proj.p;
     if (flags & ECB200_FLAG_CT) {
         // secret scalars: complete formulas, fixed windows, full table scans
+        TimedLaunch t(c, s);
         cl->mul_var(s, true, (int)n, flags, d_pts, (flags & ECB200_FLAG_PROJ) ? nullptr : d_inf, d_k, proj, d_invalid);
     } else if (flags & ECB200_FLAG_PROJ) {
         // public scalars, projective inputs: normalise once (Montgomery trick), then the Jacobian fast path
@@ -324,11 +345,13 @@ int mul_var_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* 
         uint32_t* wt = nullptr;
         int r = window_tables(c, cl, n, nullptr, (const uint32_t*)c->aff.p, s, &wt);
         if (r) return r;
+        TimedLaunch t(c, s);
         cl->mul_var_fast(s, (int)n, nullptr, (const uint32_t*)c->aff.p, nullptr, d_k, proj, d_invalid, wt);
     } else {
         uint32_t* wt = nullptr;
         int r = window_tables(c, cl, n, d_pts, nullptr, s, &wt);
         if (r) return r;
+        TimedLaunch t(c, s);
         cl->mul_var_fast(s, (int)n, d_pts, nullptr, d_inf, d_k, proj, d_invalid, wt);
     }
     cl->normalize(s, (int)n, proj, 0, resolve_compress(cl, flags) ? 1 : 0, d_out, nullptr, nullptr);
@@ -356,17 +379,8 @@ int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d
         uint32_t* wt = nullptr;
         r = window_tables(c, cl, n, d_q, nullptr, s, &wt);
         if (r) return r;
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (c->timing) {
-            CU(c, cudaEventCreate(&e0));
-            CU(c, cudaEventCreate(&e1));
-            CU(c, cudaEventRecord(e0, s));
-        }
+        TimedLaunch t(c, s);
         cl->verify_main(s, (int)n, mode, d_q, d_rs, d_z, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, nullptr, wt);
-        if (c->timing) {
-            CU(c, cudaEventRecord(e1, s));
-            c->timed.emplace_back(e0, e1);
-        }
     }
     CU(c, cudaGetLastError());
     return 0;

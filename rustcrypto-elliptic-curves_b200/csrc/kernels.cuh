@@ -226,7 +226,11 @@ template <class C> struct Bodies {
         u32 nn[L];
         ECB_UNROLL
         for (int i = 0; i < L; i++) nn[i] = C::n(i);
-        return !is_zero_n<L>(v) && !geq_n<L>(v, nn);
+        // both tests always run and are combined with a bitwise AND: the signing kernel calls this on secret scalars, and
+        // `a && b` compiled to a branch on `a` there (tools/ct_sass_audit.py)
+        const u32 nz = is_zero_n<L>(v) ? 0u : 1u;
+        const u32 lt = geq_n<L>(v, nn) ? 0u : 1u;
+        return (nz & lt) != 0u;
     }
     ECB_DEV static bool finish_verify(const Proj& R, const u32* r, bool valid) {
         // accept <=> Z != 0 and (X == r*Z or (r + n < p and X == (r+n)*Z))   (x mod n == r without inversion)
@@ -706,8 +710,8 @@ template <class C> struct Bodies {
         for (int j = cnt - 1; j >= 0; j--) {
             int i = tid + j * nthreads;
             u32 kk[L], dd[L], zz[L];
-            bool ok = load_secret_scalar(kk, k + (size_t)i * FB);
-            ok = load_secret_scalar(dd, d + (size_t)i * FB) && ok;
+            u32 okm = load_secret_scalar(kk, k + (size_t)i * FB) ? 1u : 0u;       // validity flags are combined as masks, never
+            okm &= load_secret_scalar(dd, d + (size_t)i * FB) ? 1u : 0u;          // with && / || (no branch on secret-derived bits)
             G::load_scalar(zz, z + (size_t)i * FB);
             typename Fn::E km, kinv;
             Fn::from_limbs(km, kk);
@@ -732,7 +736,8 @@ template <class C> struct Bodies {
             copy_n<L>(zm.v, zz);
             Fn::add(t, t, zm);
             Fn::mul_plain(sm.v, t.v, kinv);          // plain s
-            ok = ok && !is_zero_n<L>(rr) && !Fn::is_zero(sm);
+            okm &= is_zero_n<L>(rr) ? 0u : 1u;
+            okm &= Fn::is_zero(sm) ? 0u : 1u;
             if constexpr (C::LOW_S) {                // normalize_s + parity flip (k256/src/ecdsa.rs:192-196)
                 u32 hn[L];
                 ECB_UNROLL
@@ -743,7 +748,7 @@ template <class C> struct Bodies {
                 Fn::select(sm, high, ns, sm);
                 recid ^= high ? 1u : 0u;
             }
-            const u32 m = ok ? 0xFFFFFFFFu : 0u;
+            const u32 m = (u32)0 - okm;
             ECB_UNROLL
             for (int l = 0; l < L; l++) { rr[l] &= m; sm.v[l] &= m; }
             store_be<L>(rs_out + (size_t)i * 2 * FB, rr);
