@@ -564,9 +564,9 @@ def test_abi_error_behaviour_and_reuse(eng):
     e2.close()
 
 
-@pytest.mark.parametrize("cname,lg", [("k256", 22), ("p256", 21)])
+@pytest.mark.parametrize("cname,lg", [("k256", 22), ("p256", 22)])
 def test_verify_full_size_mask(eng, cname, lg):
-    """BASELINE.json's full batch size (2^22 secp256k1 rows; 2^21 P-256 rows to bound the tier's run time): the accept
+    """BASELINE.json's full batch size (configs[2] and configs[3]: 2^22 secp256k1 rows, 2^22 P-256 rows): the accept
     mask must equal the one implied by construction (1/16 of the rows corrupted in five ways), a sampled subset must agree
     with the oracle, and verifying the reversed batch must give the reversed mask (position independence)."""
     import ecb200
