@@ -265,3 +265,21 @@ def test_every_window_table_index_secret_path(eng, cname):
     assert out == o.batch_mul_var_affine(c, pb, None, be(ks, fb)) and not any(inv)
     out2, _ = eng.mul_batch(cname, pb, be(ks, fb), None, 0)
     assert out2 == out
+
+
+def test_plain_c_multi_device_client(tmp_path):
+    """A plain C program drives several shards (every GPU of the box, or two shards on device 0 when there is one GPU) from
+    ONE process through ecb200_init_multi and compares every result with a single-device context."""
+    import os
+    import subprocess
+    import ecb200
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cabi_multi_client")
+    libdir = os.path.dirname(ecb200.LIB_PATH)
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cabi", "multi_client.c"),
+                           "-o", exe, "-L", libdir, "-lecb200", "-Wl,-rpath," + libdir])
+    shards = max(2, torch.cuda.device_count())
+    out = subprocess.run([exe, str(shards)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    assert "cabi multi client ok: %d shards" % shards in out.stdout
