@@ -110,8 +110,21 @@ template <int L> ECB_DEV void select_n(u32* r, bool c, const u32* a, const u32* 
     ECB_UNROLL
     for (int i = 0; i < L; i++) r[i] = c ? a[i] : b[i];
 }
+// Optimisation barrier for masks derived from secrets: after it the compiler no longer knows that the value is 0 or ~0, so
+// it cannot turn (a & m) | (r & ~m) back into a select and then PREDICATE THE LOAD of `a` on the secret comparison.  ptxas did
+// exactly that to the table scans of round 1 (scripts/ct_audit.sh: the local-load sector and shared-wavefront counts of
+// k_mul_var<*, true> / k_mul_gen_smem<*, true> depended on the scalars although no branch did): a scan that only touches the
+// selected entry leaks the digit through the memory system, which is what the full scan exists to prevent
+// (k256/src/arithmetic/mul.rs:92-127, primeorder/src/projective.rs:127-147 use subtle's ConditionallySelectable for the same reason).
+ECB_DEV u32 value_barrier(u32 m) {
+#if defined(__CUDA_ARCH__) || defined(__GNUC__)
+    asm volatile("" : "+r"(m));
+#endif
+    return m;
+}
 // r = mask ? a : r  with an all-ones/zero mask (constant-time table scans)
 template <int L> ECB_DEV void cmov_n(u32* r, const u32* a, u32 mask) {
+    mask = value_barrier(mask);
     ECB_UNROLL
     for (int i = 0; i < L; i++) r[i] = (a[i] & mask) | (r[i] & ~mask);
 }

@@ -228,13 +228,16 @@ template <class C> struct EC {
 #pragma unroll 1
 #endif
         for (int j = 2; j < N; j++) {
-            // operands and result go through named temporaries: a dynamically indexed element of a local array passed by
-            // reference to the non-inlined point functions once produced wrong results (kernels.cuh lincomb_g_q, nvcc 12.9
-            // for sm_100a; root cause not isolated), so no call here ever sees such a reference
-            Proj src = t.e[(j & 1) == 0 ? (j >> 1) : (j - 1)], dst;
-            if ((j & 1) == 0) dbl(dst, src);
-            else add(dst, src, p);
-            t.e[j] = dst;
+            // Table elements are passed to the non-inlined point functions by reference.  Round 2 tried the "copy the
+            // dynamically indexed element to a named temporary first" form here (the pattern kernels.cuh lincomb_g_q needs
+            // for its accumulator operand, nvcc 12.9 / sm_100a): with it k_verify<CurveK256> (the complete-formula verify
+            // kernel) returned wrong results on the B200 while every k_mul_var instance stayed correct, so the direct form,
+            // which passes every test in every kernel that builds a table, stays.  Neither form has a defect visible in the
+            // source or in the host emulation; the root cause is not isolated.  Regression tests: every table index on the
+            // secret path (tests/test_gpu_round2.py), agreement of the two verify kernels on all Wycheproof rows
+            // (tests/test_gpu_parity.py::test_verify_kernels_agree), the MUL vectors in CT mode.
+            if ((j & 1) == 0) dbl(t.e[j], t.e[j >> 1]);
+            else add(t.e[j], t.e[j - 1], p);
         }
     }
     // constant-time |idx| lookup: scan every entry, masked move (k256 mul.rs:92-127,

@@ -1,7 +1,8 @@
 """One launch of a secret-scalar kernel with a chosen SECRET pattern and fixed public inputs (for scripts/ct_audit.sh: the
 ncu counters of the launches must not depend on the secrets).  usage: ct_dyn_run.py <curve> <mul_var|mul_gen|sign>
 The operation runs once per secret pattern - small (1, 2, 3, ...), random, high (n-1, n-2, ...), sparse (single bits) - each in
-its own cudaProfilerStart/Stop range, in this order; scripts/ct_audit_compare.py splits the ncu launch list into four equal parts."""
+its own cudaProfilerStart/Stop range, in this order, then `small` once more (identical inputs: any counter that differs between
+the two `small` runs is measurement noise, not data dependence); scripts/ct_audit_compare.py splits the ncu launch list into five equal parts."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,7 +12,7 @@ import ecb200
 from oracle import ecoracle as o
 
 curve, op = sys.argv[1], sys.argv[2]
-PATTERNS = ["small", "random", "high", "sparse"]
+PATTERNS = ["small", "random", "high", "sparse", "small_again"]      # the last one repeats the first: measurement-noise control
 c = o.curve(curve)
 fb = c.fb
 n = 1 << 14
@@ -23,6 +24,7 @@ st = ts.cuda_stream
 
 
 def secrets(pattern, salt):
+    pattern = "small" if pattern == "small_again" else pattern
     if pattern == "random":
         a = np.random.default_rng(100 + salt).integers(0, 256, size=(n, fb), dtype=np.uint8)
         a[:, 0] &= 0x7F

@@ -56,7 +56,7 @@ def _edge_batch(eng, cname, n, seed):
         xy[i, :fb], xy[i, fb:] = _be(P[0], fb), _be(P[1], fb)
 
     ident = [0]
-    xyz[0, :fb], xyz[0, fb:2 * fb], xyz[0, 2 * fb:] = _be(5, fb), _be(7, fb), _be(0, fb)      # P = identity (Z = 0)
+    xyz[0, :fb], xyz[0, fb:2 * fb], xyz[0, 2 * fb:] = _be(0, fb), _be(7, fb), _be(0, fb)      # P = identity (0 : y : 0)
     k[1] = _be(0, fb)
     k[2] = _be(1, fb)
     k[3] = _be(c.n - 1, fb)

@@ -11,9 +11,11 @@ scans, masked selects), but nothing in C++ forces ptxas to keep a ternary a SEL;
   * each must sit on a source line matching an ALLOW pattern: row guard (tid >= n), loops over public counters, public flags
     (F_PROJ, the `inf` byte), validity of PUBLIC inputs (point on curve / coordinates < p), the mbarrier wait of the TMA copy,
     and loop bounds of the Montgomery-trick bodies (rows per thread).  Anything else is a FINDING and the exit code is 1;
+  * every PREDICATED memory access (@P LDL / LDS / LDG / STL ...) is treated the same way: ptxas predicated the table-scan loads
+    of round 1 on the secret comparison (a masked select turned back into a conditional load), which no branch scan sees;
   * LDL / STL / LDS / LDG whose address register is produced by arithmetic on a value loaded from the secret buffers cannot
-    be proven absent by pattern matching; the dynamic counterpart (scripts/ct_audit.py: identical instruction, branch and
-    memory-sector counts for different secrets under ncu) covers addresses.
+    be proven absent by pattern matching; the dynamic counterpart (scripts/ct_audit.sh: identical instruction, branch and
+    memory-sector counts for different secrets under ncu) covers addresses - and is what found the predicated loads.
 
 usage: ct_sass_audit.py [--out profiles/r02_ct_sass_audit.md]      (needs the built objects in rustcrypto-elliptic-curves_b200/_build)
 """
@@ -99,7 +101,8 @@ def audit_kernel(name, body):
         guard = toks[0] if toks[0].startswith("@") else None
         op = toks[1] if guard else toks[0]
         base = op.split(".")[0]
-        if base not in ("BRA", "EXIT", "RET", "CALL", "BRX", "JMX", "JMP", "BREAK"):
+        is_mem = base in ("LDL", "LDS", "LDG", "LD", "STL", "STS", "STG", "ST", "LDSM", "ATOMS", "ATOMG", "RED")
+        if base not in ("BRA", "EXIT", "RET", "CALL", "BRX", "JMX", "JMP", "BREAK") and not (is_mem and guard and guard != "@PT"):
             continue
         pred = None
         if base in ("BRX", "JMX"):
@@ -123,11 +126,13 @@ def audit_kernel(name, body):
                 if any(re.fullmatch(re.escape(pred) + r",?", x) for x in body_[:2]):
                     setter = "%04x: %s   [%s:%d]" % (ins[j][0], t, os.path.basename(ins[j][2][0]), ins[j][2][1])
                     break
-        cond.append({"addr": addr, "text": text, "file": loc[0], "line": loc[1], "src": src_line(loc[0], loc[1]), "setter": setter, "chain": ch})
+        cond.append({"addr": addr, "text": text, "file": loc[0], "line": loc[1], "src": src_line(loc[0], loc[1]), "setter": setter, "chain": ch, "mem": is_mem})
     findings, allowed = [], []
     for c in cond:
         why = next((w for pat, w in ALLOW if re.search(pat, c["src"])), None)
-        if why is None and c["text"].startswith("BRA.U") and c["setter"]:
+        if why is None and c["mem"] and re.search(r"\bUP\d", c["setter"].split("[")[0]):
+            why = "memory access predicated on a UNIFORM predicate (kernel parameters / warp-uniform counters)"
+        if why is None and (c["text"].startswith("BRA.U") or c["mem"]) and c["setter"]:
             # a branch on a UNIFORM predicate (kernel parameters, CTA index, warp-uniform counters): judged by the line that
             # computed the predicate, since nvdisasm attributes the branch itself to the statement that follows it
             m = re.search(r"\[([\w.]+):(\d+)\]$", c["setter"])
@@ -164,7 +169,7 @@ def main():
                 total_findings += len(findings)
                 ops = " ".join(l for l in body)
                 lines += ["## `%s`" % dem.replace("ecb::", ""), "",
-                          "%d instructions, %d conditional control transfers: %d on public-quantity lines, **%d findings**; indirect branches (BRX/JMX): %d" % (
+                          "%d instructions, %d conditional control transfers / predicated memory accesses: %d on public-quantity lines, **%d findings**; indirect branches (BRX/JMX): %d" % (
                               n, len(findings) + len(allowed), len(allowed), len(findings), len(re.findall(r"\b(BRX|JMX)\b", ops))), ""]
                 if allowed:
                     lines += ["| address | instruction | source line | why public | predicate set by |", "|---|---|---|---|---|"]

@@ -36,9 +36,10 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12, "m
 
 def num(v):
     try:
-        return float(v.replace(",", ""))
+        x = float(v.replace(",", ""))
     except ValueError:
         return None
+    return None if x != x else x       # ncu occasionally reports -nan for a tiny launch: treated as missing
 
 
 def main():
@@ -84,7 +85,7 @@ def main():
         ms = num(v) * UNIT.get(u, 1.0)
         dram = sum(num(m[k][1]) * UNIT.get(m[k][0], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in m and num(m[k][1]) is not None)
         tot_wide += wide; tot_other += other; tot_inst += ninst; tot_dram += dram; tot_ms += ms
-        k = {"kernel": short, "ms": round(ms, 4), "registers": int(num(m["launch__registers_per_thread"][1])),
+        k = {"kernel": short, "ms": round(ms, 4), "registers": int(num(m["launch__registers_per_thread"][1]) or 0),
              "fmaheavy_pct": num(m["sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"][1]),
              "alu_pct": num(m["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"][1]),
              "issue_active_pct": num(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][1]),
