@@ -30,7 +30,7 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-MOV_PATCH = os.environ.get("ECB200_MOV_PATCH", "1") != "0"      # tools/sass_mov_patch.py between ptxas and fatbinary (curve units)
+MOV_PATCH = os.environ.get("ECB200_MOV_PATCH", "0") != "0"      # tools/sass_mov_patch.py between ptxas and fatbinary (curve units)
 PATCHER = os.path.join(os.path.dirname(HERE), "tools", "sass_mov_patch.py")
 
 
