@@ -126,11 +126,11 @@ def imad_peaks(sm_mhz):
     return g * mhz / ref_mhz, nominal, src
 
 
-def prof_key(op, curve, ct=False):
-    return f"{op}_{curve}" + ("_ct" if ct and op == "mul_var" else "")
+def prof_key(op, curve, ct=False, rowpath=False):
+    return f"{op}_{curve}" + ("_ct" if ct and op == "mul_var" else "") + ("_rowpath" if rowpath and op == "verify" else "")
 
 
-def roofline(op, curve, n_rows, step_ms, sm_mhz, kernel_ms=None, ct=False, io=None):
+def roofline(op, curve, n_rows, step_ms, sm_mhz, kernel_ms=None, ct=False, io=None, rowpath=False):
     """Hardware view first: the dominant kernel's executed IMAD.WIDE multiply-accumulates (ncu opcode counts of this build,
     profiles/summary.json) / its launch duration, against the measured IMAD.WIDE peak.  step_executed_frac covers every
     kernel of the step.  frac_ref_normalised = SURVEY §8d's M_ref x W_per_M figure over the same duration."""
@@ -139,8 +139,9 @@ def roofline(op, curve, n_rows, step_ms, sm_mhz, kernel_ms=None, ct=False, io=No
     dur = kernel_ms if kernel_ms else step_ms
     out = {"bound": "imad", "unit": "Gmac/s (32x32->64 multiply-accumulates)", "achieved": None, "peak": round(peak, 1), "frac": None,
            "peak_nominal": round(nominal, 1), "peak_source": src + "; peak_nominal = 32 lanes/clk/SM x 148 x SM clock",
-           "kernel": case.get("kernel"), "kernel_ms_per_launch": round(dur, 4), "rows_per_launch": n_rows, "traffic": None}
-    prof = load_json(os.path.join(ROOT, "profiles", "summary.json"), {}).get(prof_key(op, curve, ct), {})
+           "kernel": (case.get("kernel") or "").replace("k_mul_var_fast<Curve%s>" % curve.upper(), "k_mul_var<Curve%s, true>" % curve.upper()) if (ct and op == "mul_var") else case.get("kernel"),
+           "kernel_ms_per_launch": round(dur, 4), "rows_per_launch": n_rows, "traffic": None}
+    prof = load_json(os.path.join(ROOT, "profiles", "summary.json"), {}).get(prof_key(op, curve, ct, rowpath), {})
     ks = prof.get("kernels") or []
     if ks and prof.get("n_rows"):
         dom = max(ks, key=lambda k: k["ms"])
@@ -326,7 +327,7 @@ def emit(obj):
 class Work:
     """One BASELINE workload on one GPU: device-resident and host-pointer invocations of the same rows, plus its check."""
 
-    def __init__(self, pkg, eng, dev, stream, op, curve, rows, seed, lo=0, hi=None, ct=False, projective=None):
+    def __init__(self, pkg, eng, dev, stream, op, curve, rows, seed, lo=0, hi=None, ct=False, projective=None, n_keys=None):
         import torch
         self.pkg, self.eng, self.op, self.curve, self.st, self.ct = pkg, eng, op, curve, stream, ct
         wl = pkg.workloads
@@ -336,7 +337,7 @@ class Work:
         self.flags = (pkg.FLAG_CT if ct else 0)
         be = wl.EngineBackend(eng, curve)
         if op == "verify":
-            q, z, rs, exp = wl.make_verify_batch(be, curve, rows, seed)
+            q, z, rs, exp = wl.make_verify_batch(be, curve, rows, seed, n_keys=n_keys or wl.N_KEYS)
             self.host_in = [np.ascontiguousarray(a[lo:hi]) for a in (q, z, rs)]
             self.exp = exp[lo:hi]
             self.out_bytes = 1
@@ -483,6 +484,7 @@ def main():
     chk = w.check()
     assert chk["ok"], "output check failed: " + chk["check"]
     l0 = eng.launch_count
+    kt0 = eng.keytab_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     eng.kernel_timing(True)
     with ClockSampler(local) as clk:
@@ -497,6 +499,7 @@ def main():
     kernel_ms = max_over_ranks(k_ms / max(k_cnt, 1))
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count - l0
+    kt1 = eng.keytab_stats()
     ms_step = ms_total / steps
     value = n_global / (ms_step * 1e-3)
     clocks = clk.summary()
@@ -527,8 +530,17 @@ def main():
         "e2e": {"value": round(e2e_value, 1), "unit": case["unit"], "h2d_bytes_per_step": int(w.h2d), "d2h_bytes_per_step": int(w.d2h),
                 "ms_per_step": round(dt / steps * 1e3, 3),
                 "api": "ecb200_%s (host pointers to page-locked buffers; chunked H2D / compute / D2H overlap inside the call)" % {"verify": "ecdsa_verify", "mul_var": "mul_var", "mul_gen": "mul_gen"}[op]},
-        "roofline": roofline(op, curve, n, ms_step, clocks.get("sm_mhz"), kernel_ms, ct=args.ct, io=io),
+        "roofline": roofline(op, curve, n, ms_step, clocks.get("sm_mhz"), kernel_ms, ct=args.ct, io=io, rowpath=(kt1[0] == kt0[0])),
     }
+    if op == "verify":
+        on_tables = (kt1[0] - kt0[0]) // steps
+        out["verify_path"] = {"rows_per_step_on_per_key_tables": int(on_tables), "tables_built_per_step": int((kt1[1] - kt0[1]) // steps),
+                              "note": "rows are grouped by public key inside every call; the 2^16 keys of this workload repeat 64 times, so each key's "
+                                      "multiples 16^w*Q are computed once per call (inside the timed region, nothing is cached between calls) and a row "
+                                      "costs additions only.  With all keys distinct the per-row path runs: see others[] '3b'" if on_tables else
+                                      "per-row path (keys do not repeat enough for per-key tables)"}
+        if on_tables:
+            out["roofline"]["kernel"] = case["kernel"].replace("k_verify_main", "k_verify_keytab").split(" (")[0] + " (per-key tables built by k_kt_base / k_normalize / k_kt_fill before it)"
 
     if rank == 0 and world == 1 and not args.no_others and (op, curve) == ("verify", "k256"):
         out["others"] = other_configs(pkg, eng, dev, ts, clocks.get("sm_mhz"))
@@ -617,18 +629,22 @@ def other_configs(pkg, eng, dev, ts, sm_mhz):
             tot += time.perf_counter() - t0
         return tot / reps * 1e3
 
-    def config(label, op, curve, ct=False, reps=2, log2=None, projective=None):
+    def config(label, op, curve, ct=False, reps=2, log2=None, projective=None, n_keys=None):
         case = CASES[(op, curve)]
         n = 1 << (log2 or case["log2"])
-        w = Work(pkg, eng, dev, st, op, curve, n, case["seed"], ct=ct, projective=projective)
+        w = Work(pkg, eng, dev, st, op, curve, n, case["seed"], ct=ct, projective=projective, n_keys=n_keys)
+        kt0 = eng.keytab_stats()
         eng.kernel_timing(True)
         ms = timed(w.dev, reps)
         eng.kernel_timing(False)
         k_ms, k_cnt = eng.kernel_timing_read()
+        rowpath = eng.keytab_stats()[0] == kt0[0]
         chk = w.check()
         hms = host_timed(w.host, reps)
         io = IO_BYTES["mul_var_proj" if (op == "mul_var" and w.projective) else op](w.fb, getattr(w, "slot", 1))
-        rf = roofline(op, curve, n, ms, sm_mhz, k_ms / max(k_cnt, 1), ct=ct, io=io)
+        rf = roofline(op, curve, n, ms, sm_mhz, k_ms / max(k_cnt, 1), ct=ct, io=io, rowpath=rowpath)
+        if op == "verify" and not rowpath:
+            rf["kernel"] = (rf.get("kernel") or "").replace("k_verify_main", "k_verify_keytab").split(" (")[0]
         res.append({"config": label, "value": round(n / ms * 1e3, 1), "unit": case["unit"], "ms": round(ms, 4),
                     "e2e": {"value": round(n / hms * 1e3, 1), "ms": round(hms, 4), "h2d_bytes": int(w.h2d), "d2h_bytes": int(w.d2h)},
                     "output_check": chk,
@@ -640,7 +656,9 @@ def other_configs(pkg, eng, dev, ts, sm_mhz):
     config("1: k256 G*k, 2^16 scalars, CT path, 33-B SEC1", "mul_gen", "k256", ct=True, reps=5)
     config("2: k256 P*k + batch_normalize, 2^20 (X:Y:Z) inputs, VARTIME (public scalars)", "mul_var", "k256")
     config("2: k256 P*k + batch_normalize, 2^20 (X:Y:Z) inputs, CT (secret scalars)", "mul_var", "k256", ct=True)
-    config("4: p256 ECDSA verify_prehash, 2^22 rows on 1 GPU", "verify", "p256")
+    config("3b: k256 ECDSA verify_prehash, 2^22 rows, ALL KEYS DISTINCT (per-row path: 128 doublings per row)", "verify", "k256", n_keys=1 << 22)
+    config("4: p256 ECDSA verify_prehash, 2^22 rows on 1 GPU (2^16 keys: per-key tables)", "verify", "p256")
+    config("4b: p256 ECDSA verify_prehash, 2^22 rows, ALL KEYS DISTINCT (per-row path)", "verify", "p256", n_keys=1 << 22)
     config("5: p384 P*k, 2^20 on 1 GPU, uncompressed SEC1", "mul_var", "p384")
     config("5: sm2 P*k, 2^20 on 1 GPU, uncompressed SEC1", "mul_var", "sm2")
 

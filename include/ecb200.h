@@ -89,6 +89,13 @@ const char* ecb200_last_error(const ecb200_ctx* ctx);
 const char* ecb200_version(void);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches evidence). */
 uint64_t ecb200_launch_count(const ecb200_ctx* ctx);
+/* Verification statistics since the context was created: rows verified on per-key window tables and tables built.
+ * ecb200_ecdsa_verify* / ecb200_sm2dsa_verify* group the rows of a call by public key; when keys repeat (at least 8 rows per
+ * distinct key) each key's multiples 16^w * Q are computed once per call and every row needs additions only - no doublings.
+ * Calls whose keys do not repeat take the per-row path; results are identical either way.  Nothing is cached between calls.
+ * Environment: ECB200_KEYTAB=0 forces the per-row path.  A `_dev` verification call on this path synchronises its stream once
+ * (the number of distinct keys comes back to the host). */
+int ecb200_keytab_stats(const ecb200_ctx* ctx, uint64_t* rows, uint64_t* tables);
 /* Block until everything enqueued on the context's stream has finished. */
 int ecb200_sync(ecb200_ctx* ctx);
 /* Measurement hook (bench.py roofline): while enabled, every launch of the dominant kernel of an operation (the main

@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "ecb200_ecdsa_sign", "ecb200_decode_points_dev", "ecb200_ecdsa_verify_sec1_dev", "ecb200_ecdsa_recover_dev",
     "ecb200_schnorr_verify_dev", "ecb200_sm2dsa_verify_dev", "ecb200_ecdsa_sign_dev",
     "ecb200_kernel_timing", "ecb200_kernel_timing_read",
-    "ecb200_init_multi", "ecb200_device_count", "ecb200_lincomb2", "ecb200_lincomb2_dev",
+    "ecb200_init_multi", "ecb200_device_count", "ecb200_lincomb2", "ecb200_lincomb2_dev", "ecb200_keytab_stats",
 ]
 DECODE_SEC1, DECODE_COMPACT = 0, 1
 
@@ -86,6 +86,7 @@ def load_library() -> ctypes.CDLL:
     lib.ecb200_launch_count.argtypes = [vp]
     lib.ecb200_launch_count.restype = ctypes.c_uint64
     lib.ecb200_sync.argtypes = [vp]
+    lib.ecb200_keytab_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     lib.ecb200_kernel_timing.argtypes = [vp, ci]
     lib.ecb200_kernel_timing_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
     lib.ecb200_mul_gen.argtypes = [vp, ci, sz, u8p, u8p, u32]
@@ -226,6 +227,12 @@ class Engine:
 
     def sync(self):
         self._check(self.lib.ecb200_sync(self.h), "sync")
+
+    def keytab_stats(self) -> Tuple[int, int]:
+        """(rows verified on per-key window tables, tables built) since the engine was created."""
+        rows, tabs = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.lib.ecb200_keytab_stats(self.h, ctypes.byref(rows), ctypes.byref(tabs)), "keytab_stats")
+        return int(rows.value), int(tabs.value)
 
     def kernel_timing(self, enable: bool):
         self._check(self.lib.ecb200_kernel_timing(self.h, 1 if enable else 0), "kernel_timing")

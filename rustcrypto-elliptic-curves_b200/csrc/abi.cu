@@ -104,6 +104,17 @@ struct ecb200_ctx {
     DevBuf d_in[NSLOT][4], d_out[NSLOT][3];  // staging for host-pointer entry points
     PinBuf h_in[NSLOT][4], h_out[NSLOT][3];
     DevBuf proj2, inv2;                      // second product and its invalid flags (per-row two-term lincomb)
+    // Per-key window tables of the verify path (kernels.cuh): state of ONE call - the rows of its chunks are grouped by public
+    // key incrementally, tables are built once per distinct key and dropped when the call returns (nothing is cached between calls)
+    struct KeyTab {
+        DevBuf htab, gkeys, tab, kvalid, jac, rep, rep_slot, newgid, gid, counter;
+        size_t cap = 0, alloc_groups = 0, total_rows = 0;
+        uint32_t hmask = 0;
+        int built = 0;
+        bool active = false, disabled = true, first = true;
+    } kt;
+    bool use_keytab = true;                  // ECB200_KEYTAB=0: always the per-row path (A/B comparisons, tests of both paths)
+    uint64_t kt_rows = 0, kt_groups = 0;     // statistics: rows verified on per-key tables / tables built (ecb200_keytab_stats)
     std::string err;
     uint64_t launches = 0;                   // kernels launched by this context (launch.h count_launch)
     // ecb200_init_multi: the parent owns one child context per device and no device state of its own; host entry points
@@ -367,6 +378,78 @@ int batch_normalize_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const u
 }
 enum { VM_ECDSA = 0, VM_SM2DSA = 1, VM_SCHNORR = 2, VM_RECOVER = 3, DEC_SEC1 = 0, DEC_COMPACT = 1, FIN_SCHNORR = 0, FIN_RECOVER = 1 };   // = kernels.cuh
 
+// ---- per-key window tables (kernels.cuh).  Policy: a call is eligible when it is large enough to amortise anything
+// (KT_MIN_ROWS); tables are used while the call shows at least KT_MIN_REUSE rows per distinct key (a table costs ~2.6
+// verifications, saves ~0.5 per row) and the distinct keys fit the table memory; the first chunk of a multi-chunk host call
+// must already show two rows per key, so a call with all-distinct keys pays only the grouping kernels (~0.4 % of a step).
+constexpr size_t KT_MIN_ROWS = 4096, KT_MIN_REUSE = 8;
+constexpr size_t KT_MEM_CAP = (size_t)12 << 30;      // bytes of tables per context (180 GB of HBM per GPU)
+
+int kt_begin(ecb200_ctx* c, const CurveLaunch* cl, size_t total_rows, size_t max_chunk, cudaStream_t s) {
+    ecb200_ctx::KeyTab& k = c->kt;
+    k.active = true;
+    k.first = true;
+    k.built = 0;
+    k.total_rows = total_rows;
+    k.disabled = !c->use_keytab || c->verify_v1 || total_rows < KT_MIN_ROWS || total_rows >= ((size_t)1 << 30);
+    if (k.disabled) return 0;
+    const size_t key_bytes = (size_t)cl->kt_key_words * 4;
+    k.cap = std::min(total_rows / KT_MIN_REUSE, KT_MEM_CAP / key_bytes);
+    if (k.cap < 1) { k.disabled = true; return 0; }
+    size_t hs = 1024;
+    while (hs < 2 * (k.cap + max_chunk)) hs <<= 1;
+    k.hmask = (uint32_t)(hs - 1);
+    CU(c, k.htab.reserve(hs * 4));
+    CU(c, k.counter.reserve(16));
+    CU(c, k.gkeys.reserve(k.cap * (size_t)cl->kt_kbw * 4));
+    CU(c, k.kvalid.reserve(k.cap));
+    CU(c, cudaMemsetAsync(k.htab.p, 0xFF, hs * 4, s));
+    CU(c, cudaMemsetAsync(k.counter.p, 0, 16, s));
+    return 0;
+}
+void kt_end(ecb200_ctx* c) { c->kt.active = false; c->kt.disabled = true; }
+
+// groups the n rows of a chunk by key, decides, and builds the tables of the keys first seen in this chunk; *use = verify on tables
+int kt_chunk(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q, cudaStream_t s, bool* use) {
+    ecb200_ctx::KeyTab& k = c->kt;
+    *use = false;
+    CU(c, k.gid.reserve(n * 4));
+    CU(c, k.rep.reserve(n * 4));
+    CU(c, k.rep_slot.reserve(n * 4));
+    CU(c, k.newgid.reserve(n * 4));
+    cl->kt_group(s, (int)n, (const uint32_t*)d_q, (int*)k.htab.p, k.hmask, (uint32_t*)k.gkeys.p, (int*)k.gid.p, (int*)k.rep.p, (int*)k.rep_slot.p,
+                 (int*)k.newgid.p, (int*)k.counter.p, (int)k.cap);
+    int D = 0;
+    CU(c, cudaMemcpyAsync(&D, k.counter.p, 4, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));      // the one host round trip of this path: the number of distinct keys decides what is launched next
+    const bool first = k.first;
+    k.first = false;
+    if ((size_t)D > k.cap || (size_t)D * KT_MIN_REUSE > k.total_rows || (first && n < k.total_rows && (size_t)D * 2 > n)) {
+        k.disabled = true;                // little reuse (or more keys than tables): this chunk and the rest of the call take the per-row path
+        return 0;
+    }
+    if (D > k.built) {
+        const size_t kw = (size_t)cl->kt_key_words;
+        if ((size_t)D > k.alloc_groups) {  // grow the table store (position independent: old tables are copied over)
+            size_t want = std::min(k.cap, std::max<size_t>((size_t)2 * D, 65536));
+            DevBuf bigger;
+            CU(c, bigger.reserve(want * kw * 4));
+            if (k.built > 0) CU(c, cudaMemcpyAsync(bigger.p, k.tab.p, (size_t)k.built * kw * 4, cudaMemcpyDeviceToDevice, s));
+            CU(c, cudaStreamSynchronize(s));
+            k.tab.release();
+            k.tab = bigger;
+            k.alloc_groups = want;
+        }
+        const int cnt = D - k.built;
+        CU(c, k.jac.reserve((size_t)cnt * cl->kt_windows * 3 * cl->L * 4));
+        cl->kt_build(s, k.built, cnt, (const uint32_t*)k.gkeys.p, (uint32_t*)k.jac.p, (uint8_t*)k.kvalid.p, (uint32_t*)k.tab.p);
+        c->kt_groups += (uint64_t)cnt;
+        k.built = D;
+    }
+    *use = true;
+    return 0;
+}
+
 int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q, const uint8_t* d_z, const uint8_t* d_rs, uint8_t* d_ok, cudaStream_t s,
                 int mode = VM_ECDSA) {
     if (c->verify_v1 && mode == VM_ECDSA) {
@@ -375,6 +458,22 @@ int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d
         int r = ensure_gbig(c, cl);
         if (r) return r;
         CU(c, c->prep.reserve(n * (size_t)cl->prep_words * 4));
+        if (c->kt.active && !c->kt.disabled && (mode == VM_ECDSA || mode == VM_SM2DSA) && ((uintptr_t)d_q & 3) == 0) {
+            bool use = false;
+            r = kt_chunk(c, cl, n, d_q, s, &use);
+            if (r) return r;
+            if (use) {     // rows of repeated keys: no doublings, gathered additions from the per-key tables
+                cl->verify_prep(s, (int)n, mode, d_z, d_rs, (uint32_t*)c->prep.p);
+                {
+                    TimedLaunch t(c, s);
+                    cl->verify_keytab(s, (int)n, mode, d_rs, d_z, (const uint32_t*)c->prep.p, (const int*)c->kt.gid.p, (const uint8_t*)c->kt.kvalid.p,
+                                      (const uint32_t*)c->kt.tab.p, c->gbig[cl->id], c->gw, d_ok);
+                }
+                c->kt_rows += n;
+                CU(c, cudaGetLastError());
+                return 0;
+            }
+        }
         cl->verify_prep(s, (int)n, mode, d_z, d_rs, (uint32_t*)c->prep.p);
         uint32_t* wt = nullptr;
         r = window_tables(c, cl, n, d_q, nullptr, s, &wt);
@@ -649,6 +748,7 @@ int ecb200_init(int device, ecb200_ctx** out) {
     if (const char* e = getenv("ECB200_GW")) { int g = atoi(e); if (g == 4 || g == 8 || g == 16) c->gw = g; }
     if (const char* e = getenv("ECB200_VERIFY_V1")) c->verify_v1 = atoi(e) != 0;
     if (const char* e = getenv("ECB200_WINTAB")) c->use_wintab = atoi(e) != 0;
+    if (const char* e = getenv("ECB200_KEYTAB")) c->use_keytab = atoi(e) != 0;
     if (!ok || build_tables(c) != 0) {
         fprintf(stderr, "ecb200_init failed: %s (%s)\n", c->err.c_str(), cudaGetErrorString(cudaGetLastError()));
         ecb200_destroy(c);
@@ -711,6 +811,7 @@ void ecb200_destroy(ecb200_ctx* c) {
     c->proj.release();
     c->proj2.release();
     c->inv2.release();
+    for (DevBuf* b : {&c->kt.htab, &c->kt.gkeys, &c->kt.tab, &c->kt.kvalid, &c->kt.jac, &c->kt.rep, &c->kt.rep_slot, &c->kt.newgid, &c->kt.gid, &c->kt.counter}) b->release();
     c->partial.release();
     c->one_point.release();
     for (int s = 0; s < NSLOT; s++) {
@@ -733,6 +834,13 @@ uint64_t ecb200_launch_count(const ecb200_ctx* c) {
     uint64_t t = c->launches;
     for (const ecb200_ctx* k : c->kids) t += k->launches;
     return t;
+}
+int ecb200_keytab_stats(const ecb200_ctx* c, uint64_t* rows, uint64_t* tables) {
+    if (!c || !rows || !tables) return ECB200_ERR_ARG;
+    *rows = c->kt_rows;
+    *tables = c->kt_groups;
+    for (const ecb200_ctx* k : c->kids) { *rows += k->kt_rows; *tables += k->kt_groups; }
+    return 0;
 }
 int ecb200_sync(ecb200_ctx* c) {
     if (!c) return ECB200_ERR_ARG;
@@ -815,7 +923,10 @@ int ecb200_ecdsa_verify_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d
     DEV_ENTER(c, "ecdsa_verify_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
-    return verify_core(c, cl, n, d_q, d_z, d_rs, d_ok, pick(c, stream));
+    int r = kt_begin(c, cl, n, n, pick(c, stream));
+    if (!r) r = verify_core(c, cl, n, d_q, d_z, d_rs, d_ok, pick(c, stream));
+    kt_end(c);
+    return r;
 }
 int ecb200_lincomb2_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_p1, const uint8_t* d_k1, const uint8_t* d_p2, const uint8_t* d_k2,
                         uint8_t* d_out, uint8_t* d_invalid, uint32_t flags, void* stream) {
@@ -905,9 +1016,12 @@ int ecb200_ecdsa_verify(ecb200_ctx* c, int curve, size_t n, const uint8_t* q, co
     size_t in_sz[3] = {FB * 2, FB, FB * 2};
     uint8_t* o[1] = {ok};
     size_t o_sz[1] = {1};
-    return run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+    int r = kt_begin(c, cl, n, std::min(n, CHUNK), c->stream);
+    if (!r) r = run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
         return verify_core(c, cl, cnt, di[0], di[1], di[2], dout[0], s);
     });
+    kt_end(c);
+    return r;
 }
 int ecb200_field_op(ecb200_ctx* c, int curve, int which, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* ok) {
     const CurveLaunch* cl = curve_of(c, curve);
@@ -1060,7 +1174,10 @@ int ecb200_ecdsa_verify_sec1_dev(ecb200_ctx* c, int curve, size_t n, const uint8
     DEV_ENTER(c, "ecdsa_verify_sec1_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
-    return verify_sec1_core(c, cl, n, d_keys, key_stride, d_z, d_rs, d_ok, pick(c, stream));
+    int r = kt_begin(c, cl, n, n, pick(c, stream));
+    if (!r) r = verify_sec1_core(c, cl, n, d_keys, key_stride, d_z, d_rs, d_ok, pick(c, stream));
+    kt_end(c);
+    return r;
 }
 int ecb200_ecdsa_verify_sec1(ecb200_ctx* c, int curve, size_t n, const uint8_t* keys, size_t key_stride, const uint8_t* z, const uint8_t* rs, uint8_t* ok) {
     const CurveLaunch* cl = curve_of(c, curve);
@@ -1076,9 +1193,12 @@ int ecb200_ecdsa_verify_sec1(ecb200_ctx* c, int curve, size_t n, const uint8_t* 
     size_t in_sz[3] = {key_stride, FB, FB * 2};
     uint8_t* o[1] = {ok};
     size_t o_sz[1] = {1};
-    return run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+    int r = kt_begin(c, cl, n, std::min(n, CHUNK), c->stream);
+    if (!r) r = run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
         return verify_sec1_core(c, cl, cnt, di[0], key_stride, di[1], di[2], dout[0], s);
     });
+    kt_end(c);
+    return r;
 }
 int ecb200_ecdsa_recover_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_z, const uint8_t* d_rs, const uint8_t* d_recid, uint8_t* d_keys,
                              uint8_t* d_ok, uint32_t flags, void* stream) {
@@ -1139,7 +1259,10 @@ int ecb200_sm2dsa_verify_dev(ecb200_ctx* c, size_t n, const uint8_t* d_q, const 
     DEV_ENTER(c, "sm2dsa_verify_dev");
     if (!n) return 0;
     CU(c, cudaSetDevice(c->device));
-    return verify_core(c, cl, n, d_q, d_e, d_rs, d_ok, pick(c, stream), VM_SM2DSA);
+    int r = kt_begin(c, cl, n, n, pick(c, stream));
+    if (!r) r = verify_core(c, cl, n, d_q, d_e, d_rs, d_ok, pick(c, stream), VM_SM2DSA);
+    kt_end(c);
+    return r;
 }
 int ecb200_sm2dsa_verify(ecb200_ctx* c, size_t n, const uint8_t* q, const uint8_t* e, const uint8_t* rs, uint8_t* ok) {
     const CurveLaunch* cl = curve_of(c, ECB200_SM2);
@@ -1154,9 +1277,12 @@ int ecb200_sm2dsa_verify(ecb200_ctx* c, size_t n, const uint8_t* q, const uint8_
     size_t in_sz[3] = {64, 32, 64};
     uint8_t* o[1] = {ok};
     size_t o_sz[1] = {1};
-    return run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
+    int r = kt_begin(c, cl, n, std::min(n, CHUNK), c->stream);
+    if (!r) r = run_pipeline(c, n, 3, in, in_sz, 1, o, o_sz, [&](size_t cnt, const uint8_t* const* di, uint8_t* const* dout, cudaStream_t s) {
         return verify_core(c, cl, cnt, di[0], di[1], di[2], dout[0], s, VM_SM2DSA);
     });
+    kt_end(c);
+    return r;
 }
 int ecb200_ecdsa_sign_dev(ecb200_ctx* c, int curve, size_t n, const uint8_t* d_d, const uint8_t* d_k, const uint8_t* d_z, uint8_t* d_rs, uint8_t* d_recid,
                           uint8_t* d_ok, void* stream) {

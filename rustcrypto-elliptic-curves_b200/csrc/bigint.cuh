@@ -65,6 +65,15 @@ inline u32 mulhi(u32 a, u32 b) { return (u32)(((u64)a * b) >> 32); }
 inline u32 bswap32(u32 x) { return __builtin_bswap32(x); }
 #endif
 
+// 32-bit atomics for the key-grouping kernels (host emulation: the logical threads run one after another)
+#if defined(__CUDA_ARCH__) && !defined(ECB_EMU)
+ECB_DEV int atomic_cas_i32(int* p, int cmp, int val) { return atomicCAS(p, cmp, val); }
+ECB_DEV int atomic_add_i32(int* p, int v) { return atomicAdd(p, v); }
+#else
+inline int atomic_cas_i32(int* p, int cmp, int val) { int o = *p; if (o == cmp) *p = val; return o; }
+inline int atomic_add_i32(int* p, int v) { int o = *p; *p += v; return o; }
+#endif
+
 // ------------------------------------------------------------------------------------------
 // n-limb helpers (all loops fully unrolled; L is a compile-time constant)
 

@@ -24,7 +24,8 @@ enum : u32 {
     F_PROJ = 8u,           // input points are X||Y||Z projective instead of x||y affine
 };
 
-enum : int { NORM_SEC1 = 0, NORM_XY_BYTES = 1, NORM_AFF_LIMBS = 2 };
+enum : int { NORM_SEC1 = 0, NORM_XY_BYTES = 1, NORM_AFF_LIMBS = 2,
+             NORM_AFF_STRIDED = 3 };   // affine limbs, output i at out_limbs + i * stride words (stride passed in `compress`)
 
 // what the two-term public-input pipeline (prep -> main -> optional finish) computes
 enum : int {
@@ -200,7 +201,7 @@ template <class C> struct Bodies {
                 }
                 if (out_inf) out_inf[i] = isinf ? 1 : 0;
             } else {
-                u32* o = out_limbs + (size_t)i * 2 * L;
+                u32* o = out_limbs + (size_t)i * (mode == NORM_AFF_STRIDED ? (size_t)compress : (size_t)2 * L);
                 ECB_UNROLL
                 for (int l = 0; l < L; l++) { o[l] = isinf ? 0u : x.v[l]; o[L + l] = isinf ? 0u : y.v[l]; }
             }
@@ -854,6 +855,245 @@ template <class C> struct Bodies {
         for (int l = 0; l < L; l++) a.v[l] = src[l];
     }
     ECB_DEV static void store_entry(u32* dst, const E& x, const E& y) { store_fe(dst, x); store_fe(dst + L, y); }
+
+
+    // ------------------------------------------------------------------ per-key window tables (keys that repeat inside one call)
+    // Public-input verification spends 84 % of its multiplications on u2*Q: 128 (256, 384) doublings and ~62 window additions
+    // per row.  When the same public key signs many rows of a call - validators, servers, the 2^16 keys of BASELINE's configs
+    // 2 / 3 - the doublings depend on the KEY only.  The verify pipeline therefore groups the rows of a call by key (a hash table
+    // in HBM, byte-exact comparison), builds for every distinct key ONCE the full-position table
+    //     T[g][w][v-1] = v * 16^w * Q_g,   v = 1..8,  w = 0..KT_WINDOWS-1      (affine, field-internal limbs, 2L words per entry)
+    // and verifies each row with KT_WINDOWS (x2 with the GLV split) mixed additions gathered from HBM and NO doublings:
+    // secp256k1 ~920 instead of ~1890 field multiplications per row, P-256 ~890 instead of ~2900.  Tables cost ~5 k
+    // multiplications per key (2.6 verifications), so the path is taken only when the call reuses keys (abi.cu: at least 8 rows
+    // per key); otherwise the per-row path above runs.  Nothing is kept between calls: every call groups and builds afresh.
+    // The reference verifies row by row (k256/src/ecdsa.rs:200-209 -> lincomb, mul.rs:342-393) and recomputes u2*Q every time.
+    static constexpr int KT_WINDOWS = C::A_IS_ZERO ? 33 : 8 * L + 1;      // signed radix-16 digits of a GLV half / of a full scalar, + carry
+    static constexpr int KT_KEY_WORDS = KT_WINDOWS * 8 * 2 * L;           // u32 words of one key's table
+    static constexpr int KBW = 2 * FB / 4;                                // u32 words of one key as it arrives (x||y bytes)
+    static constexpr int KT_EMPTY = -1, KT_OVERFLOW = -2, KT_TAG = 0x40000000;
+
+    ECB_DEV static u32 key_hash(const u32* k) {
+        u32 h = k[0] * 0x9E3779B1u ^ k[1] * 0x85EBCA77u ^ k[2] * 0xC2B2AE3Du ^ k[3] * 0x27D4EB2Fu ^ k[KBW - 1] * 0x165667B1u ^ k[KBW / 2] * 0x9E3779B9u;
+        h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+        return h;
+    }
+    ECB_DEV static bool key_eq(const u32* a, const u32* b) {
+        u32 d = 0;
+        ECB_UNROLL
+        for (int i = 0; i < KBW; i++) d |= a[i] ^ b[i];
+        return d == 0;
+    }
+    // (1) look every row's key up among the groups numbered by earlier chunks of this call (read only): gid = group or -1
+    ECB_DEV static void body_kt_lookup(int tid, int n, const u32* q32, const int* htab, u32 hmask, const u32* gkeys, int* gid) {
+        if (tid >= n) return;
+        const u32* key = q32 + (size_t)tid * KBW;
+        u32 slot = key_hash(key) & hmask;
+        int g = -1;
+        for (;;) {
+            const int v = htab[slot];
+            if (v == KT_EMPTY) break;
+            if (v >= 0 && key_eq(gkeys + (size_t)v * KBW, key)) { g = v; break; }
+            slot = (slot + 1) & hmask;
+        }
+        gid[tid] = g;
+    }
+    // (2) rows with an unseen key: the first to claim a slot represents the key, the others find it by comparing key bytes
+    ECB_DEV static void body_kt_insert(int tid, int n, const u32* q32, int* htab, u32 hmask, const int* gid, int* rep, int* rep_slot) {
+        if (tid >= n || gid[tid] >= 0) return;
+        const u32* key = q32 + (size_t)tid * KBW;
+        u32 slot = key_hash(key) & hmask;
+        for (;;) {
+            const int old = atomic_cas_i32(htab + slot, KT_EMPTY, KT_TAG | tid);
+            if (old == KT_EMPTY) { rep[tid] = tid; rep_slot[tid] = (int)slot; return; }
+            if (old >= KT_TAG) {                       // a row of THIS chunk (numbered groups are < KT_TAG and were ruled out by the lookup)
+                const int r2 = old & ~KT_TAG;
+                if (key_eq(q32 + (size_t)r2 * KBW, key)) { rep[tid] = r2; return; }
+            }
+            slot = (slot + 1) & hmask;
+        }
+    }
+    // (3) representatives take the next group number, publish it in their slot and store the key bytes for later chunks
+    ECB_DEV static void body_kt_number(int tid, int n, const u32* q32, int* htab, const int* gid, const int* rep, const int* rep_slot,
+                                       int* counter, int cap, u32* gkeys, int* newgid) {
+        if (tid >= n || gid[tid] >= 0 || rep[tid] != tid) return;
+        const int g = atomic_add_i32(counter, 1);
+        newgid[tid] = g;
+        if (g < cap) {
+            const u32* key = q32 + (size_t)tid * KBW;
+            ECB_UNROLL
+            for (int i = 0; i < KBW; i++) gkeys[(size_t)g * KBW + i] = key[i];
+            htab[rep_slot[tid]] = g;
+        } else {
+            htab[rep_slot[tid]] = KT_OVERFLOW;         // more distinct keys than tables: the host falls back to the per-row path
+        }
+    }
+    // (4) every other row of a new group copies its representative's number
+    ECB_DEV static void body_kt_assign(int tid, int n, int* gid, const int* rep, const int* newgid) {
+        if (tid >= n || gid[tid] >= 0) return;
+        gid[tid] = newgid[rep[tid]];
+    }
+    // table construction, step 1: B_w = 16^w * Q for the keys of groups [g0, g0 + cnt) as homogeneous projective limbs (normalised
+    // next by the shared kernel); kvalid[g] = the key decodes to a point on the curve (else the generator stands in and every row
+    // of the group is rejected - ecdsa::VerifyingKey cannot hold such a key)
+    ECB_DEV static void body_kt_base(int tid, int g0, int cnt, const u32* gkeys, u32* proj, u8* kvalid) {
+        if (tid >= cnt) return;
+        const int g = g0 + tid;
+        Aff a;
+        const bool ok = G::load_affine(a, reinterpret_cast<const u8*>(gkeys + (size_t)g * KBW));
+        if (!ok) G::generator(a);
+        kvalid[g] = ok ? 1 : 0;
+        typename JJ::J p;
+        typename JJ::A qa;
+        qa.x = a.x; qa.y = a.y;
+        JJ::from_affine(p, qa);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int w = 0; w < KT_WINDOWS; w++) {
+            Proj o;
+            JJ::to_proj(o, p);
+            store_proj(proj + ((size_t)tid * KT_WINDOWS + w) * 3 * L, o);
+            if (w + 1 < KT_WINDOWS) JJ::dbl_n(p, 4);
+        }
+    }
+    // table construction, step 2: entries 2..8 of every (key, window) item by AFFINE additions with one shared inversion per
+    // round - Montgomery's trick over the items a thread owns, continued across the CTA by INV (6 multiplications per entry
+    // instead of 11-16 for Jacobian additions plus a normalisation).  Round v makes v*B = (v-1)*B + B (v = 2: the tangent).
+    // No exceptional case can occur: B has prime order n > 16, so (v-1)*B != +-B and 2y != 0.
+    static constexpr int KT_EPT = 8;
+    template <class INV = OwnInv>
+    ECB_DEV static void body_kt_fill(int tid, int nthreads, int items, u32* tab) {
+        E pref[KT_EPT];
+        for (int v = 2; v <= 8; v++) {
+            E acc;
+            F::set_one(acc);
+            int cnt = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j = 0; j < KT_EPT; j++) {
+                const int i = tid + j * nthreads;
+                if (i >= items) break;
+                const u32* ent = tab + (size_t)i * 8 * 2 * L;
+                E d;
+                if (v == 2) { E y0; load_fe(y0, ent + L); F::dbl(d, y0); }
+                else { E x0, x1; load_fe(x0, ent); load_fe(x1, ent + (size_t)(v - 2) * 2 * L); F::sub(d, x1, x0); }
+                pref[j] = acc;
+                F::mul(acc, acc, d);
+                cnt++;
+            }
+            E inv;
+            if (INV::COOPERATIVE || cnt) INV::template run<F>(inv, acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j = cnt - 1; j >= 0; j--) {
+                const int i = tid + j * nthreads;
+                u32* ent = tab + (size_t)i * 8 * 2 * L;
+                E x0, y0, x1, y1, d, dinv, lam, x3, y3, t;
+                load_fe(x0, ent); load_fe(y0, ent + L);
+                if (v == 2) { x1 = x0; y1 = y0; F::dbl(d, y0); }
+                else { load_fe(x1, ent + (size_t)(v - 2) * 2 * L); load_fe(y1, ent + (size_t)(v - 2) * 2 * L + L); F::sub(d, x1, x0); }
+                F::mul(dinv, inv, pref[j]);
+                F::mul(inv, inv, d);
+                if (v == 2) {                              // lambda = (3 x^2 + a) / (2 y)
+                    F::sqr(t, x0);
+                    if constexpr (!C::A_IS_ZERO) { E one; F::set_one(one); F::sub(t, t, one); }
+                    F::dbl(lam, t); F::add(lam, lam, t);
+                } else {
+                    F::sub(lam, y1, y0);                   // lambda = (y1 - y0) / (x1 - x0)
+                }
+                F::mul(lam, lam, dinv);
+                F::sqr(x3, lam); F::sub(x3, x3, x0); F::sub(x3, x3, x1);
+                F::sub(t, x0, x3); F::mul(y3, lam, t); F::sub(y3, y3, y0);
+                store_entry(ent + (size_t)(v - 1) * 2 * L, x3, y3);
+            }
+        }
+    }
+    // the verify main kernel on per-key tables: no doublings, KT_WINDOWS (x2) gathered mixed additions, then u1*G and the
+    // inversion-free comparison exactly as body_verify_main
+    ECB_DEV static void body_verify_keytab(int tid, int n, int mode, const u8* rs, const u8* zin, const u32* scratch, const int* gid, const u8* kvalid,
+                                           const u32* tab, const u32* gbig, int gw, u8* ok_out) {
+        if (tid >= n) return;
+        const u32* rec = scratch + (size_t)tid * PREP_WORDS;
+        const int g = gid[tid];
+        bool valid = kvalid[g] != 0;
+        const u32* tk = tab + (size_t)g * KT_KEY_WORDS;
+        u32 r[L], u1[L];
+        load_be<L>(r, rs + (size_t)tid * 2 * FB);
+        ECB_UNROLL
+        for (int l = 0; l < L; l++) u1[l] = rec[l];
+        typename JJ::J acc;
+        JJ::set_inf(acc);
+        if constexpr (C::A_IS_ZERO) {
+            K256Glv::Split sp;
+            ECB_UNROLL
+            for (int l = 0; l < 5; l++) { sp.a1[l] = rec[8 + l]; sp.a2[l] = rec[13 + l]; }
+            const u32 fl = rec[18];
+            valid = valid && (fl & 1u);
+            sp.neg1 = (u32)0 - ((fl >> 1) & 1u);
+            sp.neg2 = (u32)0 - ((fl >> 2) & 1u);
+            E beta;
+            ECB_UNROLL
+            for (int l = 0; l < 8; l++) beta.v[l] = CurveK256::beta(l);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int w = 0; w < KT_WINDOWS; w++) {
+                u32 mag, neg;
+                K256Glv::digit(sp.a1, w, mag, neg);
+                if (mag) {
+                    typename JJ::A e;
+                    JJ::load_entry(e, tk + ((size_t)w * 8 + mag - 1) * 2 * L);
+                    JJ::cneg_y(e, neg ^ sp.neg1);
+                    JJ::madd(acc, acc, e, nullptr);
+                }
+                K256Glv::digit(sp.a2, w, mag, neg);
+                if (mag) {
+                    typename JJ::A e;
+                    JJ::load_entry(e, tk + ((size_t)w * 8 + mag - 1) * 2 * L);
+                    F::mul(e.x, e.x, beta);                 // lambda * (x, y) = (beta x, y)
+                    JJ::cneg_y(e, neg ^ sp.neg2);
+                    JJ::madd(acc, acc, e, nullptr);
+                }
+            }
+        } else {
+            u32 u2[L], kb[L + 1];
+            ECB_UNROLL
+            for (int l = 0; l < L; l++) u2[l] = rec[L + l];
+            valid = valid && (rec[2 * L] & 1u);
+            kb[0] = add_cc(u2[0], 0x88888888u);
+            ECB_UNROLL
+            for (int i = 1; i < L; i++) kb[i] = addc_cc(u2[i], 0x88888888u);
+            kb[L] = addc(0u, 0u);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int w = 0; w < KT_WINDOWS; w++) {
+                u32 mag, neg;
+                JJ::digit16(kb, w, 8 * L, mag, neg);
+                if (mag) {
+                    typename JJ::A e;
+                    JJ::load_entry(e, tk + ((size_t)w * 8 + mag - 1) * 2 * L);
+                    JJ::cneg_y(e, neg);
+                    JJ::madd(acc, acc, e, nullptr);
+                }
+            }
+        }
+        JJ::add_fixed_base(acc, u1, gbig, gw);
+        if (mode == VM_ECDSA) {
+            ok_out[tid] = finish_verify_jac(acc, r, valid) ? 1 : 0;
+        } else {                                           // VM_SM2DSA: target = (r - e) mod n, the identity counts as x = 0
+            u32 e[L];
+            G::load_scalar(e, zin + (size_t)tid * FB);
+            typename Fn::E a, b, t;
+            copy_n<L>(a.v, r); copy_n<L>(b.v, e);
+            if (!valid) Fn::set_zero(a);
+            Fn::sub(t, a, b);
+            ok_out[tid] = finish_verify_jac(acc, t.v, valid, true) ? 1 : 0;
+        }
+    }
 
     // ------------------------------------------------------------------ variable-base k*P, vartime fast path (v2)
     // pts: n x 2FB big-endian affine bytes (aff_limbs == nullptr), or internal affine limbs produced by the

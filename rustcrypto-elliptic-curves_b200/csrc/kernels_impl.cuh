@@ -185,6 +185,30 @@ template <class C, int MODE> __global__ void __launch_bounds__(BLK, fast_min_cta
     Bodies<C>::template body_verify_main<win_smem_entries<C>()>(blockIdx.x * BLK + threadIdx.x, n, MODE, q, rs, z, aux, scratch, gbig, gw, ok, proj_out,
                                                                  ecb_dyn_smem + threadIdx.x, BLK, wtab);
 }
+// ---- per-key window tables: grouping (four small kernels), construction (base points, batched-affine fill), verification
+template <class C> __global__ void __launch_bounds__(256) k_kt_lookup(int n, const u32* q32, const int* htab, u32 hmask, const u32* gkeys, int* gid) {
+    Bodies<C>::body_kt_lookup(blockIdx.x * 256 + threadIdx.x, n, q32, htab, hmask, gkeys, gid);
+}
+template <class C> __global__ void __launch_bounds__(256) k_kt_insert(int n, const u32* q32, int* htab, u32 hmask, const int* gid, int* rep, int* rep_slot) {
+    Bodies<C>::body_kt_insert(blockIdx.x * 256 + threadIdx.x, n, q32, htab, hmask, gid, rep, rep_slot);
+}
+template <class C> __global__ void __launch_bounds__(256) k_kt_number(int n, const u32* q32, int* htab, const int* gid, const int* rep, const int* rep_slot, int* counter, int cap,
+                                                                       u32* gkeys, int* newgid) {
+    Bodies<C>::body_kt_number(blockIdx.x * 256 + threadIdx.x, n, q32, htab, gid, rep, rep_slot, counter, cap, gkeys, newgid);
+}
+template <class C> __global__ void __launch_bounds__(256) k_kt_assign(int n, int* gid, const int* rep, const int* newgid) {
+    Bodies<C>::body_kt_assign(blockIdx.x * 256 + threadIdx.x, n, gid, rep, newgid);
+}
+template <class C> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_kt_base(int g0, int cnt, const u32* gkeys, u32* proj, u8* kvalid) {
+    Bodies<C>::body_kt_base(blockIdx.x * BLK + threadIdx.x, g0, cnt, gkeys, proj, kvalid);
+}
+template <class C> __global__ void __launch_bounds__(BLK, wt_min_ctas<C>()) k_kt_fill(int items, u32* tab) {
+    Bodies<typename CtCurve<C>::type>::template body_kt_fill<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, items, tab);
+}
+template <class C, int MODE> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_verify_keytab(int n, const u8* rs, const u8* z, const u32* scratch, const int* gid, const u8* kvalid,
+                                                                                                          const u32* tab, const u32* gbig, int gw, u8* ok) {
+    Bodies<C>::body_verify_keytab(blockIdx.x * BLK + threadIdx.x, n, MODE, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
+}
 template <class C> __global__ void __launch_bounds__(BLK) k_decode(int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
     Bodies<typename CtCurve<C>::type>::body_decode(blockIdx.x * BLK + threadIdx.x, n, mode, enc, stride, xy, status);
 }
@@ -414,6 +438,48 @@ template <class C> struct Launch {
         }
         count_launch();
     }
+    static void kt_group(cudaStream_t s, int n, const u32* q32, int* htab, u32 hmask, u32* gkeys, int* gid, int* rep, int* rep_slot, int* newgid, int* counter, int cap) {
+        if (n <= 0) return;
+        const int g = (n + 255) / 256;
+        k_kt_lookup<C><<<g, 256, 0, s>>>(n, q32, htab, hmask, gkeys, gid);
+        k_kt_insert<C><<<g, 256, 0, s>>>(n, q32, htab, hmask, gid, rep, rep_slot);
+        k_kt_number<C><<<g, 256, 0, s>>>(n, q32, htab, gid, rep, rep_slot, counter, cap, gkeys, newgid);
+        k_kt_assign<C><<<g, 256, 0, s>>>(n, gid, rep, newgid);
+        count_launch(4);
+    }
+    // tables of groups [g0, g0 + cnt): 16^w * Q (Jacobian chain), one normalisation of all base points straight into entry 0 of
+    // every window, then seven rounds of batched affine additions
+    static void kt_build(cudaStream_t s, int g0, int cnt, const u32* gkeys, u32* proj_scratch, u8* kvalid, u32* tab) {
+        if (cnt <= 0) return;
+        typedef Bodies<C> B;
+        k_kt_base<C><<<grid(cnt), BLK, 0, s>>>(g0, cnt, gkeys, proj_scratch, kvalid);
+        count_launch();
+        const long items = (long)cnt * B::KT_WINDOWS;
+        u32* t0 = tab + (size_t)g0 * B::KT_KEY_WORDS;
+        {
+            int ept = (int)((items + 148L * BLK - 1) / (148L * BLK));
+            if (ept < 1) ept = 1;
+            if (ept > B::EPT) ept = B::EPT;
+            const int threads = (int)((items + ept - 1) / ept);
+            k_normalize<C><<<grid(threads), BLK, 0, s>>>((int)items, proj_scratch, NORM_AFF_STRIDED, 8 * 2 * C::L, nullptr, nullptr, t0);
+            count_launch();
+        }
+        {
+            const int threads = (int)((items + B::KT_EPT - 1) / B::KT_EPT);
+            k_kt_fill<C><<<grid(threads), BLK, 0, s>>>((int)items, t0);
+            count_launch();
+        }
+    }
+    static void verify_keytab(cudaStream_t s, int n, int mode, const u8* rs, const u8* z, const u32* scratch, const int* gid, const u8* kvalid,
+                              const u32* tab, const u32* gbig, int gw, u8* ok) {
+        if (n <= 0) return;
+        if (mode == VM_SM2DSA) {
+            if constexpr (C::ID == 3) k_verify_keytab<C, VM_SM2DSA><<<grid(n), BLK, 0, s>>>(n, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
+        } else {
+            k_verify_keytab<C, VM_ECDSA><<<grid(n), BLK, 0, s>>>(n, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
+        }
+        count_launch();
+    }
     static void decode(cudaStream_t s, int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
         if (n <= 0) return;
         k_decode<C><<<grid(n), BLK, 0, s>>>(n, mode, enc, stride, xy, status);
@@ -433,7 +499,8 @@ template <class C> struct Launch {
         CurveLaunch t = {
             C::ID, C::L, C::FB, C::A_IS_ZERO ? 8 : 15, Bodies<C>::GEN_WINDOWS, 8, C::COMPRESS_DEFAULT, {0},
             &field_op, &mul_var, &mul_gen, &load_proj, &normalize, &sum, &proj_to_bytes, &verify,
-            &mul_var_fast, &verify_prep, &verify_main, &decode, &finish, &sign_finish, &wintab, &add_proj, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
+            &mul_var_fast, &verify_prep, &verify_main, &decode, &finish, &sign_finish, &wintab, &add_proj,
+            Bodies<C>::KT_WINDOWS, Bodies<C>::KT_KEY_WORDS, Bodies<C>::KBW, &kt_group, &kt_build, &verify_keytab, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
         for (int i = 0; i < C::L; i++) {   // R mod n (the Montgomery "one" of the scalar field) as big-endian bytes
             const u32 w = C::Fn::Params::one(i);
             t.r_mod_n[C::FB - 4 * i - 1] = (u8)w; t.r_mod_n[C::FB - 4 * i - 2] = (u8)(w >> 8);

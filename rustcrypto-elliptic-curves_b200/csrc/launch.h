@@ -44,6 +44,14 @@ struct CurveLaunch {
     void (*wintab)(cudaStream_t s, int n, const uint8_t* pts, const uint32_t* aff_limbs, uint32_t* wtab);
     // out[i] = a[i] + b[i] on projective limbs (complete addition), invalid[i] |= invalid_b[i]: tail of the per-row 2-term lincomb
     void (*add_proj)(cudaStream_t s, int n, const uint32_t* a, const uint32_t* b, uint32_t* out, uint8_t* invalid, const uint8_t* invalid_b);
+    // per-key window tables of the verify path (kernels.cuh "per-key window tables"): group the rows of a chunk by public key,
+    // build the tables of groups [g0, g0 + cnt), verify on the tables
+    int kt_windows, kt_key_words, kt_kbw;
+    void (*kt_group)(cudaStream_t s, int n, const uint32_t* q32, int* htab, uint32_t hmask, uint32_t* gkeys, int* gid, int* rep, int* rep_slot,
+                     int* newgid, int* counter, int cap);
+    void (*kt_build)(cudaStream_t s, int g0, int cnt, const uint32_t* gkeys, uint32_t* proj_scratch, uint8_t* kvalid, uint32_t* tab);
+    void (*verify_keytab)(cudaStream_t s, int n, int mode, const uint8_t* rs, const uint8_t* z, const uint32_t* scratch, const int* gid,
+                          const uint8_t* kvalid, const uint32_t* tab, const uint32_t* gbig, int gw, uint8_t* ok);
     int prep_words;   // u32 words of scratch per row between verify_prep and verify_main
     int sum_blocks;
 };

@@ -49,14 +49,14 @@ class EngineBackend:
         return np.frombuffer(out, np.uint8).reshape(a.shape)
 
 
-def make_verify_batch(backend, curve, n: int, seed: int, corrupt_every: int = 16):
+def make_verify_batch(backend, curve, n: int, seed: int, corrupt_every: int = 16, n_keys: int = N_KEYS):
     """Returns (q[n,2fb], z[n,fb], rs[n,2fb], expected[n]) as uint8 arrays.
-    Row i uses key i mod N_KEYS.  Rows with i % corrupt_every == 5 are corrupted (kind = (i // corrupt_every) % 5):
+    Row i uses key i mod n_keys (default 2^16 distinct keys, SURVEY 8d config 3; n_keys >= n makes every key distinct).  Rows with i % corrupt_every == 5 are corrupted (kind = (i // corrupt_every) % 5):
     0 flip a bit of r, 1 flip a bit of s, 2 flip a bit of z, 3 s -> n - s (high-s twin: rejected by k256 only),
     4 r -> r + n when that fits (out of range), else r = 0."""
     cid, fb = curve_id(curve), field_bytes(curve)
     order = ORDERS[cid]
-    nk = min(N_KEYS, n)
+    nk = min(n_keys, n)
     d = random_scalars(nk, fb, seed)
     qk = backend.mul_gen_xy(d)
     idx = np.arange(n) % nk

@@ -1,6 +1,7 @@
 """One invocation of one batch operation on device-resident synthetic inputs, bracketed by cudaProfilerStart/Stop (for
 `ncu --profile-from-start off`: every kernel of the operation, nothing of the set-up).
-usage: prof_one.py <curve> <verify|mul_var|mul_var_ct|mul_var_proj|mul_var_proj_ct|mul_gen|sign> <log2 n> [reps]"""
+usage: prof_one.py <curve> <verify|verify_keys|mul_var|mul_var_ct|mul_var_proj|mul_var_proj_ct|mul_gen|sign> <log2 n> [reps]
+verify = every row its own key (per-row path); verify_keys = 2^16 distinct keys reused round-robin (BASELINE configs 2 / 3: per-key tables)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -30,6 +31,9 @@ ks = rnd(fb)
 pts_slots = torch.empty(n * slot, dtype=torch.uint8, device=dev)
 eng.mul_gen_dev(curve, n, ks, pts_slots, ecb200.FLAG_UNCOMPRESSED, st)
 pts = pts_slots.view(n, slot)[:, 1:].contiguous()
+if op == "verify_keys":
+    pts = pts[torch.arange(n, device=dev) % min(n, 1 << 16)].contiguous()
+    op = "verify"
 k2 = rnd(fb)
 out = torch.empty(n * slot, dtype=torch.uint8, device=dev)
 z = rnd(fb)

@@ -132,6 +132,50 @@ template <class C> struct Emu {
         for (int t = 0; t < nthreads; t++) B::body_wintab(t, nthreads, n, pts, aff, wt.data(), wt.data() + (size_t)n * 16 * L);
         return wt;
     }
+    // the per-key-table verify path as abi.cu drives it: rows arrive in chunks, keys are grouped incrementally (lookup, insert,
+    // number, assign), tables are built for the keys first seen in a chunk, rows are verified on the tables.  Returns the number
+    // of distinct keys found.  cap = table capacity in groups (rows of overflowing groups would take the per-row path: -1 here)
+    static int verify_keytab(int mode, int n, const u8* q, const u8* z, const u8* rs, u8* ok, int chunk, int cap, int nthreads) {
+        const int gw = 4;
+        const std::vector<u32>& gt = gbig4();
+        const int KBW = B::KBW, W = B::KT_WINDOWS;
+        size_t hs = 16;
+        while (hs < (size_t)2 * (cap + chunk)) hs <<= 1;
+        std::vector<int> htab(hs, B::KT_EMPTY), counter(4, 0);
+        std::vector<u32> gkeys((size_t)cap * KBW), tab((size_t)cap * B::KT_KEY_WORDS);
+        std::vector<u8> kvalid(cap);
+        int built = 0;
+        for (int off = 0; off < n; off += chunk) {
+            const int cnt = n - off < chunk ? n - off : chunk;
+            std::vector<u32> q32((size_t)cnt * KBW);
+            memcpy(q32.data(), q + (size_t)off * 2 * FB, (size_t)cnt * 2 * FB);
+            std::vector<int> gid(cnt, -7), rep(cnt, -7), rep_slot(cnt, -7), newgid(cnt, -7);
+            for (int t = 0; t < cnt; t++) B::body_kt_lookup(t, cnt, q32.data(), htab.data(), (u32)(hs - 1), gkeys.data(), gid.data());
+            for (int t = cnt - 1; t >= 0; t--) B::body_kt_insert(t, cnt, q32.data(), htab.data(), (u32)(hs - 1), gid.data(), rep.data(), rep_slot.data());   // any order
+            for (int t = 0; t < cnt; t++) B::body_kt_number(t, cnt, q32.data(), htab.data(), gid.data(), rep.data(), rep_slot.data(), counter.data(), cap, gkeys.data(), newgid.data());
+            for (int t = 0; t < cnt; t++) B::body_kt_assign(t, cnt, gid.data(), rep.data(), newgid.data());
+            const int D = counter[0];
+            if (D > cap) return -D;
+            if (D > built) {
+                const int c2 = D - built;
+                std::vector<u32> proj((size_t)c2 * W * 3 * L);
+                for (int t = 0; t < c2; t++) B::body_kt_base(t, built, c2, gkeys.data(), proj.data(), kvalid.data());
+                u32* t0 = tab.data() + (size_t)built * B::KT_KEY_WORDS;
+                normalize(c2 * W, proj.data(), NORM_AFF_STRIDED, 8 * 2 * L, nullptr, nullptr, t0, 0);
+                const int items = c2 * W;
+                int th = (items + B::KT_EPT - 1) / B::KT_EPT;
+                if (nthreads > th) th = nthreads;
+                for (int t = 0; t < th; t++) B::template body_kt_fill<OwnInv>(t, th, items, t0);
+                built = D;
+            }
+            std::vector<u32> scratch((size_t)cnt * B::PREP_WORDS);
+            int need = (cnt + B::PREP_EPT - 1) / B::PREP_EPT;
+            for (int t = 0; t < need; t++) B::body_verify_prep(t, need, cnt, mode, z + (size_t)off * FB, rs + (size_t)off * 2 * FB, scratch.data());
+            for (int t = 0; t < cnt; t++)
+                B::body_verify_keytab(t, cnt, mode, rs + (size_t)off * 2 * FB, z + (size_t)off * FB, scratch.data(), gid.data(), kvalid.data(), tab.data(), gt.data(), gw, ok + off);
+        }
+        return counter[0];
+    }
     static void verify2(int n, const u8* q, const u8* z, const u8* rs, u8* ok, int nthreads) {
         verify_mode(VM_ECDSA, n, q, z, rs, nullptr, ok, nullptr, 0, nthreads);
     }
@@ -219,6 +263,19 @@ int emu_batch_normalize(int curve, int n, const u8* xyz, u8* xy, u8* inf, int nt
 int emu_verify2(int curve, int n, const u8* q, const u8* z, const u8* rs, u8* ok, int nthreads) {
     DISPATCH(curve, verify2(n, q, z, rs, ok, nthreads));
     return 0;
+}
+int emu_verify_keytab(int curve, int mode, int n, const u8* q, const u8* z, const u8* rs, u8* ok, int chunk, int cap, int nthreads) {
+    int r = 0;
+    switch (curve) {
+        case 0: r = Emu<CurveK256>::verify_keytab(mode, n, q, z, rs, ok, chunk, cap, nthreads); break;
+        case 1: r = Emu<CurveP256>::verify_keytab(mode, n, q, z, rs, ok, chunk, cap, nthreads); break;
+        case 2: r = Emu<CurveP384>::verify_keytab(mode, n, q, z, rs, ok, chunk, cap, nthreads); break;
+        case 3: r = Emu<CurveSM2>::verify_keytab(mode, n, q, z, rs, ok, chunk, cap, nthreads); break;
+        case 4: r = Emu<CurveP192>::verify_keytab(mode, n, q, z, rs, ok, chunk, cap, nthreads); break;
+        case 5: r = Emu<CurveP224>::verify_keytab(mode, n, q, z, rs, ok, chunk, cap, nthreads); break;
+        default: return -1;
+    }
+    return r;
 }
 int emu_mul_var_fast(int curve, int n, const u8* pts, const u8* inf, const u8* k, u8* out, int compress, u8* invalid) {
     DISPATCH(curve, mul_var_fast(n, pts, inf, k, out, compress, invalid));

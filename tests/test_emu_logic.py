@@ -188,6 +188,14 @@ def run_verify(c, rows):
     ok2 = emu_lib.buf(len(rows))
     assert lib.emu_verify2(c.cid, len(rows), q, z, rs, ok2, 3) == 0
     assert list(ok) == list(ok2)
+    # third path: rows grouped by public key, per-key window tables, no doublings - fed in one chunk, in three chunks (groups
+    # carried over) and one row at a time; the distinct-key count must match
+    n = len(rows)
+    distinct = len({r[0] for r in rows})
+    for chunk in sorted({n, max(1, (n + 2) // 3), 1 if n <= 40 else 7}):
+        ok3 = emu_lib.buf(n)
+        assert lib.emu_verify_keytab(c.cid, 0, n, q, z, rs, ok3, chunk, n, 2) == distinct
+        assert list(ok3) == list(ok2), chunk
     return list(ok2), o.batch_verify(c, q, z, rs)
 
 
@@ -241,6 +249,38 @@ def test_verify_synthetic(cname):
     got, exp = run_verify(c, rows)
     assert got == list(exp)
     assert 0 < sum(got) < len(got)
+
+
+@pytest.mark.parametrize("cname", ["k256", "p256", "sm2", "p224"])
+def test_verify_keytab_reused_keys_and_overflow(cname):
+    """Few keys, many rows (the shape the per-key tables exist for), incl. an off-curve key shared by several rows, corrupted
+    signatures, rows whose digits are all zero in one GLV half, and a table capacity smaller than the number of keys."""
+    c = o.curve(cname)
+    fb = c.fb
+    rng = random.Random(5150 + c.cid)
+    keys = [rng.randrange(1, c.n) for _ in range(5)]
+    rows = []
+    for i in range(60):
+        d = keys[i % 5]
+        Q = o.mul_gen(c, d)
+        z = rng.randrange(1 << (8 * fb)).to_bytes(fb, "big")
+        k = rng.randrange(1, c.n)
+        r = o.mul_gen(c, k)[0] % c.n
+        s = pow(k, -1, c.n) * (o.reduce_once(c, int.from_bytes(z, "big")) + r * d) % c.n
+        if c.low_s and s > c.n >> 1:
+            s = c.n - s
+        if i % 7 == 3:
+            s ^= 4
+        if i % 11 == 5:
+            Q = (Q[0], Q[1] ^ 1)                       # the same broken key bytes recur: one invalid group
+        rows.append((Q, z, r, s))
+    got, exp = run_verify(c, rows)
+    assert got == list(exp) and 20 < sum(got) < 60
+    q = b"".join(r[0][0].to_bytes(fb, "big") + r[0][1].to_bytes(fb, "big") for r in rows)
+    z = b"".join(r[1] for r in rows)
+    rs = b"".join(r[2].to_bytes(fb, "big") + r[3].to_bytes(fb, "big") for r in rows)
+    ok = emu_lib.buf(60)
+    assert lib.emu_verify_keytab(c.cid, 0, 60, q, z, rs, ok, 60, 3, 2) < -3      # more distinct keys than capacity: reported, not mis-verified
 
 
 @pytest.mark.parametrize("cname", CUR)
@@ -339,6 +379,9 @@ def test_sm2dsa(golden):
     assert lib.emu_verify_mode(3, VM_SM2DSA, n, qb, eb, rsb, None, ok, None, 0, 2) == 0
     assert bytes(ok) == exp
     assert 0 < sum(exp) < n
+    ok3 = emu_lib.buf(n)                               # the same rows through the per-key-table path
+    assert lib.emu_verify_keytab(3, VM_SM2DSA, n, qb, eb, rsb, ok3, 4, n, 2) > 0
+    assert bytes(ok3) == exp
 
 
 @pytest.mark.parametrize("cname", ["k256", "p256"])

@@ -283,3 +283,149 @@ def test_plain_c_multi_device_client(tmp_path):
     out = subprocess.run([exe, str(shards)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     assert "cabi multi client ok: %d shards" % shards in out.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# per-key window tables of the verify path (rows grouped by public key inside a call; kernels.cuh "per-key window tables")
+
+@pytest.fixture(scope="module")
+def eng_rowpath():
+    """an engine with the per-key tables switched off: the per-row path, for A/B comparisons"""
+    import os
+    import ecb200
+    os.environ["ECB200_KEYTAB"] = "0"
+    try:
+        e = ecb200.Engine(0)
+    finally:
+        del os.environ["ECB200_KEYTAB"]
+    yield e
+    e.close()
+
+
+def _wl():
+    return __import__("importlib").import_module("rustcrypto-elliptic-curves_b200.workloads")
+
+
+@pytest.mark.parametrize("cname", CUR)
+def test_keytab_path_matches_per_row_path_and_construction(eng, eng_rowpath, cname):
+    """Few keys, many rows: the table path must give exactly the mask of the per-row path and of the construction; one key is
+    made invalid (off curve) for all of its rows, one group's rows all carry out-of-range signatures."""
+    wl = _wl()
+    c = o.curve(cname)
+    fb = c.fb
+    n, nk = (24000, 600) if fb <= 32 else (9000, 300)
+    q, z, rs, exp = wl.make_verify_batch(wl.EngineBackend(eng, cname), cname, n, 0xB2100000 + c.cid, n_keys=nk)
+    q, rs, exp = q.copy(), rs.copy(), exp.copy()
+    bad_key = np.arange(n) % nk == 7
+    q[bad_key, 2 * fb - 1] ^= 1                                   # the same broken bytes on every row of key 7
+    exp[bad_key] = 0
+    zero_r = np.arange(n) % nk == 11
+    rs[zero_r, :fb] = 0                                            # r = 0 on every row of key 11
+    exp[zero_r] = 0
+    r0, t0 = eng.keytab_stats()
+    got = np.frombuffer(eng.ecdsa_verify(cname, q, z, rs), np.uint8)
+    r1, t1 = eng.keytab_stats()
+    assert r1 - r0 == n and t1 - t0 == nk, "the per-key table path did not run"
+    ref = np.frombuffer(eng_rowpath.ecdsa_verify(cname, q, z, rs), np.uint8)
+    assert eng_rowpath.keytab_stats() == (0, 0)
+    assert np.array_equal(got, ref) and np.array_equal(got, exp)
+    assert 0 < int(got.sum()) < n
+    # oracle on a sample (incl. rows of the broken groups)
+    for i in list(range(0, n, n // 61)) + [7, 11, 7 + nk, 11 + nk, 5, 21, 37, 53, 69]:
+        Q = (int.from_bytes(q[i, :fb].tobytes(), "big"), int.from_bytes(q[i, fb:].tobytes(), "big"))
+        r, s = int.from_bytes(rs[i, :fb].tobytes(), "big"), int.from_bytes(rs[i, fb:].tobytes(), "big")
+        assert bool(got[i]) == o.verify_prehashed(c, Q, z[i].tobytes(), r, s), i
+    # permuting the rows permutes the mask (group numbering is arbitrary, results are not)
+    perm = np.random.default_rng(3).permutation(n)
+    gotp = np.frombuffer(eng.ecdsa_verify(cname, q[perm].copy(), z[perm].copy(), rs[perm].copy()), np.uint8)
+    assert np.array_equal(gotp, got[perm])
+
+
+def test_keytab_policy_and_chunked_host_calls(eng, eng_rowpath):
+    """(a) all keys distinct: the per-row path runs (no tables); (b) a host call that spans several pipeline chunks carries the
+    key groups from chunk to chunk (tables are built once per key per call); (c) below 8 rows per key the per-row path runs;
+    (d) the device-pointer entry point takes the same path; (e) SEC1-encoded keys and SM2DSA go through it too."""
+    import ecb200
+    import torch
+    wl = _wl()
+    c = o.K256
+    be_ = wl.EngineBackend(eng, "k256")
+    n = 40000
+    q, z, rs, exp = wl.make_verify_batch(be_, "k256", n, 0xB2100100, n_keys=n)          # (a)
+    r0, t0 = eng.keytab_stats()
+    assert eng.ecdsa_verify("k256", q, z, rs) == exp.tobytes()
+    assert eng.keytab_stats() == (r0, t0)
+    q, z, rs, exp = wl.make_verify_batch(be_, "k256", n, 0xB2100101, n_keys=n // 4)     # (c) 4 rows per key
+    assert eng.ecdsa_verify("k256", q, z, rs) == exp.tobytes()
+    assert eng.keytab_stats() == (r0, t0)
+    n = 1500000                                                                            # (b) 227 328 + 1 136 640 + rest: three chunks
+    nk = 3000
+    q, z, rs, exp = wl.make_verify_batch(be_, "k256", n, 0xB2100102, n_keys=nk)
+    got = eng.ecdsa_verify("k256", q, z, rs)
+    r1, t1 = eng.keytab_stats()
+    assert got == exp.tobytes()
+    assert r1 - r0 == n and t1 - t0 == nk, (r1 - r0, t1 - t0)
+    assert eng_rowpath.ecdsa_verify("k256", q, z, rs) == got
+    dev = torch.device("cuda:0")                                                           # (d)
+    m = 1 << 18
+    dq, dz, drs = (torch.from_numpy(a[:m].copy()).to(dev) for a in (q, z, rs))
+    dok = torch.empty(m, dtype=torch.uint8, device=dev)
+    eng.ecdsa_verify_dev("k256", m, dq, dz, drs, dok)
+    torch.cuda.synchronize()
+    assert dok.cpu().numpy().tobytes() == exp[:m].tobytes()
+    r2, t2 = eng.keytab_stats()
+    assert r2 - r1 == m and t2 - t1 == nk
+    # (e) compressed SEC1 keys: decoded on the device, then grouped
+    d = wl.random_scalars(nk, 32, 0xB2100102)
+    comp = np.frombuffer(eng.mul_by_generator_batch("k256", d), np.uint8).reshape(nk, 33)
+    keys = np.ascontiguousarray(comp[np.arange(m) % nk])
+    assert eng.ecdsa_verify_sec1("k256", keys, 33, z[:m].copy(), rs[:m].copy()) == exp[:m].tobytes()
+    assert eng.keytab_stats()[0] - r2 == m
+    # SM2DSA on tables vs per-row
+    ns, nks = 20000, 100
+    rng = np.random.default_rng(9)
+    dk = wl.random_scalars(nks, 32, 77)
+    pub = np.frombuffer(eng.mul_by_generator_batch("sm2", dk, ecb200.FLAG_UNCOMPRESSED), np.uint8).reshape(nks, 65)[:, 1:]
+    qs = np.ascontiguousarray(pub[np.arange(ns) % nks])
+    e = rng.integers(0, 256, size=(ns, 32), dtype=np.uint8)
+    sg = rng.integers(0, 256, size=(ns, 64), dtype=np.uint8)
+    sg[:, 0] &= 0x7F
+    sg[:, 32] &= 0x7F
+    assert eng.sm2dsa_verify(qs, e, sg) == eng_rowpath.sm2dsa_verify(qs, e, sg)
+
+
+def test_keytab_wycheproof_and_crafted_rows_tiled(eng, golden):
+    """The reference's own verification vectors (all Wycheproof rows) and the crafted exceptional-case rows (P + P, P + (-P),
+    identity accumulators, x(R) >= n), tiled so that every key repeats and the table path runs: same verdicts as the oracle."""
+    import hashlib
+    from tests import crafted
+    for cname in ("k256", "p256", "p384"):
+        c = o.curve(cname)
+        fb = c.fb
+        blob = golden["wycheproof"][cname]
+        hf = getattr(hashlib, blob["hash"])
+        rows = []
+        for wx, wy, msg, sig, flag in blob["rows"]:
+            rsv = o.der_parse_strict(bytes.fromhex(sig), c)
+            if rsv is None:
+                continue
+            Q = (int.from_bytes(bytes.fromhex(wx)[-fb:], "big"), int.from_bytes(bytes.fromhex(wy)[-fb:], "big"))
+            zb = ecb_bits2field(cname, hf(bytes.fromhex(msg)).digest())
+            if rsv[0] >= 1 << (8 * fb) or rsv[1] >= 1 << (8 * fb):
+                continue
+            rows.append((Q, zb, rsv[0], rsv[1]))
+        rows += [(Q, zb, r, s) for Q, zb, r, s in crafted.exceptional_rows(c) + crafted.reduced_x_rows(c)]
+        reps = 24
+        q = b"".join(be(r[0], fb) for r in rows) * reps
+        z = b"".join(r[1] for r in rows) * reps
+        rs = b"".join(be((r[2], r[3]), fb) for r in rows) * reps
+        exp = o.batch_verify(c, q[:len(rows) * 2 * fb], z[:len(rows) * fb], rs[:len(rows) * 2 * fb]) * reps
+        r0, _ = eng.keytab_stats()
+        got = eng.ecdsa_verify(cname, q, z, rs)
+        assert eng.keytab_stats()[0] - r0 == len(rows) * reps, "the per-key table path did not run"
+        assert got == exp and 0 < sum(got) < len(got)
+
+
+def ecb_bits2field(cname, digest):
+    import ecb200
+    return ecb200.bits2field(cname, digest)
