@@ -862,14 +862,25 @@ template <class C> struct Bodies {
     // per row.  When the same public key signs many rows of a call - validators, servers, the 2^16 keys of BASELINE's configs
     // 2 / 3 - the doublings depend on the KEY only.  The verify pipeline therefore groups the rows of a call by key (a hash table
     // in HBM, byte-exact comparison), builds for every distinct key ONCE the full-position table
-    //     T[g][w][v-1] = v * 16^w * Q_g,   v = 1..8,  w = 0..KT_WINDOWS-1      (affine, field-internal limbs, 2L words per entry)
+    //     T[g][w][v-1] = v * 2^(W w) * Q_g,   v = 1..2^(W-1),  w = 0..KT_WINDOWS-1      (affine, field-internal limbs, 2L words per entry)
     // and verifies each row with KT_WINDOWS (x2 with the GLV split) mixed additions gathered from HBM and NO doublings:
     // secp256k1 ~920 instead of ~1890 field multiplications per row, P-256 ~890 instead of ~2900.  Tables cost ~5 k
     // multiplications per key (2.6 verifications), so the path is taken only when the call reuses keys (abi.cu: at least 8 rows
     // per key); otherwise the per-row path above runs.  Nothing is kept between calls: every call groups and builds afresh.
     // The reference verifies row by row (k256/src/ecdsa.rs:200-209 -> lincomb, mul.rs:342-393) and recomputes u2*Q every time.
-    static constexpr int KT_WINDOWS = C::A_IS_ZERO ? 33 : 8 * L + 1;      // signed radix-16 digits of a GLV half / of a full scalar, + carry
-    static constexpr int KT_KEY_WORDS = KT_WINDOWS * 8 * 2 * L;           // u32 words of one key's table
+    // window width W (ECB_KT_W, bits): signed digits d_w in [-2^(W-1), 2^(W-1)) below the top window, which is unsigned and
+    // absorbs the carry of the recoding; KT_E = 2^(W-1) entries per window.  Wider windows trade table construction (KT_E - 1
+    // affine operations per window, once per key) for fewer additions per row: measured on the B200 at 2^22 rows / 2^16 keys, see DESIGN.md.
+#ifndef ECB_KT_W
+#define ECB_KT_W 4
+#endif
+    static constexpr int KT_W = ECB_KT_W;
+    static constexpr int KT_E = 1 << (KT_W - 1);                          // entries per window: multiples 1 .. 2^(W-1)
+    static constexpr int KT_BITS = C::A_IS_ZERO ? 128 : 32 * L;           // bits of the recoded value: a GLV half / a full scalar
+    static constexpr int KT_WINDOWS = KT_BITS / KT_W + 1;                 // signed windows below bit W*floor(bits/W), then the top window
+    static constexpr int KT_KEY_WORDS = KT_WINDOWS * KT_E * 2 * L;        // u32 words of one key's table
+    // v <= 2^BITS - 1 and bias <= 2^T - 1 (T = W * (KT_WINDOWS - 1)) give a top window of at most 2^(BITS - T)
+    static_assert((1 << (KT_BITS - KT_W * (KT_WINDOWS - 1))) + (C::A_IS_ZERO ? 1 : 0) <= KT_E, "top window must fit the table");
     static constexpr int KBW = 2 * FB / 4;                                // u32 words of one key as it arrives (x||y bytes)
     static constexpr int KT_EMPTY = -1, KT_OVERFLOW = -2, KT_TAG = 0x40000000;
 
@@ -954,18 +965,36 @@ template <class C> struct Bodies {
             Proj o;
             JJ::to_proj(o, p);
             store_proj(proj + ((size_t)tid * KT_WINDOWS + w) * 3 * L, o);
-            if (w + 1 < KT_WINDOWS) JJ::dbl_n(p, 4);
+            if (w + 1 < KT_WINDOWS) JJ::dbl_n(p, KT_W);
         }
     }
-    // table construction, step 2: entries 2..8 of every (key, window) item by AFFINE additions with one shared inversion per
-    // round - Montgomery's trick over the items a thread owns, continued across the CTA by INV (6 multiplications per entry
-    // instead of 11-16 for Jacobian additions plus a normalisation).  Round v makes v*B = (v-1)*B + B (v = 2: the tangent).
-    // No exceptional case can occur: B has prime order n > 16, so (v-1)*B != +-B and 2y != 0.
-    static constexpr int KT_EPT = 8;
+    // table construction, step 2: entries 2..8 of every (key, window) item by AFFINE additions / doublings with shared
+    // inversions - Montgomery's trick over the items a thread owns, continued across the CTA by INV (6-7 multiplications per
+    // entry instead of 11-16 for Jacobian additions plus a normalisation).  The seven results form a tree of depth three,
+    //     round 0: 2B = 2(B)          round 1: 3B = 2B + B, 4B = 2(2B)          round 2: 5B = 4B + B, 6B = 2(3B), 7B = 4B + 3B, 8B = 2(4B)  ...
+    // so W - 1 inversion rounds serve all 2^(W-1) - 1 of them (the first version ran seven sequential rounds: its CTA-wide inversion
+    // chains, 7 x ~270 dependent multiplications on one thread, were 60 % of the kernel's time - ncu, profiles/).  The prefix
+    // products of the trick are parked in the destination entry's x slot, which is free until the result is written: no
+    // per-thread scratch array.  No exceptional case can occur: B has prime order n > 16, so no operand pair is equal or
+    // opposite and no y is zero.
+#ifndef ECB_KT_EPT
+#define ECB_KT_EPT 16
+#endif
+    static constexpr int KT_EPT = ECB_KT_EPT;
+    // operation k of round r (k < 2^r) makes entry v = 2^r + 1 + k: an even v is the double of v / 2 (made in round r - 1), an
+    // odd v is 2^r + (v - 2^r) - both made earlier, and never equal or opposite
+    ECB_DEV static void kt_op(int r, int k, int& dst, int& a, int& b) {      // b == a: doubling
+        dst = (1 << r) + 1 + k;
+        if ((dst & 1) == 0) { a = dst >> 1; b = a; }
+        else { a = 1 << r; b = dst - a; }
+    }
     template <class INV = OwnInv>
     ECB_DEV static void body_kt_fill(int tid, int nthreads, int items, u32* tab) {
-        E pref[KT_EPT];
-        for (int v = 2; v <= 8; v++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int r = 0; r < KT_W - 1; r++) {
+            const int nops = 1 << r;
             E acc;
             F::set_one(acc);
             int cnt = 0;
@@ -975,12 +1004,19 @@ template <class C> struct Bodies {
             for (int j = 0; j < KT_EPT; j++) {
                 const int i = tid + j * nthreads;
                 if (i >= items) break;
-                const u32* ent = tab + (size_t)i * 8 * 2 * L;
-                E d;
-                if (v == 2) { E y0; load_fe(y0, ent + L); F::dbl(d, y0); }
-                else { E x0, x1; load_fe(x0, ent); load_fe(x1, ent + (size_t)(v - 2) * 2 * L); F::sub(d, x1, x0); }
-                pref[j] = acc;
-                F::mul(acc, acc, d);
+                u32* ent = tab + (size_t)i * KT_E * 2 * L;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int k = 0; k < nops; k++) {
+                    int dst, a, b;
+                    kt_op(r, k, dst, a, b);
+                    E d;
+                    if (a == b) { E ya; load_fe(ya, ent + (size_t)(a - 1) * 2 * L + L); F::dbl(d, ya); }
+                    else { E xa, xb; load_fe(xa, ent + (size_t)(a - 1) * 2 * L); load_fe(xb, ent + (size_t)(b - 1) * 2 * L); F::sub(d, xa, xb); }
+                    store_fe(ent + (size_t)(dst - 1) * 2 * L, acc);           // prefix product, parked in the result's own slot
+                    F::mul(acc, acc, d);
+                }
                 cnt++;
             }
             E inv;
@@ -990,26 +1026,74 @@ template <class C> struct Bodies {
 #endif
             for (int j = cnt - 1; j >= 0; j--) {
                 const int i = tid + j * nthreads;
-                u32* ent = tab + (size_t)i * 8 * 2 * L;
-                E x0, y0, x1, y1, d, dinv, lam, x3, y3, t;
-                load_fe(x0, ent); load_fe(y0, ent + L);
-                if (v == 2) { x1 = x0; y1 = y0; F::dbl(d, y0); }
-                else { load_fe(x1, ent + (size_t)(v - 2) * 2 * L); load_fe(y1, ent + (size_t)(v - 2) * 2 * L + L); F::sub(d, x1, x0); }
-                F::mul(dinv, inv, pref[j]);
-                F::mul(inv, inv, d);
-                if (v == 2) {                              // lambda = (3 x^2 + a) / (2 y)
-                    F::sqr(t, x0);
-                    if constexpr (!C::A_IS_ZERO) { E one; F::set_one(one); F::sub(t, t, one); }
-                    F::dbl(lam, t); F::add(lam, lam, t);
-                } else {
-                    F::sub(lam, y1, y0);                   // lambda = (y1 - y0) / (x1 - x0)
+                u32* ent = tab + (size_t)i * KT_E * 2 * L;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int k = nops - 1; k >= 0; k--) {
+                    int dst, a, b;
+                    kt_op(r, k, dst, a, b);
+                    E xa, ya, xb, yb, d, dinv, pre, lam, x3, y3, t;
+                    load_fe(xa, ent + (size_t)(a - 1) * 2 * L); load_fe(ya, ent + (size_t)(a - 1) * 2 * L + L);
+                    load_fe(pre, ent + (size_t)(dst - 1) * 2 * L);
+                    if (a == b) {                              // tangent: lambda = (3 x^2 + a) / (2 y)
+                        xb = xa; yb = ya;
+                        F::dbl(d, ya);
+                        F::sqr(t, xa);
+                        if constexpr (!C::A_IS_ZERO) { E one; F::set_one(one); F::sub(t, t, one); }
+                        F::dbl(lam, t); F::add(lam, lam, t);
+                    } else {                                   // chord: lambda = (y_a - y_b) / (x_a - x_b)
+                        load_fe(xb, ent + (size_t)(b - 1) * 2 * L); load_fe(yb, ent + (size_t)(b - 1) * 2 * L + L);
+                        F::sub(d, xa, xb);
+                        F::sub(lam, ya, yb);
+                    }
+                    F::mul(dinv, inv, pre);
+                    F::mul(inv, inv, d);
+                    F::mul(lam, lam, dinv);
+                    F::sqr(x3, lam); F::sub(x3, x3, xa); F::sub(x3, x3, xb);
+                    F::sub(t, xa, x3); F::mul(y3, lam, t); F::sub(y3, y3, ya);
+                    store_entry(ent + (size_t)(dst - 1) * 2 * L, x3, y3);
                 }
-                F::mul(lam, lam, dinv);
-                F::sqr(x3, lam); F::sub(x3, x3, x0); F::sub(x3, x3, x1);
-                F::sub(t, x0, x3); F::mul(y3, lam, t); F::sub(y3, y3, y0);
-                store_entry(ent + (size_t)(v - 1) * 2 * L, x3, y3);
             }
         }
+    }
+    // signed radix-2^W recoding of a KT_BITS-bit value v (NW words, in place, two spare words above): v + bias with one bit
+    // 2^(W i + W - 1) per signed window i; window i then holds d_i + 2^(W-1), the top window d_top >= 0 including the carry
+    ECB_DEV static void kt_recode(u32* v) {
+        constexpr int NW = KT_BITS / 32;
+        u32 c = 0;
+        ECB_UNROLL
+        for (int j = 0; j < NW; j++) {
+            u32 bias = 0;
+            ECB_UNROLL
+            for (int i = 0; i < KT_WINDOWS - 1; i++) {
+                const int bit = KT_W * i + KT_W - 1;
+                if (bit >= 32 * j && bit < 32 * j + 32) bias |= 1u << (bit - 32 * j);
+            }
+            const u32 t = v[j] + bias;
+            const u32 c1 = t < bias ? 1u : 0u;
+            v[j] = t + c;
+            c = c1 | (v[j] < t ? 1u : 0u);
+        }
+        v[NW] += c;                                        // v[NW] holds bit KT_BITS of the input if it has one (0 otherwise)
+        v[NW + 1] = 0;
+    }
+    ECB_DEV static void kt_digit(const u32* v, int w, u32& mag, u32& neg) {
+        const int bit = KT_W * w;
+        const u64 two = ((u64)v[(bit >> 5) + 1] << 32) | v[bit >> 5];
+        const u32 raw = (u32)(two >> (bit & 31));
+        if (w == KT_WINDOWS - 1) { mag = raw; neg = 0; return; }           // unsigned top window (everything above is zero)
+        const int d = (int)(raw & ((1u << KT_W) - 1u)) - (1 << (KT_W - 1));
+        neg = (u32)(d >> 31);
+        mag = (u32)((d ^ (int)neg) - (int)neg);
+    }
+    // |r| + 0x8888...8 (five words, K256Glv::bias) -> |r| (five words: bit 128 stays where it is, should a half ever reach 2^128)
+    ECB_DEV static void kt_unbias16(u32* o, const u32* a) {
+        o[0] = sub_cc(a[0], 0x88888888u);
+        o[1] = subc_cc(a[1], 0x88888888u);
+        o[2] = subc_cc(a[2], 0x88888888u);
+        o[3] = subc_cc(a[3], 0x88888888u);
+        o[4] = subc(a[4], 0u);
     }
     // the verify main kernel on per-key tables: no doublings, KT_WINDOWS (x2) gathered mixed additions, then u1*G and the
     // inversion-free comparison exactly as body_verify_main
@@ -1026,14 +1110,17 @@ template <class C> struct Bodies {
         for (int l = 0; l < L; l++) u1[l] = rec[l];
         typename JJ::J acc;
         JJ::set_inf(acc);
+        constexpr int NW = KT_BITS / 32;                    // words of the recoded value
         if constexpr (C::A_IS_ZERO) {
-            K256Glv::Split sp;
-            ECB_UNROLL
-            for (int l = 0; l < 5; l++) { sp.a1[l] = rec[8 + l]; sp.a2[l] = rec[13 + l]; }
             const u32 fl = rec[18];
             valid = valid && (fl & 1u);
-            sp.neg1 = (u32)0 - ((fl >> 1) & 1u);
-            sp.neg2 = (u32)0 - ((fl >> 2) & 1u);
+            const u32 neg1 = (u32)0 - ((fl >> 1) & 1u), neg2 = (u32)0 - ((fl >> 2) & 1u);
+            // the prep kernel stores |r1|, |r2| biased for radix 16 (K256Glv::bias): take the bias off, recode for this width
+            u32 k1[NW + 2], k2[NW + 2];
+            kt_unbias16(k1, rec + 8);
+            kt_unbias16(k2, rec + 13);
+            kt_recode(k1);
+            kt_recode(k2);
             E beta;
             ECB_UNROLL
             for (int l = 0; l < 8; l++) beta.v[l] = CurveK256::beta(l);
@@ -1042,40 +1129,38 @@ template <class C> struct Bodies {
 #endif
             for (int w = 0; w < KT_WINDOWS; w++) {
                 u32 mag, neg;
-                K256Glv::digit(sp.a1, w, mag, neg);
+                kt_digit(k1, w, mag, neg);
                 if (mag) {
                     typename JJ::A e;
-                    JJ::load_entry(e, tk + ((size_t)w * 8 + mag - 1) * 2 * L);
-                    JJ::cneg_y(e, neg ^ sp.neg1);
+                    JJ::load_entry(e, tk + ((size_t)w * KT_E + mag - 1) * 2 * L);
+                    JJ::cneg_y(e, neg ^ neg1);
                     JJ::madd(acc, acc, e, nullptr);
                 }
-                K256Glv::digit(sp.a2, w, mag, neg);
+                kt_digit(k2, w, mag, neg);
                 if (mag) {
                     typename JJ::A e;
-                    JJ::load_entry(e, tk + ((size_t)w * 8 + mag - 1) * 2 * L);
+                    JJ::load_entry(e, tk + ((size_t)w * KT_E + mag - 1) * 2 * L);
                     F::mul(e.x, e.x, beta);                 // lambda * (x, y) = (beta x, y)
-                    JJ::cneg_y(e, neg ^ sp.neg2);
+                    JJ::cneg_y(e, neg ^ neg2);
                     JJ::madd(acc, acc, e, nullptr);
                 }
             }
         } else {
-            u32 u2[L], kb[L + 1];
+            u32 kb[NW + 2];
             ECB_UNROLL
-            for (int l = 0; l < L; l++) u2[l] = rec[L + l];
+            for (int l = 0; l < L; l++) kb[l] = rec[L + l];
+            kb[L] = 0;
             valid = valid && (rec[2 * L] & 1u);
-            kb[0] = add_cc(u2[0], 0x88888888u);
-            ECB_UNROLL
-            for (int i = 1; i < L; i++) kb[i] = addc_cc(u2[i], 0x88888888u);
-            kb[L] = addc(0u, 0u);
+            kt_recode(kb);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
             for (int w = 0; w < KT_WINDOWS; w++) {
                 u32 mag, neg;
-                JJ::digit16(kb, w, 8 * L, mag, neg);
+                kt_digit(kb, w, mag, neg);
                 if (mag) {
                     typename JJ::A e;
-                    JJ::load_entry(e, tk + ((size_t)w * 8 + mag - 1) * 2 * L);
+                    JJ::load_entry(e, tk + ((size_t)w * KT_E + mag - 1) * 2 * L);
                     JJ::cneg_y(e, neg);
                     JJ::madd(acc, acc, e, nullptr);
                 }

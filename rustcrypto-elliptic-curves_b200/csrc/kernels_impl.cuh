@@ -205,7 +205,12 @@ template <class C> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_
 template <class C> __global__ void __launch_bounds__(BLK, wt_min_ctas<C>()) k_kt_fill(int items, u32* tab) {
     Bodies<typename CtCurve<C>::type>::template body_kt_fill<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, items, tab);
 }
-template <class C, int MODE> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_verify_keytab(int n, const u8* rs, const u8* z, const u32* scratch, const int* gid, const u8* kvalid,
+// resident CTAs the table-path main kernel is compiled for (its own knob: no per-thread table, smaller frame than k_verify_main)
+#ifndef ECB_KT_MIN_CTAS
+#define ECB_KT_MIN_CTAS 0
+#endif
+template <class C> constexpr int kt_min_ctas() { return ECB_KT_MIN_CTAS ? ECB_KT_MIN_CTAS : fast_min_ctas<C>(); }
+template <class C, int MODE> __global__ void __launch_bounds__(BLK, kt_min_ctas<C>()) k_verify_keytab(int n, const u8* rs, const u8* z, const u32* scratch, const int* gid, const u8* kvalid,
                                                                                                           const u32* tab, const u32* gbig, int gw, u8* ok) {
     Bodies<C>::body_verify_keytab(blockIdx.x * BLK + threadIdx.x, n, MODE, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
 }
@@ -461,7 +466,7 @@ template <class C> struct Launch {
             if (ept < 1) ept = 1;
             if (ept > B::EPT) ept = B::EPT;
             const int threads = (int)((items + ept - 1) / ept);
-            k_normalize<C><<<grid(threads), BLK, 0, s>>>((int)items, proj_scratch, NORM_AFF_STRIDED, 8 * 2 * C::L, nullptr, nullptr, t0);
+            k_normalize<C><<<grid(threads), BLK, 0, s>>>((int)items, proj_scratch, NORM_AFF_STRIDED, B::KT_E * 2 * C::L, nullptr, nullptr, t0);
             count_launch();
         }
         {

@@ -161,7 +161,7 @@ template <class C> struct Emu {
                 std::vector<u32> proj((size_t)c2 * W * 3 * L);
                 for (int t = 0; t < c2; t++) B::body_kt_base(t, built, c2, gkeys.data(), proj.data(), kvalid.data());
                 u32* t0 = tab.data() + (size_t)built * B::KT_KEY_WORDS;
-                normalize(c2 * W, proj.data(), NORM_AFF_STRIDED, 8 * 2 * L, nullptr, nullptr, t0, 0);
+                normalize(c2 * W, proj.data(), NORM_AFF_STRIDED, B::KT_E * 2 * L, nullptr, nullptr, t0, 0);
                 const int items = c2 * W;
                 int th = (items + B::KT_EPT - 1) / B::KT_EPT;
                 if (nthreads > th) th = nthreads;

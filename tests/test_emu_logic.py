@@ -283,6 +283,47 @@ def test_verify_keytab_reused_keys_and_overflow(cname):
     assert lib.emu_verify_keytab(c.cid, 0, 60, q, z, rs, ok, 60, 3, 2) < -3      # more distinct keys than capacity: reported, not mis-verified
 
 
+@pytest.mark.parametrize("kt_w", [4, 5, 6])
+def test_verify_keytab_window_widths(kt_w):
+    """The per-key tables with 4-, 5- and 6-bit windows (ECB_KT_W): recoding across word boundaries, the unsigned top window,
+    the table-construction tree of depth W - 1 - on every curve family (GLV halves, 6-, 7-, 8- and 12-limb scalars), with crafted
+    scalars whose windows are all-maximal / all-minimal, against the oracle."""
+    from tests import crafted
+    vlib = emu_lib.load_variant(kt_w)
+    for cname in CUR:
+        c = o.curve(cname)
+        fb = c.fb
+        rng = random.Random(900 + kt_w + c.cid)
+        rows = []
+        keys = [rng.randrange(1, c.n) for _ in range(3)]
+        for i in range(14 if fb <= 32 else 8):
+            d = keys[i % 3]
+            Q = o.mul_gen(c, d)
+            z = rng.randrange(1 << (8 * fb)).to_bytes(fb, "big")
+            k = rng.randrange(1, c.n)
+            r = o.mul_gen(c, k)[0] % c.n
+            s = pow(k, -1, c.n) * (o.reduce_once(c, int.from_bytes(z, "big")) + r * d) % c.n
+            if c.low_s and s > c.n >> 1:
+                s = c.n - s
+            if i % 5 == 2:
+                r ^= 2
+            rows.append((Q, z, r, s))
+        rows += crafted.exceptional_rows(c)[::4] + crafted.reduced_x_rows(c)[:4]
+        # u2 = r / s with every window at its extreme: choose s = r / u2 for patterned u2 (verdict comes from the oracle)
+        for pat in ("f" * (2 * fb), "8" * (2 * fb), "7" * (2 * fb), "10" * fb, "0f" * fb):
+            u2 = int(pat, 16) % c.n or 1
+            r = rng.randrange(1, c.n)
+            rows.append((o.mul_gen(c, keys[0]), rng.randrange(1 << (8 * fb)).to_bytes(fb, "big"), r, r * pow(u2, -1, c.n) % c.n or 1))
+        q = b"".join(x[0][0].to_bytes(fb, "big") + x[0][1].to_bytes(fb, "big") for x in rows)
+        z = b"".join(x[1] for x in rows)
+        rs = b"".join((x[2] % (1 << 8 * fb)).to_bytes(fb, "big") + (x[3] % (1 << 8 * fb)).to_bytes(fb, "big") for x in rows)
+        n = len(rows)
+        ok = emu_lib.buf(n)
+        assert vlib.emu_verify_keytab(c.cid, 0, n, q, z, rs, ok, max(1, n // 2), n, 2) == len({x[0] for x in rows})
+        assert bytes(ok) == o.batch_verify(c, q, z, rs), (cname, kt_w)
+        assert 0 < sum(ok) < n
+
+
 @pytest.mark.parametrize("cname", CUR)
 def test_verify_exceptional_cases(cname):
     """P + P, P + (-P) and identity accumulators inside the Jacobian fast path, GLV corner scalars."""
