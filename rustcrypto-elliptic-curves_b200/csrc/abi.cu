@@ -91,7 +91,9 @@ struct ecb200_ctx {
     cudaEvent_t ev_in[NSLOT] = {}, ev_done[NSLOT] = {}, ev_out[NSLOT] = {};
     const CurveLaunch* cl[NCURVE] = {};
     uint32_t* gtab[NCURVE] = {};                  // affine multiples 1..ngtab of G (internal limbs)
-    uint32_t* gentab[NCURVE] = {};                // fixed-base window tables (k256)
+    uint32_t* gentab[NCURVE] = {};                // fixed-base window tables, 4-bit windows (k_mul_gen_smem)
+    uint32_t* gentab2[NCURVE] = {};               // fixed-base window tables of the split path (k_gen_half)
+    bool use_gen2 = true;                    // ECB200_GEN2=0: one thread per scalar, complete additions (A/B comparisons)
     uint32_t* gbig[NCURVE] = {};                  // big fixed-base tables of the public-input fast path (built on first use)
     int gw = 16;                             // window width of gbig (ECB200_GW = 4, 8 or 16)
     bool verify_v1 = false;                  // ECB200_VERIFY_V1=1: complete-formula verify kernel (A/B comparisons)
@@ -247,6 +249,21 @@ int build_tables(ecb200_ctx* c) {
             int r = build_table(c, cl, sc, ne, &c->gentab[id], gxy);
             if (r) return r;
         }
+        if (cl->gen2_windows) {   // split fixed-base path: v * 2^(W w) * G, w < gen2_windows, 1 <= v <= gen2_entries
+            const int W = cl->gen2_w, NW = cl->gen2_windows, E = cl->gen2_entries;
+            const int top_bits = 8 * FB - W * (NW - 1);            // bits of the scalar that fall into the (unsigned) top window
+            std::vector<uint8_t> sc((size_t)NW * E * FB, 0);
+            for (int w = 0; w < NW; w++)
+                for (int v = 1; v <= E; v++) {
+                    uint8_t* s = &sc[((size_t)w * E + v - 1) * FB];
+                    if (w == NW - 1 && v == (1 << top_bits)) { memcpy(s, cl->r_mod_n, FB); continue; }   // 2^(8 FB) mod n
+                    if (w == NW - 1 && v > (1 << top_bits)) { s[FB - 1] = 1; continue; }                 // never selected
+                    for (int b = 0; b < W; b++)
+                        if ((v >> b) & 1) { const int pos = W * w + b; s[FB - 1 - pos / 8] |= (uint8_t)(1u << (pos % 8)); }
+                }
+            int r = build_table(c, cl, sc, NW * E, &c->gentab2[id], gxy);
+            if (r) return r;
+        }
     }
     return 0;
 }
@@ -319,13 +336,33 @@ struct TimedLaunch {
     }
 };
 
-int mul_gen_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_k, uint8_t* d_out, uint32_t flags, cudaStream_t s) {
-    CU(c, c->proj.reserve(n * 3 * cl->L * 4));
-    {
-        TimedLaunch t(c, s);
-        cl->mul_gen(s, (flags & ECB200_FLAG_CT) != 0, (int)n, d_k, c->gentab[cl->id], (uint32_t*)c->proj.p);
+// k*G for n scalars, normalised into SEC1 slots (mode 0, d_out) or affine limbs (mode 2, d_limbs).  Default: the split
+// form - two threads per scalar sum one half of the windows each (Jacobian mixed additions), the halves are added with the
+// complete formula inside the normalisation kernel.  ECB200_GEN2=0: one thread per scalar, complete mixed additions.
+int gen_points(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_k, bool ct, int mode, int compress, uint8_t* d_out,
+               uint32_t* d_limbs, cudaStream_t s) {
+    if (c->use_gen2 && c->gentab2[cl->id]) {
+        const size_t half = n * 3 * (size_t)cl->L;
+        CU(c, c->proj.reserve(2 * half * 4));
+        uint32_t* part = (uint32_t*)c->proj.p;
+        {
+            TimedLaunch t(c, s);
+            cl->mul_gen2(s, ct, (int)n, d_k, c->gentab2[cl->id], part);
+        }
+        cl->sum_normalize(s, (int)n, part, part + half, mode, compress, d_out, nullptr, d_limbs);
+    } else {
+        CU(c, c->proj.reserve(n * 3 * cl->L * 4));
+        {
+            TimedLaunch t(c, s);
+            cl->mul_gen(s, ct, (int)n, d_k, c->gentab[cl->id], (uint32_t*)c->proj.p);
+        }
+        cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, mode, compress, d_out, nullptr, d_limbs);
     }
-    cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 0, resolve_compress(cl, flags) ? 1 : 0, d_out, nullptr, nullptr);
+    return 0;
+}
+int mul_gen_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_k, uint8_t* d_out, uint32_t flags, cudaStream_t s) {
+    int r = gen_points(c, cl, n, d_k, (flags & ECB200_FLAG_CT) != 0, 0, resolve_compress(cl, flags) ? 1 : 0, d_out, nullptr, s);
+    if (r) return r;
     CU(c, cudaGetLastError());
     return 0;
 }
@@ -531,10 +568,9 @@ int recover_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* 
 // signing: constant-time fixed-base k*G -> normalise -> (r, s, recid)
 int sign_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_d, const uint8_t* d_k, const uint8_t* d_z, uint8_t* d_rs, uint8_t* d_recid,
               uint8_t* d_ok, cudaStream_t s) {
-    CU(c, c->proj.reserve(n * 3 * (size_t)cl->L * 4));
     CU(c, c->aff.reserve(n * 2 * (size_t)cl->L * 4));
-    cl->mul_gen(s, true, (int)n, d_k, c->gentab[cl->id], (uint32_t*)c->proj.p);
-    cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, nullptr, (uint32_t*)c->aff.p);
+    int r = gen_points(c, cl, n, d_k, true, 2 /*NORM_AFF_LIMBS*/, 0, nullptr, (uint32_t*)c->aff.p, s);
+    if (r) return r;
     cl->sign_finish(s, (int)n, d_d, d_k, d_z, (const uint32_t*)c->aff.p, d_rs, d_recid, d_ok);
     CU(c, cudaGetLastError());
     return 0;
@@ -748,6 +784,7 @@ int ecb200_init(int device, ecb200_ctx** out) {
     if (const char* e = getenv("ECB200_GW")) { int g = atoi(e); if (g == 4 || g == 8 || g == 16) c->gw = g; }
     if (const char* e = getenv("ECB200_VERIFY_V1")) c->verify_v1 = atoi(e) != 0;
     if (const char* e = getenv("ECB200_WINTAB")) c->use_wintab = atoi(e) != 0;
+    if (const char* e = getenv("ECB200_GEN2")) c->use_gen2 = atoi(e) != 0;
     if (const char* e = getenv("ECB200_KEYTAB")) c->use_keytab = atoi(e) != 0;
     if (!ok || build_tables(c) != 0) {
         fprintf(stderr, "ecb200_init failed: %s (%s)\n", c->err.c_str(), cudaGetErrorString(cudaGetLastError()));
@@ -801,6 +838,7 @@ void ecb200_destroy(ecb200_ctx* c) {
     for (int i = 0; i < NCURVE; i++) {
         if (c->gtab[i]) cudaFree(c->gtab[i]);
         if (c->gentab[i]) cudaFree(c->gentab[i]);
+        if (c->gentab2[i]) cudaFree(c->gentab2[i]);
         if (c->gbig[i]) cudaFree(c->gbig[i]);
     }
     c->prep.release();
@@ -1025,7 +1063,7 @@ int ecb200_ecdsa_verify(ecb200_ctx* c, int curve, size_t n, const uint8_t* q, co
 }
 int ecb200_field_op(ecb200_ctx* c, int curve, int which, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* ok) {
     const CurveLaunch* cl = curve_of(c, curve);
-    if (!cl || which < 0 || which > 1 || op < 0 || op > 6 || (n && (!a || !out || !ok))) return fail(c, ECB200_ERR_ARG, "field_op: bad argument");
+    if (!cl || which < 0 || which > 1 || op < 0 || op > 7 || (n && (!a || !out || !ok))) return fail(c, ECB200_ERR_ARG, "field_op: bad argument");
     const size_t FB = cl->FB;
     if (!c->kids.empty())
         return multi_run(c, n, false, [&](ecb200_ctx* kid, size_t, size_t lo, size_t cnt) {

@@ -8,6 +8,7 @@
 // magnitude bookkeeping (field_impl.rs) anywhere on the device.
 #pragma once
 #include "bigint.cuh"
+#include "safegcd.cuh"
 
 namespace ecb {
 
@@ -190,6 +191,21 @@ struct FpK256 {
         for (int i = 0; i < n; i++) sqr(r, r);
     }
 
+    // the same inverse by Bernstein-Yang divsteps (safegcd.cuh; values are canonical integers here, no Montgomery factor);
+    // inv_trick is what the one-chain-per-CTA Montgomery-trick kernels call (-DECB_SAFEGCD=0: the Fermat chain, for A/B)
+    ECB_DEV static void inv_gcd(E& r, const E& a) {
+        u32 pp[8];
+        ECB_UNROLL
+        for (int i = 0; i < 8; i++) pp[i] = p(i);
+        SafeGcd<8>::inv(r.v, a.v, pp);
+    }
+    ECB_DEV static void inv_trick(E& r, const E& a) {
+#if ECB_SAFEGCD
+        inv_gcd(r, a);
+#else
+        inv(r, a);
+#endif
+    }
     // a^(p-2): the addition chain of k256/src/arithmetic/field.rs:187-216 (255 S + 15 M).  0 -> 0.
     ECB_DEV static void inv(E& r, const E& a) {
         E x2, x3, x6, x9, x11, x22, x44, x88, x176, x220, x223, t;

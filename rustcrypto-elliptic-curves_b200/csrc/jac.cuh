@@ -120,6 +120,34 @@ template <class C> struct Jac {
         r.X = x3; r.Y = y3; r.Z = z3;
     }
 
+    // ---- branch-free mixed addition for the secret-scalar FIXED-BASE path (kernels.cuh body_gen_half): p += q in place.
+    // `inf` (all-ones / zero) says p is still the identity, `take` (all-ones / zero) says the digit is non-zero; both are
+    // secret-derived and only ever used as masks.  The generic madd-2004-hmv result is always computed; it is replaced by
+    // q when p was the identity and dropped when the digit is zero.  The caller guarantees p != +-q (h != 0) whenever
+    // both are real points: inside one half of the split fixed-base schedule the running sum is smaller in absolute value
+    // than every entry of the window being added (see body_gen_half), so the exceptional cases of the Jacobian formulas
+    // cannot occur and no complete formula is needed until the halves are combined.  Returns the new `inf`.
+    ECB_POINT_FN static u32 madd_ct(J& p, u32 inf, const A& q, u32 take) {
+        E z1z1, u2, s2, h, rr, hh, hhh, v, t, x3, y3, z3, one;
+        F::sqr(z1z1, p.Z);
+        F::mul(u2, q.x, z1z1);
+        F::mul(s2, q.y, p.Z); F::mul(s2, s2, z1z1);
+        F::sub(h, u2, p.X);
+        F::sub(rr, s2, p.Y);
+        F::sqr(hh, h);
+        F::mul(hhh, hh, h);
+        F::mul(v, p.X, hh);
+        F::mul(z3, p.Z, h);
+        F::sqr(x3, rr); F::sub(x3, x3, hhh); F::sub(x3, x3, v); F::sub(x3, x3, v);
+        F::sub(y3, v, x3); F::mul(y3, rr, y3);
+        F::mul(t, p.Y, hhh);
+        F::sub(y3, y3, t);
+        F::set_one(one);
+        F::cmov(x3, q.x, inf); F::cmov(y3, q.y, inf); F::cmov(z3, one, inf);
+        F::cmov(p.X, x3, take); F::cmov(p.Y, y3, take); F::cmov(p.Z, z3, take);
+        return inf & ~take;
+    }
+
     // ---- full Jacobian addition r = p + q
     ECB_POINT_FN static void add(J& r, const J& p, const J& q) {
         if (is_inf(q)) { r = p; return; }

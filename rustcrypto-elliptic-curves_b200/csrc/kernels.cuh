@@ -43,7 +43,7 @@ enum : int { FIN_SCHNORR = 0, FIN_RECOVER = 1 };
 // so that ONE chain serves all 128 threads; a cooperative policy needs every thread of the CTA to reach run().
 struct OwnInv {
     static constexpr bool COOPERATIVE = false;
-    template <class FF> ECB_DEV static void run(typename FF::E& r, const typename FF::E& a) { FF::inv(r, a); }
+    template <class FF> ECB_DEV static void run(typename FF::E& r, const typename FF::E& a) { FF::inv_trick(r, a); }
 };
 
 template <class C> struct Bodies {
@@ -70,7 +70,7 @@ template <class C> struct Bodies {
     }
 
     // ------------------------------------------------------------------ field test hook
-    // which: 0 = base field, 1 = scalar field.  op: 0 add, 1 sub, 2 mul, 3 sqr, 4 neg, 5 inv, 6 sqrt
+    // which: 0 = base field, 1 = scalar field.  op: 0 add, 1 sub, 2 mul, 3 sqr, 4 neg, 5 inv (Fermat), 6 sqrt, 7 inv (divsteps)
     // out = FB bytes canonical; out_ok[i] = 0 when an input was not canonical (>= modulus) or sqrt does not exist
     template <class FF> ECB_DEV static void field_op_one(int op, const u8* a, const u8* b, u8* out, u8* ok) {
         typename FF::E x, y, r;
@@ -85,6 +85,7 @@ template <class C> struct Bodies {
             case 3: FF::sqr(r, x); break;
             case 4: FF::neg(r, x); break;
             case 5: FF::inv(r, x); break;
+            case 7: FF::inv_gcd(r, x); break;
             default: {
                 FF::sqrt_candidate(r, x);
                 typename FF::E c;
@@ -146,9 +147,12 @@ template <class C> struct Bodies {
     // slot becomes IDENTITY.  One field inversion per thread, 3 mul per element for the trick,
     // 2 mul for (X*zinv, Y*zinv).
     static constexpr int EPT = 16;
+    // sum_with (optional): a second array of n projective points; element i is first replaced by proj[i] + sum_with[i]
+    // (complete addition, written back to proj) - the tail of the split fixed-base path, whose two halves of k*G arrive
+    // as separate partial sums (body_gen_half)
     template <class INV = OwnInv>
     ECB_DEV static void body_normalize(int tid, int nthreads, int n, const u32* proj, int mode, int compress,
-                                       u8* out_bytes, u8* out_inf, u32* out_limbs) {
+                                       u8* out_bytes, u8* out_inf, u32* out_limbs, const u32* sum_with = nullptr) {
         E pref[EPT];
         E acc;
         F::set_one(acc);
@@ -160,6 +164,13 @@ template <class C> struct Bodies {
             int i = tid + j * nthreads;
             if (i >= n) break;
             E z, one;
+            if (sum_with) {
+                Proj a, b;
+                load_proj_limbs(a, proj + (size_t)i * 3 * L);
+                load_proj_limbs(b, sum_with + (size_t)i * 3 * L);
+                G::add(a, a, b);
+                store_proj(const_cast<u32*>(proj) + (size_t)i * 3 * L, a);
+            }
             ECB_UNROLL
             for (int l = 0; l < L; l++) z.v[l] = proj[(size_t)i * 3 * L + 2 * L + l];
             F::set_one(one);
@@ -871,10 +882,15 @@ template <class C> struct Bodies {
     // window width W (ECB_KT_W, bits): signed digits d_w in [-2^(W-1), 2^(W-1)) below the top window, which is unsigned and
     // absorbs the carry of the recoding; KT_E = 2^(W-1) entries per window.  Wider windows trade table construction (KT_E - 1
     // affine operations per window, once per key) for fewer additions per row: measured on the B200 at 2^22 rows / 2^16 keys, see DESIGN.md.
-#ifndef ECB_KT_W
-#define ECB_KT_W 4
-#endif
+    // Measured at 2^22 rows / 2^16 keys (profiles/r02_ab_keytab_window_width.txt): secp256k1 88.6 (W = 4) / 96.8 (5) / 94.1 (6)
+    // M verifies/s, P-256 83.2 / 83.8 / 75.0; at 2^20 rows (16 rows per key) P-384 15.6 / 13.9 / 10.4, SM2 45.1 / 38.6 / 29.2.
+    // secp256k1 recodes two 128-bit halves, so a wider window removes twice the additions per table entry added: it takes
+    // W = 5 (break-even at ~9 rows per key, the path needs 8); the other curves keep W = 4.  -DECB_KT_W=n forces one width.
+#ifdef ECB_KT_W
     static constexpr int KT_W = ECB_KT_W;
+#else
+    static constexpr int KT_W = C::A_IS_ZERO ? 5 : 4;
+#endif
     static constexpr int KT_E = 1 << (KT_W - 1);                          // entries per window: multiples 1 .. 2^(W-1)
     static constexpr int KT_BITS = C::A_IS_ZERO ? 128 : 32 * L;           // bits of the recoded value: a GLV half / a full scalar
     static constexpr int KT_WINDOWS = KT_BITS / KT_W + 1;                 // signed windows below bit W*floor(bits/W), then the top window
@@ -1226,6 +1242,163 @@ template <class C> struct Bodies {
     // k256/src/arithmetic/mul.rs:397-439, and runs the generic window multiplication for the primeorder curves,
     // primeorder/src/projective.rs:422-431; the result point is the same).
     static constexpr int GEN_WINDOWS = 8 * L + 1;
+
+    // ------------------------------------------------------------------ fixed-base k*G, split form (round 2)
+    // The same sum  k*G = sum_w d_w * 2^(W w) * G  over signed radix-2^W digits (W = ECB_GEN2_W, 5 by default: 52 windows of
+    // 16 entries for a 256-bit curve instead of 65 windows of 8), but
+    //   * the windows are cut into two contiguous halves that are summed by two different threads (blockIdx.y of
+    //     k_gen_half): twice the threads for the same work - a 2^16-row batch (BASELINE configs[0]) fills 7 resident CTAs
+    //     per SM in one wave instead of leaving the chip at 4 warps per scheduler - and each CTA stages only its half of the
+    //     table in shared memory (26 KB for secp256k1: seven CTAs per SM fit);
+    //   * inside a half the additions are Jacobian mixed additions (8M + 3S, Jac::madd_ct) instead of complete projective
+    //     ones (11M + 2 m_3b): every entry of window w is v * 2^(W w) * G with v >= 1, while the running sum of the lower
+    //     windows of the same half is smaller than 2^(W w) in absolute value (signed digits, |d| <= 2^(W-1)) and, in the upper
+    //     half, a multiple of 2^(W NH) just like the entry, so sum = +-entry (mod n) is impossible and the exceptional cases
+    //     of the incomplete formulas never arise; "the sum is still the identity" and "the digit is zero" are handled by masks;
+    //   * the two partial sums are added with the COMPLETE formula (they may be equal, opposite or the identity) inside
+    //     the normalisation kernel (body_normalize, sum_with).
+    // Secret-scalar discipline as before (k256/src/arithmetic/mul.rs:424-439 scans its tables the same way): every entry of
+    // a window is read and combined by mask, digits never steer a branch or an address.  CT = false (public scalars) indexes
+    // the table directly and skips zero digits.
+    // Table layout: tab[(w * G2_E + v - 1) * 2L], v = 1..G2_E; the top window is unsigned (bits above W * (G2_WINDOWS - 1)
+    // plus the carry of the recoding, at most 2^(32L - W (G2_WINDOWS - 1)) <= G2_E).
+#ifndef ECB_GEN2_W
+#define ECB_GEN2_W 5
+#endif
+    static constexpr int G2_W = ECB_GEN2_W;
+    static constexpr int G2_E = 1 << (G2_W - 1);
+    static constexpr int G2_WINDOWS = (32 * L) / G2_W + 1;
+    static constexpr int G2_NH = (G2_WINDOWS + 1) / 2;                 // windows of the lower half; the upper half has the rest
+    static_assert((1 << (32 * L - G2_W * (G2_WINDOWS - 1))) <= G2_E, "top window must fit the table");
+    // k (L words, < n) -> k + bias in place (L + 2 words), one bias bit 2^(W i + W - 1) per signed window
+    ECB_DEV static void g2_recode(u32* v) {
+        u32 c = 0;
+        ECB_UNROLL
+        for (int j = 0; j < L; j++) {
+            u32 bias = 0;
+            ECB_UNROLL
+            for (int i = 0; i < G2_WINDOWS - 1; i++) {
+                const int bit = G2_W * i + G2_W - 1;
+                if (bit >= 32 * j && bit < 32 * j + 32) bias |= 1u << (bit - 32 * j);
+            }
+            const u32 t = v[j] + bias;
+            const u32 c1 = t < bias ? 1u : 0u;
+            v[j] = t + c;
+            c = c1 | (v[j] < t ? 1u : 0u);
+        }
+        v[L] = c;
+        v[L + 1] = 0;
+    }
+    ECB_DEV static void g2_digit(const u32* v, int w, u32& mag, u32& neg) {
+        const int bit = G2_W * w;
+        const u64 two = ((u64)v[(bit >> 5) + 1] << 32) | v[bit >> 5];
+        const u32 raw = (u32)(two >> (bit & 31));
+        const int d = (int)(raw & ((1u << G2_W) - 1u)) - (1 << (G2_W - 1));
+        const u32 sneg = (u32)(d >> 31);
+        const u32 smag = (u32)((d ^ (int)sneg) - (int)sneg);
+        const u32 top = (u32)0 - (u32)(w == G2_WINDOWS - 1);            // public: the window index
+        mag = (raw & top) | (smag & ~top);
+        neg = sneg & ~top;
+    }
+    ECB_DEV static void g2_load_entry(typename JJ::A& e, const u32* p) {
+#if defined(__CUDA_ARCH__)
+        if constexpr (L % 4 == 0) {
+            const uint4* q = reinterpret_cast<const uint4*>(p);
+            ECB_UNROLL
+            for (int k = 0; k < L / 4; k++) {
+                const uint4 a = q[k], b = q[L / 4 + k];
+                e.x.v[4 * k] = a.x; e.x.v[4 * k + 1] = a.y; e.x.v[4 * k + 2] = a.z; e.x.v[4 * k + 3] = a.w;
+                e.y.v[4 * k] = b.x; e.y.v[4 * k + 1] = b.y; e.y.v[4 * k + 2] = b.z; e.y.v[4 * k + 3] = b.w;
+            }
+            return;
+        }
+#endif
+        ECB_UNROLL
+        for (int l = 0; l < L; l++) { e.x.v[l] = p[l]; e.y.v[l] = p[L + l]; }
+    }
+    // half: 0 = windows [0, G2_NH), 1 = [G2_NH, G2_WINDOWS); tabh: the entries of THIS half's windows (shared memory on the
+    // device); part: 2 x n x 3L limbs, half h of row i at (h * n + i) * 3L as a homogeneous projective point
+    // ECB_GEN2_SHFL (device only): the 16 entries of a window are spread over the lanes of the warp (lane j holds entry
+    // (j & 15) + 1, a PUBLIC address) and every lane fetches the entry of its own digit with one warp shuffle per word - the
+    // secret digit selects a source LANE of a register exchange, never a memory address or a branch; 4 LDS.128 + 16 SHFL per
+    // window instead of 64 LDS.128 + 256 LOP3 for the masked scan.  Every lane of the warp must take part, so rows past the
+    // end of the batch are clamped to the last row instead of returning early (their result is not stored).
+#ifndef ECB_GEN2_SHFL
+#define ECB_GEN2_SHFL 0
+#endif
+    template <bool CT> ECB_DEV static void body_gen_half(int tid, int n, int half, const u8* k, const u32* tabh, u32* part) {
+#if defined(__CUDA_ARCH__) && ECB_GEN2_SHFL
+        const bool live = tid < n;
+        if (!live) tid = n - 1;
+        const int lane16 = (int)(threadIdx.x & 15u);
+#else
+        if (tid >= n) return;
+#endif
+        u32 kb[L + 2];
+        G::load_scalar(kb, k + (size_t)tid * FB);
+        g2_recode(kb);
+        const int w0 = half * G2_NH;
+        const int w1 = half ? G2_WINDOWS : G2_NH;
+        typename JJ::J acc;
+        JJ::set_inf(acc);
+        u32 inf = 0xFFFFFFFFu;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int w = w0; w < w1; w++) {
+            u32 mag, neg;
+            g2_digit(kb, w, mag, neg);
+            const u32* win = tabh + (size_t)(w - w0) * G2_E * 2 * L;
+            typename JJ::A g;
+            if constexpr (CT) {
+#if defined(__CUDA_ARCH__) && ECB_GEN2_SHFL
+                static_assert(G2_E <= 16, "one entry per lane of a half warp");
+                typename JJ::A mine;
+                g2_load_entry(mine, win + (size_t)(lane16 & (G2_E - 1)) * 2 * L);
+                const int src = (int)((mag - 1u) & (u32)(G2_E - 1));       // digit 0 reads some entry; the addition is masked out below
+                ECB_UNROLL
+                for (int l = 0; l < L; l++) {
+                    g.x.v[l] = __shfl_sync(0xFFFFFFFFu, mine.x.v[l], src);
+                    g.y.v[l] = __shfl_sync(0xFFFFFFFFu, mine.y.v[l], src);
+                }
+#else
+                F::set_zero(g.x); F::set_zero(g.y);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+                for (u32 j = 1; j <= (u32)G2_E; j++) {
+                    typename JJ::A c;
+                    g2_load_entry(c, win + (size_t)(j - 1) * 2 * L);
+                    const u32 m = (u32)0 - (u32)(j == mag);
+                    F::cmov(g.x, c.x, m); F::cmov(g.y, c.y, m);
+                }
+#endif
+                JJ::cneg_y(g, neg);
+                inf = JJ::madd_ct(acc, inf, g, (u32)0 - (u32)(mag != 0));
+            } else {
+                if (mag) {
+                    g2_load_entry(g, win + (size_t)(mag - 1) * 2 * L);
+                    JJ::cneg_y(g, neg);
+                    JJ::madd(acc, acc, g, nullptr);
+                    inf = 0;
+                }
+            }
+        }
+        // Jacobian -> homogeneous (X Z : Y : Z^3); the identity becomes (0 : 1 : 0) by mask
+        Proj o, id;
+        E zz;
+        F::sqr(zz, acc.Z);
+        F::mul(o.X, acc.X, acc.Z);
+        o.Y = acc.Y;
+        F::mul(o.Z, zz, acc.Z);
+        G::set_identity(id);
+        if constexpr (!CT) inf = JJ::is_inf(acc) ? 0xFFFFFFFFu : 0u;
+        G::cmov(o, id, inf);
+#if defined(__CUDA_ARCH__) && ECB_GEN2_SHFL
+        if (!live) return;
+#endif
+        store_proj(part + ((size_t)half * n + tid) * 3 * L, o);
+    }
     template <bool CT> ECB_DEV static void body_mul_gen(int tid, int n, const u8* k, const u32* tab, u32* out) {
         if (tid >= n) return;
         u32 kk[L];

@@ -108,7 +108,7 @@ struct BlockInv {
                 for (int w = 0; w < W; w++) { t.v[w] = sh[k * W + w]; sh[(NW + k) * W + w] = tot.v[w]; }
                 FF::mul(tot, tot, t);
             }
-            FF::inv(inv, tot);
+            FF::inv_trick(inv, tot);      // divsteps (safegcd.cuh): ~4x shorter dependent path than the Fermat chain
 #pragma unroll 1
             for (int k = NW - 1; k >= 0; k--) {
 #pragma unroll
@@ -146,6 +146,10 @@ template <class C> __global__ void __launch_bounds__(BLK) k_load_proj(int n, con
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_normalize(int n, const u32* proj, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
     Bodies<typename CtCurve<C>::type>::template body_normalize<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, proj, mode, compress, out_bytes, out_inf, out_limbs);
+}
+// proj[i] += sum_with[i] (complete addition), then the same normalisation: tail of the split fixed-base path
+template <class C> __global__ void __launch_bounds__(BLK) k_sum_normalize(int n, u32* proj, const u32* sum_with, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
+    Bodies<typename CtCurve<C>::type>::template body_normalize<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, n, proj, mode, compress, out_bytes, out_inf, out_limbs, sum_with);
 }
 template <class C> __global__ void __launch_bounds__(BLK) k_verify(int n, const u8* q, const u8* z, const u8* rs, const u32* gtab, u8* ok) {
     Bodies<C>::body_verify(blockIdx.x * BLK + threadIdx.x, n, q, z, rs, gtab, ok);
@@ -202,7 +206,11 @@ template <class C> __global__ void __launch_bounds__(256) k_kt_assign(int n, int
 template <class C> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_kt_base(int g0, int cnt, const u32* gkeys, u32* proj, u8* kvalid) {
     Bodies<C>::body_kt_base(blockIdx.x * BLK + threadIdx.x, g0, cnt, gkeys, proj, kvalid);
 }
-template <class C> __global__ void __launch_bounds__(BLK, wt_min_ctas<C>()) k_kt_fill(int items, u32* tab) {
+#ifndef ECB_KTF_MIN_CTAS
+#define ECB_KTF_MIN_CTAS ECB_WT_MIN_CTAS
+#endif
+template <class C> constexpr int ktf_min_ctas() { return C::L > 8 ? 3 : ECB_KTF_MIN_CTAS; }
+template <class C> __global__ void __launch_bounds__(BLK, ktf_min_ctas<C>()) k_kt_fill(int items, u32* tab) {
     Bodies<typename CtCurve<C>::type>::template body_kt_fill<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, items, tab);
 }
 // resident CTAs the table-path main kernel is compiled for (its own knob: no per-thread table, smaller frame than k_verify_main)
@@ -298,6 +306,40 @@ template <class C, bool CT> __global__ void __launch_bounds__(BLK, ct_min_ctas<C
     Bodies<C>::template body_mul_gen<CT>(blockIdx.x * BLK + threadIdx.x, n, k, stab, proj);
 }
 
+// Split fixed-base kernel (kernels.cuh body_gen_half): blockIdx.y picks the half of the windows, the CTA stages that half of
+// the table with one TMA bulk copy.  Compiled for the public-input kernels' occupancy (Jacobian arithmetic, acc in local
+// memory): 7 resident CTAs per SM on the 8-limb curves, so that the 2 x 512 CTAs of a 2^16-row batch are one wave.
+#ifndef ECB_GEN2_MIN_CTAS
+#define ECB_GEN2_MIN_CTAS 7
+#endif
+template <class C> constexpr int gen2_min_ctas() { return C::L > 8 ? 3 : ECB_GEN2_MIN_CTAS; }
+template <class C, bool CT> __global__ void __launch_bounds__(BLK, gen2_min_ctas<C>()) k_gen_half(int n, const u8* k, const u32* tab, u32* part) {
+    typedef Bodies<C> B;
+    extern __shared__ __align__(128) u32 stab[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int half = blockIdx.y;
+    const int w0 = half * B::G2_NH;
+    const int nw = half ? B::G2_WINDOWS - B::G2_NH : B::G2_NH;
+    const u32 bytes = (u32)nw * B::G2_E * 2u * C::L * 4u;
+    const u32* src = tab + (size_t)w0 * B::G2_E * 2 * C::L;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_addr(stab)), "l"(src), "r"(bytes), "r"(smem_addr(&bar)) : "memory");
+    }
+    u32 done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_addr(&bar)) : "memory");
+    }
+    B::template body_gen_half<CT>(blockIdx.x * BLK + threadIdx.x, n, half, k, stab, part);
+}
+
 // ---------------------------------------------------------------------------------------------
 template <class C> struct Launch {
     static int grid(int n) { return (n + BLK - 1) / BLK; }
@@ -332,6 +374,30 @@ template <class C> struct Launch {
         }
         if (ct) k_mul_gen_smem<C, true><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
         else k_mul_gen_smem<C, false><<<grid(n), BLK, bytes, s>>>(n, k, tab, bytes, proj);
+        count_launch();
+    }
+    // split form: part = 2 x n x 3L limbs (lower-half sums, then upper-half sums); finish with sum_normalize(part, part + n * 3L)
+    static void mul_gen2(cudaStream_t s, bool ct, int n, const u8* k, const u32* tab2, u32* part) {
+        if (n <= 0) return;
+        typedef Bodies<C> B;
+        const u32 bytes = (u32)B::G2_NH * B::G2_E * 2u * C::L * 4u;   // the larger half
+        static std::atomic<bool> seen[64] = {};
+        if (first_use_on_device(seen)) {
+            cudaFuncSetAttribute(k_gen_half<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            cudaFuncSetAttribute(k_gen_half<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        }
+        const dim3 g((unsigned)grid(n), 2u);
+        if (ct) k_gen_half<C, true><<<g, BLK, bytes, s>>>(n, k, tab2, part);
+        else k_gen_half<C, false><<<g, BLK, bytes, s>>>(n, k, tab2, part);
+        count_launch();
+    }
+    static void sum_normalize(cudaStream_t s, int n, u32* proj, const u32* sum_with, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
+        if (n <= 0) return;
+        int ept = (n + 148 * 1 * BLK - 1) / (148 * 1 * BLK);
+        if (ept < 1) ept = 1;
+        if (ept > Bodies<C>::EPT) ept = Bodies<C>::EPT;
+        int threads = (n + ept - 1) / ept;
+        k_sum_normalize<C><<<grid(threads), BLK, 0, s>>>(n, proj, sum_with, mode, compress, out_bytes, out_inf, out_limbs);
         count_launch();
     }
     static void load_proj(cudaStream_t s, int n, const u8* xyz, u32* proj, u8* invalid) {
@@ -505,7 +571,8 @@ template <class C> struct Launch {
             C::ID, C::L, C::FB, C::A_IS_ZERO ? 8 : 15, Bodies<C>::GEN_WINDOWS, 8, C::COMPRESS_DEFAULT, {0},
             &field_op, &mul_var, &mul_gen, &load_proj, &normalize, &sum, &proj_to_bytes, &verify,
             &mul_var_fast, &verify_prep, &verify_main, &decode, &finish, &sign_finish, &wintab, &add_proj,
-            Bodies<C>::KT_WINDOWS, Bodies<C>::KT_KEY_WORDS, Bodies<C>::KBW, &kt_group, &kt_build, &verify_keytab, Bodies<C>::PREP_WORDS, SUM_BLOCKS};
+            Bodies<C>::KT_WINDOWS, Bodies<C>::KT_KEY_WORDS, Bodies<C>::KBW, &kt_group, &kt_build, &verify_keytab, Bodies<C>::PREP_WORDS, SUM_BLOCKS,
+            Bodies<C>::G2_W, Bodies<C>::G2_WINDOWS, Bodies<C>::G2_E, &mul_gen2, &sum_normalize};
         for (int i = 0; i < C::L; i++) {   // R mod n (the Montgomery "one" of the scalar field) as big-endian bytes
             const u32 w = C::Fn::Params::one(i);
             t.r_mod_n[C::FB - 4 * i - 1] = (u8)w; t.r_mod_n[C::FB - 4 * i - 2] = (u8)(w >> 8);

@@ -54,6 +54,12 @@ struct CurveLaunch {
                           const uint8_t* kvalid, const uint32_t* tab, const uint32_t* gbig, int gw, uint8_t* ok);
     int prep_words;   // u32 words of scratch per row between verify_prep and verify_main
     int sum_blocks;
+    // split fixed-base path (kernels.cuh body_gen_half): table of gen2_windows x gen2_entries affine entries
+    // v * 2^(gen2_w * w) * G; mul_gen2 leaves the two half sums in part (2 x n x 3L limbs), sum_normalize adds and normalises
+    int gen2_w, gen2_windows, gen2_entries;
+    void (*mul_gen2)(cudaStream_t s, bool ct, int n, const uint8_t* k, const uint32_t* tab2, uint32_t* part);
+    void (*sum_normalize)(cudaStream_t s, int n, uint32_t* proj, const uint32_t* sum_with, int mode, int compress, uint8_t* out_bytes,
+                          uint8_t* out_inf, uint32_t* out_limbs);
 };
 
 const CurveLaunch* launch_k256();

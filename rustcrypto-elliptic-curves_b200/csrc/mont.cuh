@@ -11,6 +11,7 @@
 // one(i) = R mod p, r2(i) = R^2 mod p.
 #pragma once
 #include "bigint.cuh"
+#include "safegcd.cuh"
 #include "fp_k256.cuh"   // Fe<L>
 
 namespace ecb {
@@ -403,6 +404,27 @@ template <class P, bool SQSPLIT = false> struct Mont {
         ECB_UNROLL
         for (int i = 1; i < L; i++) e[i] = subc_cc(P::p(i), 0u);
         pow_limbs(r, a, e);
+    }
+    // The same inverse by Bernstein-Yang divsteps (safegcd.cuh): a quarter of Fermat's dependent path, constant time.  The
+    // stored value aR is inverted as a plain integer, (aR)^-1 = a^-1 R^-1, and two Montgomery products with R^2 bring it
+    // to a^-1 R.  inv_trick is what the one-chain-per-CTA Montgomery-trick kernels call (-DECB_SAFEGCD=0: Fermat, for A/B).
+    ECB_DEV static void inv_gcd(E& r, const E& a) {
+        u32 pp[L];
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) pp[i] = P::p(i);
+        E t, r2;
+        SafeGcd<L>::inv(t.v, a.v, pp);
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) r2.v[i] = P::r2(i);
+        mul(t, t, r2);
+        mul(r, t, r2);
+    }
+    ECB_DEV static void inv_trick(E& r, const E& a) {
+#if ECB_SAFEGCD
+        inv_gcd(r, a);
+#else
+        inv(r, a);
+#endif
     }
     // p = 1 (mod 4) (P-224: p - 1 = 2^96 (2^128 - 1)): Tonelli-Shanks, variable time - square roots are only taken of public
     // data (point decompression).  The reference runs the constant-time form of the same algorithm

@@ -220,6 +220,50 @@ template <class C> struct Emu {
         }
         normalize(n, proj.data(), NORM_SEC1, compress, out, nullptr, nullptr, 0);
     }
+    // split fixed-base table: v * 2^(W w) * G, w < G2_WINDOWS, 1 <= v <= G2_E (as abi.cu build_tables)
+    static std::vector<u32> gentab2() {
+        const int W = B::G2_W, NW = B::G2_WINDOWS, E = B::G2_E, ne = NW * E, top_bits = 8 * FB - W * (NW - 1);
+        std::vector<u8> pts(2 * FB * (size_t)ne), ks(FB * (size_t)ne, 0);
+        typename EC<C>::Aff g;
+        EC<C>::generator(g);
+        u32 t[L];
+        for (int e = 0; e < ne; e++) {
+            C::F::to_limbs(t, g.x); store_be<L>(&pts[2 * FB * (size_t)e], t);
+            C::F::to_limbs(t, g.y); store_be<L>(&pts[2 * FB * (size_t)e + FB], t);
+            const int w = e / E, v = e % E + 1;
+            u8* s = &ks[FB * (size_t)e];
+            if (w == NW - 1 && v == (1 << top_bits)) {
+                u32 one[L];
+                for (int l = 0; l < L; l++) one[l] = C::Fn::Params::one(l);   // R mod n = 2^(8FB) mod n
+                store_be<L>(s, one);
+            } else if (w == NW - 1 && v > (1 << top_bits)) {
+                s[FB - 1] = 1;
+            } else {
+                for (int b = 0; b < W; b++) if ((v >> b) & 1) { int pos = W * w + b; s[FB - 1 - pos / 8] |= (u8)(1u << (pos % 8)); }
+            }
+        }
+        std::vector<u32> proj(3 * L * (size_t)ne), out(2 * L * (size_t)ne);
+        for (int i = 0; i < ne; i++) B::template body_mul_var<false>(i, ne, 0, pts.data(), nullptr, ks.data(), proj.data(), nullptr);
+        normalize(ne, proj.data(), NORM_AFF_LIMBS, 0, nullptr, nullptr, out.data(), 0);
+        return out;
+    }
+    // the split fixed-base path as abi.cu gen_points drives it: two half sums per scalar, complete addition inside the normalisation
+    static void mul_gen2(int ct, int n, const u8* k, u8* out, int compress, int nthreads) {
+        static std::vector<u32> tab;
+        if (tab.empty()) tab = gentab2();
+        std::vector<u32> part((size_t)2 * 3 * L * n);
+        for (int h = 0; h < 2; h++) {
+            const u32* th = tab.data() + (size_t)h * B::G2_NH * B::G2_E * 2 * L;
+            for (int i = 0; i < n; i++) {
+                if (ct) B::template body_gen_half<true>(i, n, h, k, th, part.data());
+                else B::template body_gen_half<false>(i, n, h, k, th, part.data());
+            }
+        }
+        int need = (n + B::EPT - 1) / B::EPT;
+        if (nthreads < need) nthreads = need;
+        for (int t = 0; t < nthreads; t++)
+            B::body_normalize(t, nthreads, n, part.data(), NORM_SEC1, compress, out, nullptr, nullptr, part.data() + (size_t)3 * L * n);
+    }
     static void batch_normalize(int n, const u8* xyz, u8* xy, u8* inf, int nthreads) {
         std::vector<u32> proj((size_t)3 * L * n);
         for (int i = 0; i < n; i++) B::body_load_proj(i, n, xyz, proj.data(), nullptr);
@@ -254,6 +298,10 @@ int emu_mul_var(int curve, int ct, int n, unsigned flags, const u8* pts, const u
 }
 int emu_mul_gen(int curve, int ct, int n, const u8* k, u8* out, int compress) {
     DISPATCH(curve, mul_gen(ct, n, k, out, compress));
+    return 0;
+}
+int emu_mul_gen2(int curve, int ct, int n, const u8* k, u8* out, int compress, int nthreads) {
+    DISPATCH(curve, mul_gen2(ct, n, k, out, compress, nthreads));
     return 0;
 }
 int emu_batch_normalize(int curve, int n, const u8* xyz, u8* xy, u8* inf, int nthreads) {

@@ -22,4 +22,5 @@ def test_secret_scalar_kernels_have_no_data_dependent_branch(tmp_path):
     assert "Total findings: 0" in text
     # all three kernel families of all six curves were actually inspected
     assert text.count("## `void k_mul_var<") == 6 and text.count("## `void k_mul_gen_smem<") == 6 and text.count("## `void k_sign_finish<") == 6
+    assert text.count("## `void k_gen_half<") == 6 and text.count("## `void k_sum_normalize<") == 6      # split fixed-base path
     assert "indirect branches (BRX/JMX): 0" in text and "BRX/JMX): 1" not in text

@@ -52,6 +52,11 @@ def test_field_ops(cname, which):
     A2 = ev + [rng.randrange(m) for _ in range(20)]
     got, _ = field_op(c, which, 5, A2)
     assert got == [pow(a, m - 2, m) for a in A2]
+    # the same inverse by divsteps (safegcd.cuh): edge values, powers of two, values around 2^30 limb boundaries
+    A3 = A2 + [1 << k for k in range(0, 8 * c.fb - 1, 7)] + [(1 << k) - 1 for k in range(29, 8 * c.fb, 30)] + [m - (1 << k) for k in range(1, 8 * c.fb - 2, 29)]
+    A3 = [a % m for a in A3] + [rng.randrange(m) for _ in range(300)]
+    got, _ = field_op(c, which, 7, A3)
+    assert got == [pow(a, m - 2, m) for a in A3]
     # non-canonical input is flagged
     _, ok = field_op(c, which, 0, [m, 2**(8 * c.fb) - 1], [0, 0])
     assert ok == [0, 0]
@@ -147,6 +152,45 @@ def test_mul_gen(cname, ct, golden):
     out = emu_lib.buf(len(ks) * stride)
     assert lib.emu_mul_gen(c.cid, ct, len(ks), kb, out, int(c.compress)) == 0
     assert bytes(out) == o.batch_mul_gen(c, kb)
+
+
+def split_gen_scalars(c, rng, W=5):
+    """Scalars that stress the split fixed-base schedule: zero halves, one non-zero digit per half, runs of maximal digits
+    (carries of the signed recoding through every window), the half boundary, the top window and its carry."""
+    fb, n = c.fb, c.n
+    bits = 8 * fb
+    nwin = bits // W + 1
+    nh = (nwin + 1) // 2
+    cut = W * nh                                   # first bit of the upper half
+    ks = scalars_edge(c, rng, 8)
+    ks += [0, 1, 2, n - 1, n - 2, n, n + 1, (1 << bits) - 1, (1 << bits) - 2]
+    ks += [1 << cut, (1 << cut) - 1, (1 << cut) + 1, (1 << (cut - 1)), (1 << (cut - 1)) - 1, ((1 << cut) - 1) ^ ((1 << (cut - W)) - 1)]
+    ks += [rng.randrange(1 << cut), rng.randrange(1 << (bits - cut)) << cut]            # one half empty
+    ks += [(1 << (W * w)) * v % n for w in (0, 1, nh - 1, nh, nh + 1, nwin - 2, nwin - 1) for v in (1, (1 << (W - 1)) - 1, 1 << (W - 1), (1 << (W - 1)) + 1, (1 << W) - 1)]
+    ks += [int("8" * (2 * fb), 16) % n, int("7" * (2 * fb), 16) % n, int("F" * (2 * fb), 16) % n, n - 8, n >> 1, (n >> 1) + 1]
+    half_pattern = sum(1 << (W * w + W - 1) for w in range(nwin - 1))                   # every signed window at -2^(W-1) + carry chain
+    ks += [half_pattern % n, (half_pattern - 1) % n, (half_pattern + 1) % n, (n - half_pattern) % n]
+    return ks
+
+
+@pytest.mark.parametrize("cname", CUR)
+@pytest.mark.parametrize("ct", [0, 1])
+def test_mul_gen_split(cname, ct, golden):
+    """split fixed-base path (two half sums with Jacobian mixed additions, complete addition in the normalisation)"""
+    c = o.curve(cname)
+    rng = random.Random(31 + ct)
+    ks = split_gen_scalars(c, rng) + [rng.randrange(c.n) for _ in range(40)]
+    ks += [int(k, 16) for k, _, _ in golden["group"].get(cname, {"mul": []})["mul"]]
+    fb = c.fb
+    kb = b"".join((k % (1 << (8 * fb))).to_bytes(fb, "big") for k in ks)
+    stride = 1 + (fb if c.compress else 2 * fb)
+    for nthreads in (0, 7):
+        out = emu_lib.buf(len(ks) * stride)
+        assert lib.emu_mul_gen2(c.cid, ct, len(ks), kb, out, int(c.compress), nthreads) == 0
+        exp = o.batch_mul_gen(c, kb)
+        got = bytes(out)
+        bad = [i for i in range(len(ks)) if got[i * stride:(i + 1) * stride] != exp[i * stride:(i + 1) * stride]]
+        assert not bad, (cname, ct, [hex(ks[i]) for i in bad[:4]])
 
 
 @pytest.mark.parametrize("cname", CUR)

@@ -6,7 +6,7 @@ k256/src/arithmetic/mul.rs:92-127 and primeorder/src/projective.rs:127-147.  The
 scans, masked selects), but nothing in C++ forces ptxas to keep a ternary a SEL; this tool looks at the machine code:
 
   * every CONDITIONAL control transfer (predicated BRA / EXIT / RET / CALL, BRA.U on a uniform predicate, any indirect
-    BRX / JMX) of k_mul_var<*, true>, k_mul_gen_smem<*, true> and k_sign_finish<*> - including the device functions they
+    BRX / JMX) of k_mul_var<*, true>, k_mul_gen_smem<*, true>, k_gen_half<*, true>, k_sum_normalize<*> and k_sign_finish<*> - including the device functions they
     call - is listed with the source line nvdisasm attributes it to (-lineinfo) and the instruction that set its predicate;
   * each must sit on a source line matching an ALLOW pattern: row guard (tid >= n), loops over public counters, public flags
     (F_PROJ, the `inf` byte), validity of PUBLIC inputs (point on curve / coordinates < p), the mbarrier wait of the TMA copy,
@@ -28,7 +28,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "rustcrypto-elliptic-curves_b200", "_build")
 CURVES = ["k256", "p256", "p384", "sm2", "p192", "p224"]
-KERNELS = [r"k_mul_varINS_\w+ELb1E", r"k_mul_gen_smemINS_\w+ELb1E", r"k_sign_finishINS_"]
+KERNELS = [r"k_mul_varINS_\w+ELb1E", r"k_mul_gen_smemINS_\w+ELb1E", r"k_sign_finishINS_", r"k_gen_halfINS_\w+ELb1E", r"k_sum_normalizeINS_"]
 # source-line patterns under which a conditional branch is legitimate in a secret-scalar kernel (all public quantities)
 ALLOW = [
     (r"if \(tid >= n\) return", "row guard (public batch size)"),
@@ -48,6 +48,15 @@ ALLOW = [
     (r"if \(n <= 0\)", "launcher"),
     (r"return on_curve\(a\) && ok|bool ok = F::from_limbs|ok = F::from_limbs|return F::eq\(lhs, rhs\)", "validation of the PUBLIC input point"),
     (r"if \(invalid\) invalid\[tid\]", "optional output pointer (public)"),
+    # k_sum_normalize (tail of the split fixed-base path): output format switches, and the identity test of the RESULT point -
+    # the result is what the call returns in clear (an all-zero SEC1 slot / the ok byte of a signature), so it is public by
+    # construction; the complete addition and the inversion before it carry no branch at all
+    (r"if \(mode == NORM_SEC1\)|mode == NORM_XY_BYTES|mode == NORM_AFF_STRIDED", "output format (public call argument)"),
+    (r"if \(inf\) \{|if \(isinf\) \{|out_inf\[i\] = isinf", "identity test of the result point, which the call outputs in clear"),
+    (r"out\[0\] = \(u8\)\(2u \+ \(t\[0\] & 1u\)\)|if \(compress\)", "SEC1 compression flag (public call argument)"),
+    (r"if \(sum_with\)", "optional second operand array (public call shape)"),
+    (r"e\.v\[i - 1\] = \(int\)ce & M30; ce >>= 30;|g\.v\[i - 1\] = \(int\)cg & M30; cg >>= 30;|g >>= 1; u <<= 1; v <<= 1;",
+     "back edge of a fixed-trip-count limb / divstep loop of safegcd.cuh (public counter; ptxas keeps the 13-limb loop rolled)"),
 ]
 
 
