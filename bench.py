@@ -54,7 +54,7 @@ CASES = {
     ("mul_var", "p256"): dict(cfg="configs[4] shape on P-256", m_ref=4366, log2=20, seed=0xB2000009, unit="scalar-mul/s", projective=False,
                               metric="P-256 variable-base P*k throughput", kernel="k_mul_var_fast<CurveP256> (k_wintab<CurveP256> before it)"),
     ("mul_gen", "k256"): dict(cfg="configs[0]", m_ref=817, log2=16, seed=0xB2000001, unit="scalar-mul/s",
-                              metric="secp256k1 fixed-base G*k throughput (constant-time path)", kernel="k_mul_gen_smem<CurveK256, true>"),
+                              metric="secp256k1 fixed-base G*k throughput (constant-time path)", kernel="k_gen_half<CurveK256, true> (two half sums per scalar; k_sum_normalize<CurveK256> after it)"),
 }
 IO_BYTES = {"verify": lambda fb, slot: (5 * fb, 1), "mul_gen": lambda fb, slot: (fb, slot),
             "mul_var": lambda fb, slot: (3 * fb, slot), "mul_var_proj": lambda fb, slot: (4 * fb, slot)}

@@ -312,31 +312,89 @@ template <int L> ECB_DEV void sqr_wide(u32* r, const u32* a) {
 // ------------------------------------------------------------------------------------------
 // big-endian byte string <-> little-endian limbs (FB = 4L bytes)
 
-template <int L> ECB_DEV void load_be(u32* v, const u8* p) {
+template <int L> ECB_DEV void load_be_bytes(u32* v, const u8* p) {
     ECB_UNROLL
     for (int i = 0; i < L; i++) {
         const u8* q = p + 4 * (L - 1 - i);
         v[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
     }
 }
-template <int L> ECB_DEV void store_be(u8* p, const u32* v) {
+template <int L> ECB_DEV void store_be_bytes(u8* p, const u32* v) {
     ECB_UNROLL
     for (int i = 0; i < L; i++) {
         u8* q = p + 4 * (L - 1 - i);
         q[0] = (u8)(v[i] >> 24); q[1] = (u8)(v[i] >> 16); q[2] = (u8)(v[i] >> 8); q[3] = (u8)v[i];
     }
 }
-// 16-byte aligned variant: p points at 4L bytes, 16-byte aligned (device buffers are)
-template <int L> ECB_DEV void load_be_aligned(u32* v, const u8* p) {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    ECB_UNROLL
-    for (int k = 0; k < L / 4; k++) {
-        uint4 w = q[k];
-        v[L - 1 - 4 * k] = bswap32(w.x);
-        v[L - 2 - 4 * k] = bswap32(w.y);
-        v[L - 3 - 4 * k] = bswap32(w.z);
-        v[L - 4 - 4 * k] = bswap32(w.w);
+// N consecutive words between registers and global / local memory with the widest access the word count allows: 128-bit
+// for N % 4 == 0, 64-bit for even N, 32-bit otherwise.  The address must be aligned accordingly (16 / 8 / 4 bytes): every
+// internal limb array of the engine is (element sizes are multiples of 4L bytes on cudaMalloc'd bases).  Per-thread rows of
+// the table kernels lie hundreds of bytes apart, so every access of a lane is its own L1 wavefront whatever its width: the
+// 32-bit form cost k_kt_fill / k_wintab four times the LSU cycles (ncu: LDG.E x 32 wavefronts dominated the kernels).
+template <int N> ECB_DEV void ld_words(u32* dst, const u32* src) {
+#if defined(__CUDA_ARCH__) && !defined(ECB_EMU)
+    if constexpr (N % 4 == 0) {
+        const ::uint4* q = reinterpret_cast<const ::uint4*>(src);
+        ECB_UNROLL
+        for (int k = 0; k < N / 4; k++) { const ::uint4 w = q[k]; dst[4 * k] = w.x; dst[4 * k + 1] = w.y; dst[4 * k + 2] = w.z; dst[4 * k + 3] = w.w; }
+        return;
+    } else if constexpr (N % 2 == 0) {
+        const ::uint2* q = reinterpret_cast<const ::uint2*>(src);
+        ECB_UNROLL
+        for (int k = 0; k < N / 2; k++) { const ::uint2 w = q[k]; dst[2 * k] = w.x; dst[2 * k + 1] = w.y; }
+        return;
     }
+#endif
+    ECB_UNROLL
+    for (int k = 0; k < N; k++) dst[k] = src[k];
+}
+template <int N> ECB_DEV void st_words(u32* dst, const u32* src) {
+#if defined(__CUDA_ARCH__) && !defined(ECB_EMU)
+    if constexpr (N % 4 == 0) {
+        ::uint4* q = reinterpret_cast<::uint4*>(dst);
+        ECB_UNROLL
+        for (int k = 0; k < N / 4; k++) q[k] = make_uint4(src[4 * k], src[4 * k + 1], src[4 * k + 2], src[4 * k + 3]);
+        return;
+    } else if constexpr (N % 2 == 0) {
+        ::uint2* q = reinterpret_cast<::uint2*>(dst);
+        ECB_UNROLL
+        for (int k = 0; k < N / 2; k++) q[k] = make_uint2(src[2 * k], src[2 * k + 1]);
+        return;
+    }
+#endif
+    ECB_UNROLL
+    for (int k = 0; k < N; k++) dst[k] = src[k];
+}
+
+// The ABI's element arrays are 4L-byte strings one after another.  When the element address is aligned for the widest access
+// its size allows (16 bytes for L % 4 == 0, 8 for even L, 4 otherwise - always true for the context's own staging buffers and
+// for cudaMalloc'd caller buffers) the string moves as 128 / 64 / 32-bit words + byte swaps instead of 4L byte accesses; the
+// test is uniform across a launch (same base, strides that are multiples of the element size).
+template <int L> ECB_DEV void load_be(u32* v, const u8* p) {
+#if defined(__CUDA_ARCH__) && !defined(ECB_EMU)
+    constexpr unsigned long long A = (L % 4 == 0) ? 15ull : (L % 2 == 0) ? 7ull : 3ull;
+    if ((reinterpret_cast<unsigned long long>(p) & A) == 0ull) {
+        u32 w[L];
+        ld_words<L>(w, reinterpret_cast<const u32*>(p));
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) v[i] = bswap32(w[L - 1 - i]);
+        return;
+    }
+#endif
+    load_be_bytes<L>(v, p);
+}
+template <int L> ECB_DEV void store_be(u8* p, const u32* v) {
+#if defined(__CUDA_ARCH__) && !defined(ECB_EMU)
+    constexpr unsigned long long A = (L % 4 == 0) ? 15ull : (L % 2 == 0) ? 7ull : 3ull;
+    if ((reinterpret_cast<unsigned long long>(p) & A) == 0ull) {
+        u32 w[L];
+        ECB_UNROLL
+        for (int i = 0; i < L; i++) w[i] = bswap32(v[L - 1 - i]);
+        st_words<L>(reinterpret_cast<u32*>(p), w);
+        return;
+    }
+#endif
+    store_be_bytes<L>(p, v);
 }
 
 }  // namespace ecb

@@ -238,9 +238,7 @@ template <class C> struct Jac {
             }
             if (mag) {
                 A g;
-                const u32* e = tab + (((size_t)w << (gw - 1)) + mag - 1) * 2 * L;
-                ECB_UNROLL
-                for (int l = 0; l < L; l++) { g.x.v[l] = e[l]; g.y.v[l] = e[L + l]; }
+                load_entry(g, tab + (((size_t)w << (gw - 1)) + mag - 1) * 2 * L);   // 128-bit gathers: every lane reads its own line
                 cneg_y(g, neg);
                 madd(acc, acc, g, nullptr);
             }

@@ -56,18 +56,10 @@ template <class C> struct Bodies {
     static constexpr int L = C::L;
     static constexpr int FB = C::FB;
 
-    ECB_DEV static void store_proj(u32* dst, const Proj& p) {
-        ECB_UNROLL
-        for (int i = 0; i < L; i++) { dst[i] = p.X.v[i]; dst[L + i] = p.Y.v[i]; dst[2 * L + i] = p.Z.v[i]; }
-    }
-    ECB_DEV static void load_proj_limbs(Proj& p, const u32* src) {
-        ECB_UNROLL
-        for (int i = 0; i < L; i++) { p.X.v[i] = src[i]; p.Y.v[i] = src[L + i]; p.Z.v[i] = src[2 * L + i]; }
-    }
-    ECB_DEV static void load_aff_limbs(Aff& a, const u32* src) {
-        ECB_UNROLL
-        for (int i = 0; i < L; i++) { a.x.v[i] = src[i]; a.y.v[i] = src[L + i]; }
-    }
+    // internal limb arrays: widest aligned access per coordinate (bigint.cuh ld_words / st_words)
+    ECB_DEV static void store_proj(u32* dst, const Proj& p) { st_words<L>(dst, p.X.v); st_words<L>(dst + L, p.Y.v); st_words<L>(dst + 2 * L, p.Z.v); }
+    ECB_DEV static void load_proj_limbs(Proj& p, const u32* src) { ld_words<L>(p.X.v, src); ld_words<L>(p.Y.v, src + L); ld_words<L>(p.Z.v, src + 2 * L); }
+    ECB_DEV static void load_aff_limbs(Aff& a, const u32* src) { ld_words<L>(a.x.v, src); ld_words<L>(a.y.v, src + L); }
 
     // ------------------------------------------------------------------ field test hook
     // which: 0 = base field, 1 = scalar field.  op: 0 add, 1 sub, 2 mul, 3 sqr, 4 neg, 5 inv (Fermat), 6 sqrt, 7 inv (divsteps)
@@ -171,8 +163,7 @@ template <class C> struct Bodies {
                 G::add(a, a, b);
                 store_proj(const_cast<u32*>(proj) + (size_t)i * 3 * L, a);
             }
-            ECB_UNROLL
-            for (int l = 0; l < L; l++) z.v[l] = proj[(size_t)i * 3 * L + 2 * L + l];
+            ld_words<L>(z.v, proj + (size_t)i * 3 * L + 2 * L);
             F::set_one(one);
             bool zz = F::is_zero(z);
             F::select(z, zz, one, z);
@@ -212,9 +203,9 @@ template <class C> struct Bodies {
                 }
                 if (out_inf) out_inf[i] = isinf ? 1 : 0;
             } else {
-                u32* o = out_limbs + (size_t)i * (mode == NORM_AFF_STRIDED ? (size_t)compress : (size_t)2 * L);
-                ECB_UNROLL
-                for (int l = 0; l < L; l++) { o[l] = isinf ? 0u : x.v[l]; o[L + l] = isinf ? 0u : y.v[l]; }
+                u32* o = out_limbs + (size_t)i * (mode == NORM_AFF_STRIDED ? (size_t)compress : (size_t)2 * L);   // stride: a multiple of 2L words
+                if (isinf) { F::set_zero(x); F::set_zero(y); }
+                st_words<L>(o, x.v); st_words<L>(o + L, y.v);
             }
         }
     }
@@ -463,7 +454,7 @@ template <class C> struct Bodies {
                 if (!valid) zero_n<L>(u1);
                 copy_n<L>(u2, ne.v);
             }
-            u32* o = scratch + (size_t)i * PREP_WORDS;
+            u32 o[PREP_WORDS];                    // the record is assembled in registers and leaves as 128-bit stores
             ECB_UNROLL
             for (int l = 0; l < L; l++) o[l] = u1[l];
             if constexpr (C::A_IS_ZERO) {
@@ -477,7 +468,10 @@ template <class C> struct Bodies {
                 ECB_UNROLL
                 for (int l = 0; l < L; l++) o[L + l] = u2[l];
                 o[2 * L] = valid ? 1u : 0u;
+                ECB_UNROLL
+                for (int l = 2 * L + 1; l < PREP_WORDS; l++) o[l] = 0;
             }
+            st_words<PREP_WORDS>(scratch + (size_t)i * PREP_WORDS, o);
         }
     }
 
@@ -551,15 +545,14 @@ template <class C> struct Bodies {
         const u32* rec = scratch + (size_t)tid * PREP_WORDS;
         typename JJ::A Q;
         bool valid;
-        u32 r[L];
-        load_be<L>(r, rs + (size_t)tid * 2 * FB);
         if (mode == VM_SCHNORR) {
             u32 x[L];
             load_be<L>(x, q + (size_t)tid * FB);
             valid = decompress(Q, x, 0u);             // lift_x: the even root (k256/src/schnorr/verifying.rs:35-45)
         } else if (mode == VM_RECOVER) {
             const u32 id = aux[tid];
-            u32 x[L], nn[L];
+            u32 x[L], nn[L], r[L];
+            load_be<L>(r, rs + (size_t)tid * 2 * FB);
             valid = id < 4u;
             copy_n<L>(x, r);
             if (id & 2u) {                            // x(R) was reduced: restore r + n, reject on overflow (>= p fails in decompress)
@@ -574,9 +567,6 @@ template <class C> struct Bodies {
             Q.x = Qa.x; Q.y = Qa.y;
         }
         if (!valid) { Aff g; G::generator(g); Q.x = g.x; Q.y = g.y; }
-        u32 u1[L];
-        ECB_UNROLL
-        for (int l = 0; l < L; l++) u1[l] = rec[l];
         typename JJ::J acc;
         if constexpr (C::A_IS_ZERO) {
             K256Glv::Split sp;
@@ -599,7 +589,12 @@ template <class C> struct Bodies {
             if (wtab && (mode == VM_ECDSA || mode == VM_SM2DSA)) JJ::mul_window_affine(acc, wtab + (size_t)tid * 16 * L, u2);
             else JJ::mul_window_signed(acc, Q, u2);
         }
+        // u1 and r are fetched only now: nothing of them stays live across the window loop
+        u32 u1[L], r[L];
+        ECB_UNROLL
+        for (int l = 0; l < L; l++) u1[l] = rec[l];
         JJ::add_fixed_base(acc, u1, gbig, gw);
+        if (mode == VM_ECDSA || mode == VM_SM2DSA) load_be<L>(r, rs + (size_t)tid * 2 * FB);
         if (mode == VM_ECDSA) {
             ok_out[tid] = finish_verify_jac(acc, r, valid) ? 1 : 0;
         } else if (mode == VM_SM2DSA) {
@@ -857,14 +852,8 @@ template <class C> struct Bodies {
             }
         }
     }
-    ECB_DEV static void store_fe(u32* dst, const E& a) {
-        ECB_UNROLL
-        for (int l = 0; l < L; l++) dst[l] = a.v[l];
-    }
-    ECB_DEV static void load_fe(E& a, const u32* src) {
-        ECB_UNROLL
-        for (int l = 0; l < L; l++) a.v[l] = src[l];
-    }
+    ECB_DEV static void store_fe(u32* dst, const E& a) { st_words<L>(dst, a.v); }
+    ECB_DEV static void load_fe(E& a, const u32* src) { ld_words<L>(a.v, src); }
     ECB_DEV static void store_entry(u32* dst, const E& x, const E& y) { store_fe(dst, x); store_fe(dst + L, y); }
 
 
@@ -882,14 +871,18 @@ template <class C> struct Bodies {
     // window width W (ECB_KT_W, bits): signed digits d_w in [-2^(W-1), 2^(W-1)) below the top window, which is unsigned and
     // absorbs the carry of the recoding; KT_E = 2^(W-1) entries per window.  Wider windows trade table construction (KT_E - 1
     // affine operations per window, once per key) for fewer additions per row: measured on the B200 at 2^22 rows / 2^16 keys, see DESIGN.md.
-    // Measured at 2^22 rows / 2^16 keys (profiles/r02_ab_keytab_window_width.txt): secp256k1 88.6 (W = 4) / 96.8 (5) / 94.1 (6)
-    // M verifies/s, P-256 83.2 / 83.8 / 75.0; at 2^20 rows (16 rows per key) P-384 15.6 / 13.9 / 10.4, SM2 45.1 / 38.6 / 29.2.
-    // secp256k1 recodes two 128-bit halves, so a wider window removes twice the additions per table entry added: it takes
-    // W = 5 (break-even at ~9 rows per key, the path needs 8); the other curves keep W = 4.  -DECB_KT_W=n forces one width.
+    // Measured at 2^22 rows / 2^16 keys (64 rows per key).  With the first k_kt_fill (32-bit accesses, 7.2 ms per 2^16 secp256k1
+    // keys; profiles/r02_ab_keytab_window_width.txt): secp256k1 88.6 (W = 4) / 96.8 (5) / 94.1 (6) M verifies/s, P-256 83.2 / 83.8 /
+    // 75.0; at 2^20 rows (16 rows per key) P-384 15.6 / 13.9 / 10.4, SM2 45.1 / 38.6 / 29.2.  With 128-bit accesses the fill costs a
+    // third (2.5 ms) and one more bit pays: secp256k1 111.9 (5) / 118.7 (6), P-256 97.0 (4) / 107.3 (5)
+    // (profiles/r02_ab_vector_access.txt).  secp256k1 recodes two 128-bit halves, so a wider window removes twice the additions per
+    // table entry added: W = 6 (22 windows of 32 entries per half, 45 KB per key; a table costs ~8 rows' worth of the per-row path,
+    // the policy in abi.cu asks for 8 rows per key); P-256 takes W = 5 (52 windows of 16 entries, 53 KB per key); P-384 / SM2 and the
+    // small curves keep W = 4 (their BASELINE-shaped case has 16 rows per key).  -DECB_KT_W=n forces one width for every curve.
 #ifdef ECB_KT_W
     static constexpr int KT_W = ECB_KT_W;
 #else
-    static constexpr int KT_W = C::A_IS_ZERO ? 5 : 4;
+    static constexpr int KT_W = C::A_IS_ZERO ? 6 : (C::ID == 1 ? 5 : 4);
 #endif
     static constexpr int KT_E = 1 << (KT_W - 1);                          // entries per window: multiples 1 .. 2^(W-1)
     static constexpr int KT_BITS = C::A_IS_ZERO ? 128 : 32 * L;           // bits of the recoded value: a GLV half / a full scalar
@@ -994,7 +987,7 @@ template <class C> struct Bodies {
     // per-thread scratch array.  No exceptional case can occur: B has prime order n > 16, so no operand pair is equal or
     // opposite and no y is zero.
 #ifndef ECB_KT_EPT
-#define ECB_KT_EPT 16
+#define ECB_KT_EPT 32
 #endif
     static constexpr int KT_EPT = ECB_KT_EPT;
     // operation k of round r (k < 2^r) makes entry v = 2^r + 1 + k: an even v is the double of v / 2 (made in round r - 1), an
@@ -1120,10 +1113,6 @@ template <class C> struct Bodies {
         const int g = gid[tid];
         bool valid = kvalid[g] != 0;
         const u32* tk = tab + (size_t)g * KT_KEY_WORDS;
-        u32 r[L], u1[L];
-        load_be<L>(r, rs + (size_t)tid * 2 * FB);
-        ECB_UNROLL
-        for (int l = 0; l < L; l++) u1[l] = rec[l];
         typename JJ::J acc;
         JJ::set_inf(acc);
         constexpr int NW = KT_BITS / 32;                    // words of the recoded value
@@ -1137,9 +1126,6 @@ template <class C> struct Bodies {
             kt_unbias16(k2, rec + 13);
             kt_recode(k1);
             kt_recode(k2);
-            E beta;
-            ECB_UNROLL
-            for (int l = 0; l < 8; l++) beta.v[l] = CurveK256::beta(l);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -1156,6 +1142,17 @@ template <class C> struct Bodies {
                 if (mag) {
                     typename JJ::A e;
                     JJ::load_entry(e, tk + ((size_t)w * KT_E + mag - 1) * 2 * L);
+                    // beta is rebuilt from immediates here (the empty volatile asm pins that): hoisted out of the loop it held
+                    // eight registers across every call of the window loop, which ptxas paid for in spills
+                    E beta;
+                    ECB_UNROLL
+                    for (int l = 0; l < 8; l++) {
+                        u32 c = CurveK256::beta(l);
+#if defined(__CUDA_ARCH__) && !defined(ECB_EMU)
+                        asm volatile("" : "+r"(c));
+#endif
+                        beta.v[l] = c;
+                    }
                     F::mul(e.x, e.x, beta);                 // lambda * (x, y) = (beta x, y)
                     JJ::cneg_y(e, neg ^ neg2);
                     JJ::madd(acc, acc, e, nullptr);
@@ -1182,7 +1179,12 @@ template <class C> struct Bodies {
                 }
             }
         }
+        // u1 and r are fetched only now: nothing of them stays live across the window loop
+        u32 r[L], u1[L];
+        ECB_UNROLL
+        for (int l = 0; l < L; l++) u1[l] = rec[l];
         JJ::add_fixed_base(acc, u1, gbig, gw);
+        load_be<L>(r, rs + (size_t)tid * 2 * FB);
         if (mode == VM_ECDSA) {
             ok_out[tid] = finish_verify_jac(acc, r, valid) ? 1 : 0;
         } else {                                           // VM_SM2DSA: target = (r - e) mod n, the identity counts as x = 0
@@ -1323,8 +1325,11 @@ template <class C> struct Bodies {
     // secret digit selects a source LANE of a register exchange, never a memory address or a branch; 4 LDS.128 + 16 SHFL per
     // window instead of 64 LDS.128 + 256 LOP3 for the masked scan.  Every lane of the warp must take part, so rows past the
     // end of the batch are clamped to the last row instead of returning early (their result is not stored).
+    // Measured (profiles/r02_ab_vector_access.txt): k*G at 2^16 scalars 0.579 -> 0.531 ms, 2^20 134.9 -> 149.8 M/s, signing 138.4 ->
+    // 153.7 M/s; the dynamic audit (scripts/ct_audit.sh on this build: instruction, branch, local / global sector and shared
+    // wavefront counters of five secret patterns) finds no launch that depends on the secrets.  -DECB_GEN2_SHFL=0 builds the scan.
 #ifndef ECB_GEN2_SHFL
-#define ECB_GEN2_SHFL 0
+#define ECB_GEN2_SHFL 1
 #endif
     template <bool CT> ECB_DEV static void body_gen_half(int tid, int n, int half, const u8* k, const u32* tabh, u32* part) {
 #if defined(__CUDA_ARCH__) && ECB_GEN2_SHFL

@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "launch.h"
 #include <atomic>
+#include <cstdlib>
 
 namespace ecb {
 
@@ -393,7 +394,8 @@ template <class C> struct Launch {
     }
     static void sum_normalize(cudaStream_t s, int n, u32* proj, const u32* sum_with, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
         if (n <= 0) return;
-        int ept = (n + 148 * 1 * BLK - 1) / (148 * 1 * BLK);
+        const int per = 148 * trick_ctas_per_sm() * BLK;
+        int ept = (n + per - 1) / per;
         if (ept < 1) ept = 1;
         if (ept > Bodies<C>::EPT) ept = Bodies<C>::EPT;
         int threads = (n + ept - 1) / ept;
@@ -405,13 +407,20 @@ template <class C> struct Launch {
         k_load_proj<C><<<grid(n), BLK, 0, s>>>(n, xyz, proj, invalid);
         count_launch();
     }
+    // resident CTAs per SM the Montgomery-trick kernels aim at when they pick the rows per thread (ECB200_TRICK_CTAS_PER_SM
+    // overrides, for measurements)
+    static int trick_ctas_per_sm() {
+        static const int v = [] { const char* e = getenv("ECB200_TRICK_CTAS_PER_SM"); const int x = e ? atoi(e) : 0; return x >= 1 && x <= 16 ? x : 1; }();
+        return v;
+    }
     static void normalize(cudaStream_t s, int n, const u32* proj, int mode, int compress, u8* out_bytes, u8* out_inf, u32* out_limbs) {
         if (n <= 0) return;
         // elements per thread: the kernel is one ~270-multiplication inversion chain per thread plus 5 multiplications per
         // element, so below ~2 warps per SM sub-partition it is latency-bound and more elements per thread are free:
         // aim at 1 CTA per SM, at most EPT (config 1 at 2^16, whole call: 0.944 ms with one element per thread, 0.890 ms at
         // 2 CTAs per SM, 0.865 ms at 1)
-        int ept = (n + 148 * 1 * BLK - 1) / (148 * 1 * BLK);
+        const int per = 148 * trick_ctas_per_sm() * BLK;
+        int ept = (n + per - 1) / per;
         if (ept < 1) ept = 1;
         if (ept > Bodies<C>::EPT) ept = Bodies<C>::EPT;
         int threads = (n + ept - 1) / ept;
@@ -478,7 +487,8 @@ template <class C> struct Launch {
         count_launch();
     }
     static int ept_threads(int n) {   // threads for the Montgomery-trick kernels: rows per thread that keep ~1 CTA per SM busy (latency-bound below that, see normalize)
-        int ept = (n + 148 * 1 * BLK - 1) / (148 * 1 * BLK);
+        const int per = 148 * trick_ctas_per_sm() * BLK;
+        int ept = (n + per - 1) / per;
         if (ept < 1) ept = 1;
         if (ept > Bodies<C>::PREP_EPT) ept = Bodies<C>::PREP_EPT;
         return (n + ept - 1) / ept;
@@ -536,7 +546,14 @@ template <class C> struct Launch {
             count_launch();
         }
         {
-            const int threads = (int)((items + B::KT_EPT - 1) / B::KT_EPT);
+            // items per thread: whole waves of resident CTAs with equal shares (2^16 secp256k1 keys = 1.7 M items: one wave
+            // of 23 items per thread instead of 1.4 waves of 16), at most KT_EPT
+            const long wave = 148L * ktf_min_ctas<C>() * BLK;
+            const long waves = (items + wave * B::KT_EPT - 1) / (wave * B::KT_EPT);
+            long ept = (items + waves * wave - 1) / (waves * wave);
+            if (ept < 1) ept = 1;
+            if (ept > B::KT_EPT) ept = B::KT_EPT;
+            const int threads = (int)((items + ept - 1) / ept);
             k_kt_fill<C><<<grid(threads), BLK, 0, s>>>((int)items, t0);
             count_launch();
         }

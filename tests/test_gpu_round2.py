@@ -429,3 +429,73 @@ def test_keytab_wycheproof_and_crafted_rows_tiled(eng, golden):
 def ecb_bits2field(cname, digest):
     import ecb200
     return ecb200.bits2field(cname, digest)
+
+
+@pytest.mark.parametrize("cname", CUR)
+@pytest.mark.parametrize("shift", [1, 4, 8])
+def test_device_pointers_of_any_alignment(eng, cname, shift):
+    """The kernels move the ABI's byte strings as 128 / 64 / 32-bit words when the element address allows it and byte by byte
+    otherwise (bigint.cuh load_be / store_be).  Every `_dev` entry point must give the same bytes for caller buffers at any
+    offset from a cudaMalloc'd base: the same batch runs from 256-byte aligned tensors and from views shifted by 1, 4 and 8
+    bytes (inputs AND outputs), through fixed-base, variable-base (CT and public), normalisation, signing and verification."""
+    import torch
+    import ecb200
+    c = o.curve(cname)
+    fb = c.fb
+    n = 300
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(500 + c.cid)
+
+    def scal(m):
+        a = rng.integers(0, 256, size=(m, fb), dtype=np.uint8)
+        a[:, 0] &= 0x3F
+        a[:, -1] |= 1
+        return a
+
+    def put(a, sh):          # device copy of `a` starting `sh` bytes into a fresh allocation
+        a = np.ascontiguousarray(a).reshape(-1)
+        t = torch.zeros(a.size + 64, dtype=torch.uint8, device=dev)
+        v = t[sh:sh + a.size]
+        v.copy_(torch.from_numpy(a).to(dev))
+        return v
+
+    def room(size, sh):
+        return torch.zeros(size + 64, dtype=torch.uint8, device=dev)[sh:sh + size]
+
+    k, d, z, k2 = scal(n), scal(n), scal(n), scal(n)
+    slot = 1 + 2 * fb
+    res = {}
+    for sh in (0, shift):
+        r = {}
+        # fixed base, CT, uncompressed slots
+        out = room(n * slot, sh)
+        eng.mul_gen_dev(cname, n, put(d, sh), out, ecb200.FLAG_CT | ecb200.FLAG_UNCOMPRESSED)
+        torch.cuda.synchronize()
+        r["gen"] = out.cpu().numpy().tobytes()
+        pts = np.frombuffer(r["gen"], np.uint8).reshape(n, slot)[:, 1:]
+        # variable base, public and secret scalars, compressed slots
+        for ct in (0, ecb200.FLAG_CT):
+            o2 = room(n * (1 + fb), sh)
+            inv = room(n, sh)
+            eng.mul_var_dev(cname, n, put(pts, sh), None, put(k2, sh), o2, inv, ct | ecb200.FLAG_COMPRESSED)
+            torch.cuda.synchronize()
+            r["var%d" % ct] = o2.cpu().numpy().tobytes() + inv.cpu().numpy().tobytes()
+        # sign, then verify (valid rows and rows with a flipped message byte)
+        rs, rid, ok = room(n * 2 * fb, sh), room(n, sh), room(n, sh)
+        eng.ecdsa_sign_dev(cname, n, put(d, sh), put(k, sh), put(z, sh), rs, rid, ok)
+        torch.cuda.synchronize()
+        r["sign"] = rs.cpu().numpy().tobytes() + rid.cpu().numpy().tobytes() + ok.cpu().numpy().tobytes()
+        zz = z.copy()
+        zz[::3, fb - 1] ^= 1
+        acc = room(n, sh)
+        eng.ecdsa_verify_dev(cname, n, put(pts, sh), put(zz, sh), put(np.frombuffer(r["sign"][:n * 2 * fb], np.uint8), sh), acc)
+        torch.cuda.synchronize()
+        r["verify"] = acc.cpu().numpy().tobytes()
+        res[sh] = r
+    assert res[0] == res[shift]
+    v = np.frombuffer(res[0]["verify"], np.uint8)
+    assert v[1::3].all() and v[2::3].all() and not v[::3].any()
+    # and the aligned run is right: first rows against the oracle
+    for i in range(4):
+        di = int.from_bytes(d[i].tobytes(), "big")
+        assert res[0]["gen"][i * slot:(i + 1) * slot] == o.slot_encode(c, o.mul_gen(c, di), False)

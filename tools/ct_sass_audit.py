@@ -33,6 +33,7 @@ KERNELS = [r"k_mul_varINS_\w+ELb1E", r"k_mul_gen_smemINS_\w+ELb1E", r"k_sign_fin
 ALLOW = [
     (r"if \(tid >= n\) return", "row guard (public batch size)"),
     (r"if \(i >= n\) break", "row guard inside the rows-per-thread loop (public batch size)"),
+    (r"if \(!live\) return", "row guard of the shuffle-fetch kernel (public batch size; rows past the end are clamped, computed and not stored)"),
     (r"\bfor \(", "loop over a public counter"),
     (r"flags & F_PROJ", "public flag: projective vs affine input"),
     (r"inf && inf\[tid\]", "public identity flag of the input point"),
@@ -58,6 +59,9 @@ ALLOW = [
     (r"e\.v\[i - 1\] = \(int\)ce & M30; ce >>= 30;|g\.v\[i - 1\] = \(int\)cg & M30; cg >>= 30;|g >>= 1; u <<= 1; v <<= 1;",
      "back edge of a fixed-trip-count limb / divstep loop of safegcd.cuh (public counter; ptxas keeps the 13-limb loop rolled)"),
 ]
+
+
+ADDRESS_ALIGNMENT = r"reinterpret_cast<unsigned long long>\(p\) & A\) == 0ull"
 
 
 def sh(cmd, **kw):
@@ -150,6 +154,16 @@ def audit_kernel(name, body):
                 if path:
                     sl = src_line(path, int(m.group(2)))
                     why = next((w + " (uniform predicate, set at %s:%s)" % (m.group(1), m.group(2)) for pat, w in ALLOW if re.search(pat, sl)), None)
+        if why is None and c["setter"]:
+            # the alignment dispatch of load_be / store_be: the predicate is an AND of the element address (buffer base + row
+            # index, public) with a constant; nvdisasm attributes the branch to the closing brace of the if, so it is judged
+            # by the line that set the predicate
+            m = re.search(r"\[([\w.]+):(\d+)\]$", c["setter"])
+            path = m and next((p for p in _src_cache if os.path.basename(p) == m.group(1)), None)
+            if path and re.search(ADDRESS_ALIGNMENT, src_line(path, int(m.group(2)))) and re.search(r"LOP3\.LUT P\d, RZ, R\d+, 0x[37f],", c["setter"]):
+                why = "alignment of a buffer ADDRESS (base pointer + row index, public): word or byte path of load_be / store_be (set at %s:%s)" % (m.group(1), m.group(2))
+        if why is None and "SYNCS.PHASECHK" in c["setter"]:
+            why = "mbarrier try_wait of the TMA table copy (nvdisasm attributes the back edge to the statement that follows the wait loop)"
         (allowed if why else findings).append(dict(c, why=why))
     return len(ins), findings, allowed
 
