@@ -288,7 +288,7 @@ def config_block(args, n_gpus, bounded=None):
     case = CASES[(args.op, args.curve)]
     lg = args.log2_rows or case["log2"]
     rows = 1 << lg
-    what = {"verify": "%s ECDSA verify_prehash (2^16 distinct keys, 1/16 rows corrupted)", "mul_var": "%s variable-base P*k + normalisation to SEC1",
+    what = {"verify": "%s ECDSA verify_prehash (" + ("every key distinct" if getattr(args, "distinct_keys", False) else "2^16 distinct keys") + ", 1/16 rows corrupted)", "mul_var": "%s variable-base P*k + normalisation to SEC1",
             "mul_gen": "%s fixed-base G*k, constant-time path, SEC1 output"}[args.op] % args.curve
     strong = args.scaling == "strong"
     fb = FB[args.curve]
@@ -378,12 +378,19 @@ class Work:
             self.pin_out_t = torch.empty(self.n * self.out_bytes, dtype=torch.uint8).pin_memory()
             self.pin_out = self.pin_out_t.numpy()
 
-    def host(self):
-        """the call a user makes: host pointers in, results in a host buffer when it returns"""
+    def host(self, pageable=False):
+        """the call a user makes: host pointers in, results in a host buffer when it returns (pageable: ordinary malloc'd
+        buffers, which the library stages through its pinned double buffers, instead of page-locked ones)"""
         self.pin()
         lib, h, cid, n = self.eng.lib, self.eng.h, self.pkg.curve_id(self.curve), self.n
-        p = [ctypes.c_void_p(a.ctypes.data) for a in self.pin_in]
-        o = ctypes.c_void_p(self.pin_out.ctypes.data)
+        if pageable:
+            if getattr(self, "page_out", None) is None:
+                self.page_out = np.empty(self.n * self.out_bytes, dtype=np.uint8)
+            p = [ctypes.c_void_p(a.ctypes.data) for a in self.host_in]
+            o = ctypes.c_void_p(self.page_out.ctypes.data)
+        else:
+            p = [ctypes.c_void_p(a.ctypes.data) for a in self.pin_in]
+            o = ctypes.c_void_p(self.pin_out.ctypes.data)
         if self.op == "verify":
             rc = lib.ecb200_ecdsa_verify(h, cid, n, p[0], p[1], p[2], o)
         elif self.op == "mul_gen":
@@ -426,6 +433,7 @@ def main():
     ap.add_argument("--ct", action="store_true", help="mul_var: the secret-scalar (constant-time) kernels instead of the public-input path")
     ap.add_argument("--log2-rows", type=int, default=0, help="rows per GPU (weak) or in the global batch (strong); default = the BASELINE config's size")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: every rank processes its own 2^L rows; strong: ONE 2^L-row batch, each rank takes shard_range(rank)")
+    ap.add_argument("--distinct-keys", action="store_true", help="verify: every row its own public key (per-row path) instead of SURVEY 8d's 2^16 keys reused round-robin")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -458,9 +466,9 @@ def main():
     # ---- inputs (synthetic, generated by the engine; not timed).  strong: the same global batch on every rank, own shard only
     if args.scaling == "strong":
         lo, hi = pkg.shard_range(rows, rank, world)
-        w = Work(pkg, eng, dev, st, op, curve, rows, case["seed"], lo, hi, ct=args.ct)
+        w = Work(pkg, eng, dev, st, op, curve, rows, case["seed"], lo, hi, ct=args.ct, n_keys=(rows if args.distinct_keys else None))
     else:
-        w = Work(pkg, eng, dev, st, op, curve, rows, case["seed"] + 1000 * rank, ct=args.ct)
+        w = Work(pkg, eng, dev, st, op, curve, rows, case["seed"] + 1000 * rank, ct=args.ct, n_keys=(rows if args.distinct_keys else None))
     n = w.n
     n_global = rows if args.scaling == "strong" else rows * world
 
@@ -520,6 +528,15 @@ def main():
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_global * steps / dt
+    # the same call with pageable (ordinary) host buffers: staged through the context's pinned double buffers
+    w.host(pageable=True)
+    assert np.array_equal(w.page_out, w.pin_out), "pageable and page-locked host calls disagree"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, steps // 2)):
+        w.host(pageable=True)
+    torch.cuda.synchronize()
+    e2e_pageable = n_global * max(1, steps // 2) / max_over_ranks(time.perf_counter() - t0)
 
     io = IO_BYTES["mul_var_proj" if (op == "mul_var" and w.projective) else op](w.fb, getattr(w, "slot", 1))
     out = {
@@ -528,7 +545,7 @@ def main():
         "scaling": args.scaling, "vs_baseline": None, "dtype": "u32 limbs (%dx32, IMAD.WIDE carry chains)" % (w.fb // 4), "data": "synthetic",
         "config": config_block(args, world), "clocks": clocks, "gpu_launches": int(launches), "output_check": chk,
         "e2e": {"value": round(e2e_value, 1), "unit": case["unit"], "h2d_bytes_per_step": int(w.h2d), "d2h_bytes_per_step": int(w.d2h),
-                "ms_per_step": round(dt / steps * 1e3, 3),
+                "ms_per_step": round(dt / steps * 1e3, 3), "pageable_buffers_value": round(e2e_pageable, 1),
                 "api": "ecb200_%s (host pointers to page-locked buffers; chunked H2D / compute / D2H overlap inside the call)" % {"verify": "ecdsa_verify", "mul_var": "mul_var", "mul_gen": "mul_gen"}[op]},
         "roofline": roofline(op, curve, n, ms_step, clocks.get("sm_mhz"), kernel_ms, ct=args.ct, io=io, rowpath=(kt1[0] == kt0[0])),
     }
@@ -536,7 +553,7 @@ def main():
         on_tables = (kt1[0] - kt0[0]) // steps
         out["verify_path"] = {"rows_per_step_on_per_key_tables": int(on_tables), "tables_built_per_step": int((kt1[1] - kt0[1]) // steps),
                               "note": "rows are grouped by public key inside every call; the 2^16 keys of this workload repeat 64 times, so each key's "
-                                      "multiples 16^w*Q are computed once per call (inside the timed region, nothing is cached between calls) and a row "
+                                      "window multiples v*2^(W w)*Q (W = 6 bits on secp256k1, 5 on P-256, 4 elsewhere) are computed once per call (inside the timed region, nothing is cached between calls) and a row "
                                       "costs additions only.  With all keys distinct the per-row path runs: see others[] '3b'" if on_tables else
                                       "per-row path (keys do not repeat enough for per-key tables)"}
         if on_tables:

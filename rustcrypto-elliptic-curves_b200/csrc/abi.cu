@@ -95,7 +95,7 @@ struct ecb200_ctx {
     uint32_t* gentab2[NCURVE] = {};               // fixed-base window tables of the split path (k_gen_half)
     bool use_gen2 = true;                    // ECB200_GEN2=0: one thread per scalar, complete additions (A/B comparisons)
     uint32_t* gbig[NCURVE] = {};                  // big fixed-base tables of the public-input fast path (built on first use)
-    int gw = 16;                             // window width of gbig (ECB200_GW = 4, 8 or 16)
+    int gw = 0;                              // window width of gbig forced by ECB200_GW (2 .. 24 bits); 0 = the per-curve default, gw_of()
     bool verify_v1 = false;                  // ECB200_VERIFY_V1=1: complete-formula verify kernel (A/B comparisons)
     bool use_wintab = true;                  // ECB200_WINTAB=0: per-thread Jacobian window tables on the primeorder curves (A/B comparisons)
     DevBuf prep, aff;                        // verify_prep scratch; affine limbs of normalised projective inputs
@@ -113,8 +113,10 @@ struct ecb200_ctx {
         size_t cap = 0, alloc_groups = 0, total_rows = 0;
         uint32_t hmask = 0;
         int built = 0;
+        int wide = 1;                        // table width of this call: 1 = the curve's default, 0 = the narrow one (few rows per key)
         bool active = false, disabled = true, first = true;
     } kt;
+    int kt_force_wide = -1;                  // ECB200_KT_WIDE = 0 / 1 forces the width (tests, A/B); -1 = by rows per key
     bool use_keytab = true;                  // ECB200_KEYTAB=0: always the per-row path (A/B comparisons, tests of both paths)
     uint64_t kt_rows = 0, kt_groups = 0;     // statistics: rows verified on per-key tables / tables built (ecb200_keytab_stats)
     std::string err;
@@ -275,11 +277,17 @@ cudaStream_t pick(ecb200_ctx* c, void* stream) { return stream ? (cudaStream_t)s
 // v up to 2^gw (v = 2^gw is 2^(8 FB) * G).  Affine internal limbs (34 MiB for a 256-bit curve at gw = 16; it lives in
 // HBM/L2 and is gathered 64-96 B at a time).
 // Built on first use with the engine's own kernels: scalar v << (gw*w), point G, Jacobian fast path, normalise.
+// Window width of the table.  Measured on the B200 at 2^22 rows / 2^16 keys (profiles/r02_ab_fixed_base_width.txt), M verifies/s at
+// gw = 16 / 18 / 20 / 22: secp256k1 118.5 / 120.1 / 123.4 / 124.6, P-256 107.0 / 108.3 / 110.9 / 112.2, per-row secp256k1 53.8 /
+// 54.1 / 54.7 / 55.1, P-384 (2^20 rows) 21.2 / 21.4 / 21.6 / 21.8.  The 256-bit and smaller curves take 20 bits (13 additions
+// instead of 16 for 410 MB of HBM per curve, built in ~0.15 s on first use; 22 bits would buy one more addition for 1.5 GB);
+// P-384 keeps 16 (78 MiB; 20 bits would cost 956 MB for +2 %).
+int gw_of(const ecb200_ctx* c, const CurveLaunch* cl) { return c->gw ? c->gw : (cl->FB > 32 ? 16 : 20); }
 int ensure_gbig(ecb200_ctx* c, const CurveLaunch* cl) {
     if (c->gbig[cl->id]) return 0;
-    const int FB = cl->FB, L = cl->L, gw = c->gw;
-    const int nwin = (8 * FB) / gw;
-    const size_t per = (size_t)1 << (gw - 1), top_base = (size_t)(nwin - 1) * per, ne = top_base + 2 * per;
+    const int FB = cl->FB, L = cl->L, gw = gw_of(c, cl);
+    const int nwin = (8 * FB + gw - 1) / gw, tb = 8 * FB - gw * (nwin - 1);      // windows; bits of the (unsigned) top window
+    const size_t per = (size_t)1 << (gw - 1), top_base = (size_t)(nwin - 1) * per, ne = top_base + ((size_t)1 << tb);
     std::vector<uint8_t> gxy(2 * FB);
     hex_to(gxy.data(), GX[cl->id], FB);
     hex_to(gxy.data() + FB, GY[cl->id], FB);
@@ -300,7 +308,7 @@ int ensure_gbig(ecb200_ctx* c, const CurveLaunch* cl) {
         for (size_t e = 0; e < cnt; e++) {
             size_t idx = off + e;
             uint8_t* s = &sc[e * FB];
-            if (idx == ne - 1) { memcpy(s, cl->r_mod_n, FB); continue; }   // v = 2^gw in the top window: 2^(8 FB) mod n
+            if (idx == ne - 1) { memcpy(s, cl->r_mod_n, FB); continue; }   // v = 2^tb in the top window: 2^(8 FB) mod n
             size_t w = idx < top_base ? idx >> (gw - 1) : (size_t)(nwin - 1), v = idx - w * per + 1;
             int bit = (int)w * gw;
             for (int b = 0; b < gw; b++)
@@ -419,7 +427,10 @@ enum { VM_ECDSA = 0, VM_SM2DSA = 1, VM_SCHNORR = 2, VM_RECOVER = 3, DEC_SEC1 = 0
 // (KT_MIN_ROWS); tables are used while the call shows at least KT_MIN_REUSE rows per distinct key (a table costs ~2.6
 // verifications, saves ~0.5 per row) and the distinct keys fit the table memory; the first chunk of a multi-chunk host call
 // must already show two rows per key, so a call with all-distinct keys pays only the grouping kernels (~0.4 % of a step).
-constexpr size_t KT_MIN_ROWS = 4096, KT_MIN_REUSE = 8;
+// Table width: the curve's wide default (6 bits on secp256k1, 5 on P-256) when the call has at least KT_WIDE_REUSE rows per
+// distinct key, else 4 bits - a table is paid per key, its additions per row (kernels.cuh).  Decided once per call, on the
+// first chunk: total rows of the call / distinct keys seen so far.
+constexpr size_t KT_MIN_ROWS = 4096, KT_MIN_REUSE = 8, KT_WIDE_REUSE = 32;
 constexpr size_t KT_MEM_CAP = (size_t)12 << 30;      // bytes of tables per context (180 GB of HBM per GPU)
 
 int kt_begin(ecb200_ctx* c, const CurveLaunch* cl, size_t total_rows, size_t max_chunk, cudaStream_t s) {
@@ -430,7 +441,7 @@ int kt_begin(ecb200_ctx* c, const CurveLaunch* cl, size_t total_rows, size_t max
     k.total_rows = total_rows;
     k.disabled = !c->use_keytab || c->verify_v1 || total_rows < KT_MIN_ROWS || total_rows >= ((size_t)1 << 30);
     if (k.disabled) return 0;
-    const size_t key_bytes = (size_t)cl->kt_key_words * 4;
+    const size_t key_bytes = (size_t)std::max(cl->kt_key_words[0], cl->kt_key_words[1]) * 4;
     k.cap = std::min(total_rows / KT_MIN_REUSE, KT_MEM_CAP / key_bytes);
     if (k.cap < 1) { k.disabled = true; return 0; }
     size_t hs = 1024;
@@ -446,7 +457,9 @@ int kt_begin(ecb200_ctx* c, const CurveLaunch* cl, size_t total_rows, size_t max
 }
 void kt_end(ecb200_ctx* c) { c->kt.active = false; c->kt.disabled = true; }
 
-// groups the n rows of a chunk by key, decides, and builds the tables of the keys first seen in this chunk; *use = verify on tables
+// groups the n rows of a chunk by key, decides, and builds the tables of the keys first seen in this chunk; *use = verify on tables.
+// (Measured and not kept: the chunk's verify_prep on a side stream next to the table construction - the step stayed at 34.0 ms,
+// k_kt_fill keeps the multiplier pipe 60 % busy on its own.)
 int kt_chunk(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q, cudaStream_t s, bool* use) {
     ecb200_ctx::KeyTab& k = c->kt;
     *use = false;
@@ -465,8 +478,9 @@ int kt_chunk(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q,
         k.disabled = true;                // little reuse (or more keys than tables): this chunk and the rest of the call take the per-row path
         return 0;
     }
+    if (first) k.wide = c->kt_force_wide >= 0 ? c->kt_force_wide : ((size_t)D * KT_WIDE_REUSE <= k.total_rows ? 1 : 0);
     if (D > k.built) {
-        const size_t kw = (size_t)cl->kt_key_words;
+        const size_t kw = (size_t)cl->kt_key_words[k.wide];
         if ((size_t)D > k.alloc_groups) {  // grow the table store (position independent: old tables are copied over)
             size_t want = std::min(k.cap, std::max<size_t>((size_t)2 * D, 65536));
             DevBuf bigger;
@@ -478,8 +492,9 @@ int kt_chunk(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q,
             k.alloc_groups = want;
         }
         const int cnt = D - k.built;
-        CU(c, k.jac.reserve((size_t)cnt * cl->kt_windows * 3 * cl->L * 4));
-        cl->kt_build(s, k.built, cnt, (const uint32_t*)k.gkeys.p, (uint32_t*)k.jac.p, (uint8_t*)k.kvalid.p, (uint32_t*)k.tab.p);
+        CU(c, k.jac.reserve((size_t)cnt * cl->kt_windows[k.wide] * 3 * cl->L * 4));
+        cl->kt_build(s, k.wide, k.built, cnt, (const uint32_t*)k.gkeys.p, (uint32_t*)k.jac.p, (uint8_t*)k.kvalid.p, (uint32_t*)k.tab.p);
+
         c->kt_groups += (uint64_t)cnt;
         k.built = D;
     }
@@ -503,8 +518,8 @@ int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d
                 cl->verify_prep(s, (int)n, mode, d_z, d_rs, (uint32_t*)c->prep.p);
                 {
                     TimedLaunch t(c, s);
-                    cl->verify_keytab(s, (int)n, mode, d_rs, d_z, (const uint32_t*)c->prep.p, (const int*)c->kt.gid.p, (const uint8_t*)c->kt.kvalid.p,
-                                      (const uint32_t*)c->kt.tab.p, c->gbig[cl->id], c->gw, d_ok);
+                    cl->verify_keytab(s, c->kt.wide, (int)n, mode, d_rs, d_z, (const uint32_t*)c->prep.p, (const int*)c->kt.gid.p, (const uint8_t*)c->kt.kvalid.p,
+                                      (const uint32_t*)c->kt.tab.p, c->gbig[cl->id], gw_of(c, cl), d_ok);
                 }
                 c->kt_rows += n;
                 CU(c, cudaGetLastError());
@@ -516,7 +531,7 @@ int verify_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d
         r = window_tables(c, cl, n, d_q, nullptr, s, &wt);
         if (r) return r;
         TimedLaunch t(c, s);
-        cl->verify_main(s, (int)n, mode, d_q, d_rs, d_z, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, nullptr, wt);
+        cl->verify_main(s, (int)n, mode, d_q, d_rs, d_z, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], gw_of(c, cl), d_ok, nullptr, wt);
     }
     CU(c, cudaGetLastError());
     return 0;
@@ -545,7 +560,7 @@ int schnorr_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* 
     CU(c, c->kxy.reserve(n * 2 * (size_t)cl->FB));
     CU(c, c->kst.reserve(n));
     cl->verify_prep(s, (int)n, VM_SCHNORR, d_e, d_sig, (uint32_t*)c->prep.p);
-    cl->verify_main(s, (int)n, VM_SCHNORR, d_pk, d_sig, d_e, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, (uint32_t*)c->proj.p, nullptr);
+    cl->verify_main(s, (int)n, VM_SCHNORR, d_pk, d_sig, d_e, nullptr, (const uint32_t*)c->prep.p, c->gbig[cl->id], gw_of(c, cl), d_ok, (uint32_t*)c->proj.p, nullptr);
     cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 1 /*NORM_XY_BYTES*/, 0, (uint8_t*)c->kxy.p, (uint8_t*)c->kst.p, nullptr);
     cl->finish(s, (int)n, FIN_SCHNORR, (const uint8_t*)c->kxy.p, 0, (const uint8_t*)c->kst.p, d_sig, d_ok);
     CU(c, cudaGetLastError());
@@ -559,7 +574,7 @@ int recover_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* 
     CU(c, c->prep.reserve(n * (size_t)cl->prep_words * 4));
     CU(c, c->proj.reserve(n * 3 * (size_t)cl->L * 4));
     cl->verify_prep(s, (int)n, VM_RECOVER, d_z, d_rs, (uint32_t*)c->prep.p);
-    cl->verify_main(s, (int)n, VM_RECOVER, nullptr, d_rs, d_z, d_recid, (const uint32_t*)c->prep.p, c->gbig[cl->id], c->gw, d_ok, (uint32_t*)c->proj.p, nullptr);
+    cl->verify_main(s, (int)n, VM_RECOVER, nullptr, d_rs, d_z, d_recid, (const uint32_t*)c->prep.p, c->gbig[cl->id], gw_of(c, cl), d_ok, (uint32_t*)c->proj.p, nullptr);
     cl->normalize(s, (int)n, (const uint32_t*)c->proj.p, 0, resolve_compress(cl, flags) ? 1 : 0, d_keys, nullptr, nullptr);
     cl->finish(s, (int)n, FIN_RECOVER, d_keys, (int)slot_bytes(cl, flags), nullptr, nullptr, d_ok);
     CU(c, cudaGetLastError());
@@ -781,11 +796,12 @@ int ecb200_init(int device, ecb200_ctx** out) {
         ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
-    if (const char* e = getenv("ECB200_GW")) { int g = atoi(e); if (g == 4 || g == 8 || g == 16) c->gw = g; }
+    if (const char* e = getenv("ECB200_GW")) { int g = atoi(e); if (g >= 2 && g <= 24) c->gw = g; }
     if (const char* e = getenv("ECB200_VERIFY_V1")) c->verify_v1 = atoi(e) != 0;
     if (const char* e = getenv("ECB200_WINTAB")) c->use_wintab = atoi(e) != 0;
     if (const char* e = getenv("ECB200_GEN2")) c->use_gen2 = atoi(e) != 0;
     if (const char* e = getenv("ECB200_KEYTAB")) c->use_keytab = atoi(e) != 0;
+    if (const char* e = getenv("ECB200_KT_WIDE")) c->kt_force_wide = atoi(e) != 0 ? 1 : 0;
     if (!ok || build_tables(c) != 0) {
         fprintf(stderr, "ecb200_init failed: %s (%s)\n", c->err.c_str(), cudaGetErrorString(cudaGetLastError()));
         ecb200_destroy(c);

@@ -205,34 +205,39 @@ template <class C> struct Jac {
         F::cmov(a.y, ny, mask);
     }
 
-    // ---- u1 * G from the big fixed-base table (gw-bit windows, gw divides 32).  All windows but the top one are
+    // ---- u1 * G from the big fixed-base table: nwin = ceil(32L / gw) windows of gw bits (any 2 <= gw <= 24; windows may
+    // straddle words), the top one holds the tb = 32L - gw (nwin - 1) bits that are left.  All windows but the top one are
     // SIGNED: with the bias 2^(gw-1) added to each of them, window w holds d_w + 2^(gw-1), d_w in [-2^(gw-1), 2^(gw-1));
-    // the top window absorbs the carry and stays unsigned, v in [0, 2^gw] (so no extra addition for a carry window).
+    // the top window absorbs the carry and stays unsigned, v in [0, 2^tb] (so no extra addition for a carry window).
     //   tab[(w << (gw-1)) + v - 1]        = v * 2^(gw*w) * G, 1 <= v <= 2^(gw-1), w < nwin-1   (negative digits negate y)
-    //   tab[((nwin-1) << (gw-1)) + v - 1] = v * 2^(gw*(nwin-1)) * G, 1 <= v <= 2^gw
-    // 34 MiB instead of the 64 MiB of an all-unsigned table for a 256-bit curve at gw = 16.
+    //   tab[((nwin-1) << (gw-1)) + v - 1] = v * 2^(gw*(nwin-1)) * G, 1 <= v <= 2^tb
+    // 34 MiB instead of the 64 MiB of an all-unsigned table for a 256-bit curve at gw = 16 (16 additions per row); the table is
+    // built once per context and curve, so wider windows trade HBM for additions: gw = 20 -> 13 additions, 410 MB; 22 -> 12, 1.5 GB.
     ECB_DEV static void add_fixed_base(J& acc, const u32* u1, const u32* tab, int gw) {
-        const int nwin = (32 * L) / gw;
-        const u32 half = 1u << (gw - 1);
-        u32 bias = 0;
-        for (int b = gw - 1; b < 32; b += gw) bias |= 1u << b;
-        u32 kb[L + 1];
-        kb[0] = add_cc(u1[0], L == 1 ? (bias & 0x7FFFFFFFu) : bias);
+        const int nwin = (32 * L + gw - 1) / gw;
+        const int top_bit = gw * (nwin - 1);
+        u32 kb[L + 2];
         ECB_UNROLL
-        for (int i = 1; i < L; i++) kb[i] = addc_cc(u1[i], i == L - 1 ? (bias & 0x7FFFFFFFu) : bias);   // no bias on the top window
+        for (int i = 0; i < L + 2; i++) kb[i] = 0;
+        for (int b = gw - 1; b < top_bit; b += gw) kb[b >> 5] |= 1u << (b & 31);   // the bias, one bit per signed window
+        kb[0] = add_cc(u1[0], kb[0]);
+        ECB_UNROLL
+        for (int i = 1; i < L; i++) kb[i] = addc_cc(u1[i], kb[i]);
         kb[L] = addc(0u, 0u);
-        const u32 vmask = (gw == 32) ? 0xFFFFFFFFu : ((1u << gw) - 1u);
+        const u32 vmask = (1u << gw) - 1u;
+        const u32 half = 1u << (gw - 1);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
         for (int w = 0; w < nwin; w++) {
             const int bit = w * gw;
-            const u32 raw = (kb[bit >> 5] >> (bit & 31)) & vmask;
+            const u64 two = ((u64)kb[(bit >> 5) + 1] << 32) | kb[bit >> 5];
+            const u32 raw = (u32)(two >> (bit & 31));
             u32 mag, neg = 0;
             if (w == nwin - 1) {
-                mag = raw + (kb[L] << gw);                       // unsigned, up to 2^gw
+                mag = raw;                                       // unsigned: everything from top_bit up, carry included (<= 2^tb)
             } else {
-                const int d = (int)raw - (int)half;
+                const int d = (int)(raw & vmask) - (int)half;
                 neg = (u32)(d >> 31);
                 mag = (u32)((d ^ (int)neg) - (int)neg);
             }

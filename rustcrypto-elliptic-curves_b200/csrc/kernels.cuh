@@ -46,7 +46,9 @@ struct OwnInv {
     template <class FF> ECB_DEV static void run(typename FF::E& r, const typename FF::E& a) { FF::inv_trick(r, a); }
 };
 
-template <class C> struct Bodies {
+// KTW: window width of the per-key tables for THIS instantiation (0 = the curve's default width; the launchers instantiate the
+// three table kernels a second time with the narrow width, kernels_impl.cuh kt_narrow)
+template <class C, int KTW = 0> struct Bodies {
     typedef EC<C> G;
     typedef typename G::Proj Proj;
     typedef typename G::Aff Aff;
@@ -879,11 +881,15 @@ template <class C> struct Bodies {
     // table entry added: W = 6 (22 windows of 32 entries per half, 45 KB per key; a table costs ~8 rows' worth of the per-row path,
     // the policy in abi.cu asks for 8 rows per key); P-256 takes W = 5 (52 windows of 16 entries, 53 KB per key); P-384 / SM2 and the
     // small curves keep W = 4 (their BASELINE-shaped case has 16 rows per key).  -DECB_KT_W=n forces one width for every curve.
+    // The widths above are for calls with many rows per key; a table is paid per KEY, so calls with 8 .. 32 rows per key (the
+    // policy in abi.cu asks for 8) take the narrow width W = 4 instead: per 2^16 keys the secp256k1 fill costs ~1.3 / 2.5 / 5.0 ms at
+    // W = 4 / 5 / 6 and the additions of 2^22 rows ~36 / 32 / 29 ms, so the widths cross at ~32 rows per key.
 #ifdef ECB_KT_W
-    static constexpr int KT_W = ECB_KT_W;
+    static constexpr int KT_W_DEFAULT = ECB_KT_W;
 #else
-    static constexpr int KT_W = C::A_IS_ZERO ? 6 : (C::ID == 1 ? 5 : 4);
+    static constexpr int KT_W_DEFAULT = C::A_IS_ZERO ? 6 : (C::ID == 1 ? 5 : 4);
 #endif
+    static constexpr int KT_W = KTW ? KTW : KT_W_DEFAULT;
     static constexpr int KT_E = 1 << (KT_W - 1);                          // entries per window: multiples 1 .. 2^(W-1)
     static constexpr int KT_BITS = C::A_IS_ZERO ? 128 : 32 * L;           // bits of the recoded value: a GLV half / a full scalar
     static constexpr int KT_WINDOWS = KT_BITS / KT_W + 1;                 // signed windows below bit W*floor(bits/W), then the top window

@@ -204,25 +204,29 @@ template <class C> __global__ void __launch_bounds__(256) k_kt_number(int n, con
 template <class C> __global__ void __launch_bounds__(256) k_kt_assign(int n, int* gid, const int* rep, const int* newgid) {
     Bodies<C>::body_kt_assign(blockIdx.x * 256 + threadIdx.x, n, gid, rep, newgid);
 }
-template <class C> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_kt_base(int g0, int cnt, const u32* gkeys, u32* proj, u8* kvalid) {
-    Bodies<C>::body_kt_base(blockIdx.x * BLK + threadIdx.x, g0, cnt, gkeys, proj, kvalid);
+// W: window width of the tables (0 = the curve's default, else the narrow width - see kt_narrow below)
+template <class C, int W = 0> __global__ void __launch_bounds__(BLK, fast_min_ctas<C>()) k_kt_base(int g0, int cnt, const u32* gkeys, u32* proj, u8* kvalid) {
+    Bodies<C, W>::body_kt_base(blockIdx.x * BLK + threadIdx.x, g0, cnt, gkeys, proj, kvalid);
 }
 #ifndef ECB_KTF_MIN_CTAS
 #define ECB_KTF_MIN_CTAS ECB_WT_MIN_CTAS
 #endif
 template <class C> constexpr int ktf_min_ctas() { return C::L > 8 ? 3 : ECB_KTF_MIN_CTAS; }
-template <class C> __global__ void __launch_bounds__(BLK, ktf_min_ctas<C>()) k_kt_fill(int items, u32* tab) {
-    Bodies<typename CtCurve<C>::type>::template body_kt_fill<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, items, tab);
+template <class C, int W = 0> __global__ void __launch_bounds__(BLK, ktf_min_ctas<C>()) k_kt_fill(int items, u32* tab) {
+    Bodies<typename CtCurve<C>::type, W>::template body_kt_fill<TrickInv>(blockIdx.x * BLK + threadIdx.x, gridDim.x * BLK, items, tab);
 }
 // resident CTAs the table-path main kernel is compiled for (its own knob: no per-thread table, smaller frame than k_verify_main)
 #ifndef ECB_KT_MIN_CTAS
 #define ECB_KT_MIN_CTAS 0
 #endif
 template <class C> constexpr int kt_min_ctas() { return ECB_KT_MIN_CTAS ? ECB_KT_MIN_CTAS : fast_min_ctas<C>(); }
-template <class C, int MODE> __global__ void __launch_bounds__(BLK, kt_min_ctas<C>()) k_verify_keytab(int n, const u8* rs, const u8* z, const u32* scratch, const int* gid, const u8* kvalid,
-                                                                                                          const u32* tab, const u32* gbig, int gw, u8* ok) {
-    Bodies<C>::body_verify_keytab(blockIdx.x * BLK + threadIdx.x, n, MODE, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
+template <class C, int MODE, int W = 0> __global__ void __launch_bounds__(BLK, kt_min_ctas<C>()) k_verify_keytab(int n, const u8* rs, const u8* z, const u32* scratch, const int* gid, const u8* kvalid,
+                                                                                                                     const u32* tab, const u32* gbig, int gw, u8* ok) {
+    Bodies<C, W>::body_verify_keytab(blockIdx.x * BLK + threadIdx.x, n, MODE, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
 }
+// narrow table width of a curve (calls with few rows per key); equal to the default width where only one is built
+template <class C> constexpr int kt_narrow() { return Bodies<C>::KT_W_DEFAULT > 4 ? 4 : Bodies<C>::KT_W_DEFAULT; }
+template <class C> constexpr bool kt_two_widths() { return kt_narrow<C>() != Bodies<C>::KT_W_DEFAULT; }
 template <class C> __global__ void __launch_bounds__(BLK) k_decode(int n, int mode, const u8* enc, int stride, u8* xy, u8* status) {
     Bodies<typename CtCurve<C>::type>::body_decode(blockIdx.x * BLK + threadIdx.x, n, mode, enc, stride, xy, status);
 }
@@ -530,10 +534,17 @@ template <class C> struct Launch {
     }
     // tables of groups [g0, g0 + cnt): 16^w * Q (Jacobian chain), one normalisation of all base points straight into entry 0 of
     // every window, then seven rounds of batched affine additions
-    static void kt_build(cudaStream_t s, int g0, int cnt, const u32* gkeys, u32* proj_scratch, u8* kvalid, u32* tab) {
+    // wide = 1: the curve's default width, 0: the narrow one (kt_narrow; the same kernels where a curve has one width)
+    static void kt_build(cudaStream_t s, int wide, int g0, int cnt, const u32* gkeys, u32* proj_scratch, u8* kvalid, u32* tab) {
         if (cnt <= 0) return;
-        typedef Bodies<C> B;
-        k_kt_base<C><<<grid(cnt), BLK, 0, s>>>(g0, cnt, gkeys, proj_scratch, kvalid);
+        if constexpr (kt_two_widths<C>()) {
+            if (!wide) { kt_build_w<kt_narrow<C>()>(s, g0, cnt, gkeys, proj_scratch, kvalid, tab); return; }
+        }
+        kt_build_w<0>(s, g0, cnt, gkeys, proj_scratch, kvalid, tab);
+    }
+    template <int W> static void kt_build_w(cudaStream_t s, int g0, int cnt, const u32* gkeys, u32* proj_scratch, u8* kvalid, u32* tab) {
+        typedef Bodies<C, W> B;
+        k_kt_base<C, W><<<grid(cnt), BLK, 0, s>>>(g0, cnt, gkeys, proj_scratch, kvalid);
         count_launch();
         const long items = (long)cnt * B::KT_WINDOWS;
         u32* t0 = tab + (size_t)g0 * B::KT_KEY_WORDS;
@@ -554,17 +565,24 @@ template <class C> struct Launch {
             if (ept < 1) ept = 1;
             if (ept > B::KT_EPT) ept = B::KT_EPT;
             const int threads = (int)((items + ept - 1) / ept);
-            k_kt_fill<C><<<grid(threads), BLK, 0, s>>>((int)items, t0);
+            k_kt_fill<C, W><<<grid(threads), BLK, 0, s>>>((int)items, t0);
             count_launch();
         }
     }
-    static void verify_keytab(cudaStream_t s, int n, int mode, const u8* rs, const u8* z, const u32* scratch, const int* gid, const u8* kvalid,
+    static void verify_keytab(cudaStream_t s, int wide, int n, int mode, const u8* rs, const u8* z, const u32* scratch, const int* gid, const u8* kvalid,
                               const u32* tab, const u32* gbig, int gw, u8* ok) {
         if (n <= 0) return;
+        if constexpr (kt_two_widths<C>()) {
+            if (!wide) { verify_keytab_w<kt_narrow<C>()>(s, n, mode, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok); return; }
+        }
+        verify_keytab_w<0>(s, n, mode, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
+    }
+    template <int W> static void verify_keytab_w(cudaStream_t s, int n, int mode, const u8* rs, const u8* z, const u32* scratch, const int* gid, const u8* kvalid,
+                                                 const u32* tab, const u32* gbig, int gw, u8* ok) {
         if (mode == VM_SM2DSA) {
-            if constexpr (C::ID == 3) k_verify_keytab<C, VM_SM2DSA><<<grid(n), BLK, 0, s>>>(n, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
+            if constexpr (C::ID == 3) k_verify_keytab<C, VM_SM2DSA, W><<<grid(n), BLK, 0, s>>>(n, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
         } else {
-            k_verify_keytab<C, VM_ECDSA><<<grid(n), BLK, 0, s>>>(n, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
+            k_verify_keytab<C, VM_ECDSA, W><<<grid(n), BLK, 0, s>>>(n, rs, z, scratch, gid, kvalid, tab, gbig, gw, ok);
         }
         count_launch();
     }
@@ -588,7 +606,8 @@ template <class C> struct Launch {
             C::ID, C::L, C::FB, C::A_IS_ZERO ? 8 : 15, Bodies<C>::GEN_WINDOWS, 8, C::COMPRESS_DEFAULT, {0},
             &field_op, &mul_var, &mul_gen, &load_proj, &normalize, &sum, &proj_to_bytes, &verify,
             &mul_var_fast, &verify_prep, &verify_main, &decode, &finish, &sign_finish, &wintab, &add_proj,
-            Bodies<C>::KT_WINDOWS, Bodies<C>::KT_KEY_WORDS, Bodies<C>::KBW, &kt_group, &kt_build, &verify_keytab, Bodies<C>::PREP_WORDS, SUM_BLOCKS,
+            {Bodies<C, kt_narrow<C>()>::KT_WINDOWS, Bodies<C>::KT_WINDOWS}, {Bodies<C, kt_narrow<C>()>::KT_KEY_WORDS, Bodies<C>::KT_KEY_WORDS},
+            {kt_narrow<C>(), Bodies<C>::KT_W_DEFAULT}, Bodies<C>::KBW, &kt_group, &kt_build, &verify_keytab, Bodies<C>::PREP_WORDS, SUM_BLOCKS,
             Bodies<C>::G2_W, Bodies<C>::G2_WINDOWS, Bodies<C>::G2_E, &mul_gen2, &sum_normalize};
         for (int i = 0; i < C::L; i++) {   // R mod n (the Montgomery "one" of the scalar field) as big-endian bytes
             const u32 w = C::Fn::Params::one(i);

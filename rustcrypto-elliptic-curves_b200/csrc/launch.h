@@ -46,11 +46,13 @@ struct CurveLaunch {
     void (*add_proj)(cudaStream_t s, int n, const uint32_t* a, const uint32_t* b, uint32_t* out, uint8_t* invalid, const uint8_t* invalid_b);
     // per-key window tables of the verify path (kernels.cuh "per-key window tables"): group the rows of a chunk by public key,
     // build the tables of groups [g0, g0 + cnt), verify on the tables
-    int kt_windows, kt_key_words, kt_kbw;
+    // two table widths per curve, index 0 = narrow (calls with few rows per key), 1 = wide (the default); equal where a curve
+    // has only one
+    int kt_windows[2], kt_key_words[2], kt_w[2], kt_kbw;
     void (*kt_group)(cudaStream_t s, int n, const uint32_t* q32, int* htab, uint32_t hmask, uint32_t* gkeys, int* gid, int* rep, int* rep_slot,
                      int* newgid, int* counter, int cap);
-    void (*kt_build)(cudaStream_t s, int g0, int cnt, const uint32_t* gkeys, uint32_t* proj_scratch, uint8_t* kvalid, uint32_t* tab);
-    void (*verify_keytab)(cudaStream_t s, int n, int mode, const uint8_t* rs, const uint8_t* z, const uint32_t* scratch, const int* gid,
+    void (*kt_build)(cudaStream_t s, int wide, int g0, int cnt, const uint32_t* gkeys, uint32_t* proj_scratch, uint8_t* kvalid, uint32_t* tab);
+    void (*verify_keytab)(cudaStream_t s, int wide, int n, int mode, const uint8_t* rs, const uint8_t* z, const uint32_t* scratch, const int* gid,
                           const uint8_t* kvalid, const uint32_t* tab, const uint32_t* gbig, int gw, uint8_t* ok);
     int prep_words;   // u32 words of scratch per row between verify_prep and verify_main
     int sum_blocks;

@@ -5,6 +5,7 @@
 // parity claims are made on the B200 through libecb200.so.
 #define ECB_EMU 1
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include "../../rustcrypto-elliptic-curves_b200/csrc/kernels.cuh"
 
@@ -72,10 +73,12 @@ template <class C> struct Emu {
         return out;
     }
 
-    // big fixed-base table: signed gw-bit windows below the top one (entry (w << (gw-1)) + v - 1 = v * 2^(gw*w) * G,
-    // v <= 2^(gw-1)), unsigned top window with v up to 2^gw (the last entry is 2^(8FB) * G)
+    // big fixed-base table: nwin = ceil(8FB / gw) windows; signed gw-bit windows below the top one (entry (w << (gw-1)) + v - 1 =
+    // v * 2^(gw*w) * G, v <= 2^(gw-1)), unsigned top window of tb = 8FB - gw (nwin - 1) bits with v up to 2^tb (the last entry is
+    // 2^(8FB) * G) - the layout abi.cu ensure_gbig builds.  ECB_EMU_GW picks the width (default 5: windows that straddle words
+    // and a short top window; 4 = the word-aligned case)
     static std::vector<u32> gbig(int gw) {
-        const int nwin = (32 * L) / gw, per = 1 << (gw - 1), top_base = (nwin - 1) * per, ne = top_base + 2 * per;
+        const int nwin = (32 * L + gw - 1) / gw, tb = 32 * L - gw * (nwin - 1), per = 1 << (gw - 1), top_base = (nwin - 1) * per, ne = top_base + (1 << tb);
         std::vector<u8> pts(2 * FB * (size_t)ne), ks(FB * (size_t)ne, 0);
         typename EC<C>::Aff g;
         EC<C>::generator(g);
@@ -97,15 +100,20 @@ template <class C> struct Emu {
         normalize(ne, proj.data(), NORM_AFF_LIMBS, 0, nullptr, nullptr, out.data(), 0);
         return out;
     }
-    static const std::vector<u32>& gbig4() {
-        static std::vector<u32> gt;
-        if (gt.empty()) gt = gbig(4);
-        return gt;
+    static int emu_gw() {
+        const char* e = getenv("ECB_EMU_GW");
+        const int g = e ? atoi(e) : 5;
+        return g >= 2 && g <= 8 ? g : 5;
+    }
+    static const std::vector<u32>& gbig_cached(int gw) {
+        static std::vector<u32> gt[9];
+        if (gt[gw].empty()) gt[gw] = gbig(gw);
+        return gt[gw];
     }
     // the two-term pipeline in every mode (VM_*): prep -> main [-> normalise -> finish]
     static void verify_mode(int mode, int n, const u8* q, const u8* z, const u8* rs, const u8* aux, u8* ok, u8* out, int compress, int nthreads) {
-        const int gw = 4;
-        const std::vector<u32>& gt = gbig4();
+        const int gw = emu_gw();
+        const std::vector<u32>& gt = gbig_cached(gw);
         std::vector<u32> scratch((size_t)n * B::PREP_WORDS), proj((size_t)3 * L * n);
         int need = (n + B::PREP_EPT - 1) / B::PREP_EPT;
         if (nthreads < need) nthreads = need;
@@ -136,8 +144,8 @@ template <class C> struct Emu {
     // number, assign), tables are built for the keys first seen in a chunk, rows are verified on the tables.  Returns the number
     // of distinct keys found.  cap = table capacity in groups (rows of overflowing groups would take the per-row path: -1 here)
     static int verify_keytab(int mode, int n, const u8* q, const u8* z, const u8* rs, u8* ok, int chunk, int cap, int nthreads) {
-        const int gw = 4;
-        const std::vector<u32>& gt = gbig4();
+        const int gw = emu_gw();
+        const std::vector<u32>& gt = gbig_cached(gw);
         const int KBW = B::KBW, W = B::KT_WINDOWS;
         size_t hs = 16;
         while (hs < (size_t)2 * (cap + chunk)) hs <<= 1;

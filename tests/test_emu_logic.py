@@ -295,6 +295,38 @@ def test_verify_synthetic(cname):
     assert 0 < sum(got) < len(got)
 
 
+@pytest.mark.parametrize("cname", ["k256", "p256", "p384", "p224"])
+@pytest.mark.parametrize("gw", [4, 7, 8])
+def test_verify_fixed_base_window_widths(cname, gw, monkeypatch):
+    """u1*G from the big fixed-base table with windows of any width (jac.cuh add_fixed_base): word-aligned (4, 8) and
+    straddling (7; the other emulation tests run at 5) widths, top windows shorter than the rest, u1 with all-ones words
+    (carries through every window of the recoding), u1 = 0 and 1."""
+    monkeypatch.setenv("ECB_EMU_GW", str(gw))
+    c = o.curve(cname)
+    rng = random.Random(900 + gw)
+    rows = []
+    top = 1 << (8 * c.fb)
+    for u1 in [0, 1, c.n - 1, (top >> 1) % c.n, (top - 1) % c.n, 0x88888888, rng.randrange(c.n), rng.randrange(c.n)]:
+        # a signature whose u1 = z / s is the chosen value: k = u1 + u2 d with u2 = r / s  =>  s = r d / (k - u1), z = u1 s
+        d = rng.randrange(1, c.n)
+        Q = o.mul_gen(c, d)
+        k = rng.randrange(1, c.n)
+        if (k - u1) % c.n == 0:
+            k = k % (c.n - 1) + 1
+        r = o.mul_gen(c, k)[0] % c.n
+        s = r * d * pow((k - u1) % c.n, -1, c.n) % c.n
+        z = u1 * s % c.n
+        if r == 0 or s == 0:
+            continue
+        if c.low_s and s > c.n >> 1:          # (r, n - s) verifies with -u1, -u2: same x(R)
+            s = c.n - s
+        rows.append((Q, z.to_bytes(c.fb, "big"), r, s))
+        rows.append((Q, z.to_bytes(c.fb, "big"), r, s % (c.n - 1) + 1))
+    got, exp = run_verify(c, rows)
+    assert got == list(exp)
+    assert sum(got) >= len(rows) // 2 - 1
+
+
 @pytest.mark.parametrize("cname", ["k256", "p256", "sm2", "p224"])
 def test_verify_keytab_reused_keys_and_overflow(cname):
     """Few keys, many rows (the shape the per-key tables exist for), incl. an off-curve key shared by several rows, corrupted

@@ -499,3 +499,96 @@ def test_device_pointers_of_any_alignment(eng, cname, shift):
     for i in range(4):
         di = int.from_bytes(d[i].tobytes(), "big")
         assert res[0]["gen"][i * slot:(i + 1) * slot] == o.slot_encode(c, o.mul_gen(c, di), False)
+
+
+@pytest.fixture(scope="module")
+def eng_widths():
+    """two engines with the per-key table width forced: narrow (4 bits) and wide (the curve's default: 6 bits on secp256k1,
+    5 on P-256); abi.cu otherwise picks by rows per key (32 and more: wide)"""
+    import os
+    import ecb200
+    es = []
+    for v in ("0", "1"):
+        os.environ["ECB200_KT_WIDE"] = v
+        try:
+            es.append(ecb200.Engine(0))
+        finally:
+            del os.environ["ECB200_KT_WIDE"]
+    yield es
+    for e in es:
+        e.close()
+
+
+@pytest.mark.parametrize("cname", ["k256", "p256", "sm2"])
+def test_keytab_both_table_widths(eng, eng_rowpath, eng_widths, golden, cname):
+    """The narrow and the wide per-key tables (different recodings, different kernels instantiations) give the mask of the per-row
+    path on a synthetic batch with broken keys, and the oracle's verdicts on the reference's Wycheproof rows and the crafted
+    exceptional-case rows tiled so that keys repeat; the automatic choice follows rows per key."""
+    import hashlib
+    from tests import crafted
+    wl = _wl()
+    c = o.curve(cname)
+    fb = c.fb
+    n, nk = 20000, 500
+    q, z, rs, exp = wl.make_verify_batch(wl.EngineBackend(eng, cname), cname, n, 0xB2200000 + c.cid, n_keys=nk)
+    q, exp = q.copy(), exp.copy()
+    bad_key = np.arange(n) % nk == 3
+    q[bad_key, fb - 1] ^= 1
+    exp[bad_key] = 0
+    ref = np.frombuffer(eng_rowpath.ecdsa_verify(cname, q, z, rs), np.uint8)
+    assert np.array_equal(ref, exp)
+    for e in eng_widths:
+        r0, t0 = e.keytab_stats()
+        got = np.frombuffer(e.ecdsa_verify(cname, q, z, rs), np.uint8)
+        r1, t1 = e.keytab_stats()
+        assert r1 - r0 == n and t1 - t0 == nk
+        assert np.array_equal(got, ref)
+    if cname == "sm2":
+        return
+    blob = golden["wycheproof"][cname]
+    hf = getattr(hashlib, blob["hash"])
+    rows = []
+    for wx, wy, msg, sig, flag in blob["rows"]:
+        rsv = o.der_parse_strict(bytes.fromhex(sig), c)
+        if rsv is None or rsv[0] >= 1 << (8 * fb) or rsv[1] >= 1 << (8 * fb):
+            continue
+        Q = (int.from_bytes(bytes.fromhex(wx)[-fb:], "big"), int.from_bytes(bytes.fromhex(wy)[-fb:], "big"))
+        rows.append((Q, ecb_bits2field(cname, hf(bytes.fromhex(msg)).digest()), rsv[0], rsv[1]))
+    rows += [(Q, zb, r, s) for Q, zb, r, s in crafted.exceptional_rows(c) + crafted.reduced_x_rows(c)]
+    reps = 12
+    qb = b"".join(be(r[0], fb) for r in rows) * reps
+    zb = b"".join(r[1] for r in rows) * reps
+    rsb = b"".join(be((r[2], r[3]), fb) for r in rows) * reps
+    expw = o.batch_verify(c, qb[:len(rows) * 2 * fb], zb[:len(rows) * fb], rsb[:len(rows) * 2 * fb]) * reps
+    for e in eng_widths:
+        r0, _ = e.keytab_stats()
+        assert e.ecdsa_verify(cname, qb, zb, rsb) == expw
+        assert e.keytab_stats()[0] - r0 == len(rows) * reps, "the per-key table path did not run"
+
+
+@pytest.mark.parametrize("gw", [7, 16, 18])
+def test_fixed_base_table_widths(eng, gw):
+    """The big fixed-base table of u1*G (jac.cuh add_fixed_base) at other window widths than the default 20 bits: 16 (the
+    round-1 layout, word-aligned), 18 and 7 (windows straddling words, a short top window) - per-row path and per-key tables,
+    the reference's Wycheproof rows plus a synthetic batch, on every 256-bit curve the table differs for."""
+    import os
+    import ecb200
+    os.environ["ECB200_GW"] = str(gw)
+    try:
+        e = ecb200.Engine(0)
+    finally:
+        del os.environ["ECB200_GW"]
+    try:
+        wl = _wl()
+        for cname in ("k256", "p256", "p384", "p224"):
+            c = o.curve(cname)
+            n, nk = 6000, 150
+            q, z, rs, exp = wl.make_verify_batch(wl.EngineBackend(eng, cname), cname, n, 0xB2300000 + c.cid + gw, n_keys=nk)
+            got = np.frombuffer(e.ecdsa_verify(cname, q, z, rs), np.uint8)
+            assert np.array_equal(got, exp), (cname, "tables")
+            m = 1500                               # below the table policy's minimum: per-row path
+            got = np.frombuffer(e.ecdsa_verify(cname, q[:m].copy(), z[:m].copy(), rs[:m].copy()), np.uint8)
+            assert np.array_equal(got, exp[:m]), (cname, "per-row")
+            assert np.array_equal(got, np.frombuffer(eng.ecdsa_verify(cname, q[:m].copy(), z[:m].copy(), rs[:m].copy()), np.uint8))
+    finally:
+        e.close()
