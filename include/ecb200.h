@@ -90,10 +90,10 @@ const char* ecb200_version(void);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches evidence). */
 uint64_t ecb200_launch_count(const ecb200_ctx* ctx);
 /* Verification statistics since the context was created: rows verified on per-key window tables and tables built.
- * ecb200_ecdsa_verify* / ecb200_sm2dsa_verify* group the rows of a call by public key; when keys repeat (at least 8 rows per
+ * ecb200_ecdsa_verify* / ecb200_sm2dsa_verify* group the rows of a call by public key; when keys repeat (at least 4 rows per
  * distinct key) each key's window multiples v * 2^(W w) * Q are computed once per call and every row needs additions only - no doublings.
  * Calls whose keys do not repeat take the per-row path; results are identical either way.  Nothing is cached between calls.
- * The window width W follows the reuse: 4 bits below 32 rows per key, the curve's wide tables (6 bits on secp256k1, 5 on P-256)
+ * The window width W follows the reuse: 4 bits below 20 rows per key, the curve's wide tables (6 bits on secp256k1, 5 on P-256)
  * from there on.  Environment (read by ecb200_init, for tests and A/B measurements): ECB200_KEYTAB=0 forces the per-row path,
  * ECB200_KT_WIDE=0/1 the narrow / wide tables, ECB200_GW=<bits> the window width of the fixed-base table of u1*G (default 20
  * bits = 410 MB per 256-bit curve, built on the first verification).  A `_dev` verification call on the table path

@@ -110,7 +110,7 @@ struct ecb200_ctx {
     // key incrementally, tables are built once per distinct key and dropped when the call returns (nothing is cached between calls)
     struct KeyTab {
         DevBuf htab, gkeys, tab, kvalid, jac, rep, rep_slot, newgid, gid, counter;
-        size_t cap = 0, alloc_groups = 0, total_rows = 0;
+        size_t cap = 0, alloc_words = 0, total_rows = 0;   // alloc_words: u32 words of `tab` (the width, hence the words per key, can change from call to call)
         uint32_t hmask = 0;
         int built = 0;
         int wide = 1;                        // table width of this call: 1 = the curve's default, 0 = the narrow one (few rows per key)
@@ -424,13 +424,16 @@ int batch_normalize_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const u
 enum { VM_ECDSA = 0, VM_SM2DSA = 1, VM_SCHNORR = 2, VM_RECOVER = 3, DEC_SEC1 = 0, DEC_COMPACT = 1, FIN_SCHNORR = 0, FIN_RECOVER = 1 };   // = kernels.cuh
 
 // ---- per-key window tables (kernels.cuh).  Policy: a call is eligible when it is large enough to amortise anything
-// (KT_MIN_ROWS); tables are used while the call shows at least KT_MIN_REUSE rows per distinct key (a table costs ~2.6
+// (KT_MIN_ROWS); tables are used while the call shows at least KT_MIN_REUSE rows per distinct key (a narrow table costs ~3
 // verifications, saves ~0.5 per row) and the distinct keys fit the table memory; the first chunk of a multi-chunk host call
 // must already show two rows per key, so a call with all-distinct keys pays only the grouping kernels (~0.4 % of a step).
 // Table width: the curve's wide default (6 bits on secp256k1, 5 on P-256) when the call has at least KT_WIDE_REUSE rows per
 // distinct key, else 4 bits - a table is paid per key, its additions per row (kernels.cuh).  Decided once per call, on the
 // first chunk: total rows of the call / distinct keys seen so far.
-constexpr size_t KT_MIN_ROWS = 4096, KT_MIN_REUSE = 8, KT_WIDE_REUSE = 32;
+// Measured (profiles/r02_ab_table_width_by_reuse.txt, M verifies/s narrow / wide at 8, 16, 32, 64 rows per key): secp256k1 67.7 / 57.7,
+// 82.7 / 82.5, 93.8 / 106.2, 100.0 / 123.4; P-256 52.5 / 47.6, 71.6 / 70.4, 88.1 / 93.2, 99.3 / 111.0 - the widths cross at ~16 rows per
+// key, and the narrow tables already beat the per-row path (54.7 / 34.1 M/s) well below 8: their cost per key equals ~3 rows' worth.
+constexpr size_t KT_MIN_ROWS = 4096, KT_MIN_REUSE = 4, KT_WIDE_REUSE = 20;
 constexpr size_t KT_MEM_CAP = (size_t)12 << 30;      // bytes of tables per context (180 GB of HBM per GPU)
 
 int kt_begin(ecb200_ctx* c, const CurveLaunch* cl, size_t total_rows, size_t max_chunk, cudaStream_t s) {
@@ -481,7 +484,7 @@ int kt_chunk(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q,
     if (first) k.wide = c->kt_force_wide >= 0 ? c->kt_force_wide : ((size_t)D * KT_WIDE_REUSE <= k.total_rows ? 1 : 0);
     if (D > k.built) {
         const size_t kw = (size_t)cl->kt_key_words[k.wide];
-        if ((size_t)D > k.alloc_groups) {  // grow the table store (position independent: old tables are copied over)
+        if ((size_t)D * kw > k.alloc_words) {  // grow the table store (position independent: old tables are copied over)
             size_t want = std::min(k.cap, std::max<size_t>((size_t)2 * D, 65536));
             DevBuf bigger;
             CU(c, bigger.reserve(want * kw * 4));
@@ -489,7 +492,7 @@ int kt_chunk(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_q,
             CU(c, cudaStreamSynchronize(s));
             k.tab.release();
             k.tab = bigger;
-            k.alloc_groups = want;
+            k.alloc_words = want * kw;
         }
         const int cnt = D - k.built;
         CU(c, k.jac.reserve((size_t)cnt * cl->kt_windows[k.wide] * 3 * cl->L * 4));
@@ -591,6 +594,25 @@ int sign_core(ecb200_ctx* c, const CurveLaunch* cl, size_t n, const uint8_t* d_d
     return 0;
 }
 
+// Staging copy between pageable caller memory and the context's pinned buffers.  One host thread moves ~10 GB/s, a third
+// of what the 2^22-row verify pipeline consumes (671 MB per 34 ms), so large copies are cut over a few threads
+// (measured with bench.py's pageable-buffer leg: 72.6 M verifies/s single-threaded against 117.9 M/s from page-locked buffers).
+void staged_copy(void* dst, const void* src, size_t bytes) {
+    constexpr size_t MIN_PER_THREAD = (size_t)4 << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t t = std::min<size_t>({(size_t)8, hw ? (size_t)std::max(1u, hw / 2) : (size_t)1, bytes / MIN_PER_THREAD});
+    if (t <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    th.reserve(t - 1);
+    const size_t per = ((bytes + t - 1) / t + 63) & ~(size_t)63;
+    for (size_t i = 1; i < t; i++) {
+        const size_t lo = std::min(bytes, i * per), hi = std::min(bytes, lo + per);
+        if (hi > lo) th.emplace_back([=] { memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+    }
+    memcpy(dst, src, std::min(bytes, per));
+    for (auto& x : th) x.join();
+}
+
 // -------------------------------------------------------------------------------------------
 // Host-pointer pipeline: the batch is cut into CHUNK-element pieces; piece i is copied into pinned
 // memory and sent H2D on the copy-in stream while piece i-1 computes and piece i-2 drains D2H.
@@ -630,7 +652,7 @@ int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, co
                 const void* src = in[k] + off * in_sz[k];
                 if (!in_pinned[k]) {
                     CU(c, c->h_in[slot][k].reserve(cap * in_sz[k]));
-                    memcpy(c->h_in[slot][k].p, src, bytes);
+                    staged_copy(c->h_in[slot][k].p, src, bytes);
                     src = c->h_in[slot][k].p;
                 }
                 c->in_used[slot][k] = std::max(c->in_used[slot][k], bytes);
@@ -666,7 +688,7 @@ int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, co
             CU(c, cudaEventSynchronize(c->ev_out[slot]));
             for (int k = 0; k < n_out; k++) {
                 if (!out[k] || !out_sz[k] || out_pinned[k]) continue;
-                memcpy(out[k] + off * out_sz[k], c->h_out[slot][k].p, cnt * out_sz[k]);
+                staged_copy(out[k] + off * out_sz[k], c->h_out[slot][k].p, cnt * out_sz[k]);
             }
         }
     }

@@ -867,7 +867,7 @@ template <class C, int KTW = 0> struct Bodies {
     //     T[g][w][v-1] = v * 2^(W w) * Q_g,   v = 1..2^(W-1),  w = 0..KT_WINDOWS-1      (affine, field-internal limbs, 2L words per entry)
     // and verifies each row with KT_WINDOWS (x2 with the GLV split) mixed additions gathered from HBM and NO doublings:
     // secp256k1 ~920 instead of ~1890 field multiplications per row, P-256 ~890 instead of ~2900.  Tables cost ~5 k
-    // multiplications per key (2.6 verifications), so the path is taken only when the call reuses keys (abi.cu: at least 8 rows
+    // multiplications per key (2.6 verifications), so the path is taken only when the call reuses keys (abi.cu: at least 4 rows
     // per key); otherwise the per-row path above runs.  Nothing is kept between calls: every call groups and builds afresh.
     // The reference verifies row by row (k256/src/ecdsa.rs:200-209 -> lincomb, mul.rs:342-393) and recomputes u2*Q every time.
     // window width W (ECB_KT_W, bits): signed digits d_w in [-2^(W-1), 2^(W-1)) below the top window, which is unsigned and
@@ -878,12 +878,12 @@ template <class C, int KTW = 0> struct Bodies {
     // 75.0; at 2^20 rows (16 rows per key) P-384 15.6 / 13.9 / 10.4, SM2 45.1 / 38.6 / 29.2.  With 128-bit accesses the fill costs a
     // third (2.5 ms) and one more bit pays: secp256k1 111.9 (5) / 118.7 (6), P-256 97.0 (4) / 107.3 (5)
     // (profiles/r02_ab_vector_access.txt).  secp256k1 recodes two 128-bit halves, so a wider window removes twice the additions per
-    // table entry added: W = 6 (22 windows of 32 entries per half, 45 KB per key; a table costs ~8 rows' worth of the per-row path,
-    // the policy in abi.cu asks for 8 rows per key); P-256 takes W = 5 (52 windows of 16 entries, 53 KB per key); P-384 / SM2 and the
-    // small curves keep W = 4 (their BASELINE-shaped case has 16 rows per key).  -DECB_KT_W=n forces one width for every curve.
-    // The widths above are for calls with many rows per key; a table is paid per KEY, so calls with 8 .. 32 rows per key (the
-    // policy in abi.cu asks for 8) take the narrow width W = 4 instead: per 2^16 keys the secp256k1 fill costs ~1.3 / 2.5 / 5.0 ms at
-    // W = 4 / 5 / 6 and the additions of 2^22 rows ~36 / 32 / 29 ms, so the widths cross at ~32 rows per key.
+    // table entry added: W = 6 (22 windows of 32 entries per half, 45 KB per key; a wide table costs ~8 rows' worth of the per-row
+    // path); P-256 takes W = 5 (52 windows of 16 entries, 53 KB per key); P-384 / SM2 and the small curves keep W = 4 (their
+    // BASELINE-shaped case has 16 rows per key).  -DECB_KT_W=n forces one width for every curve.
+    // The widths above are for calls with many rows per key; a table is paid per KEY, so calls with 4 .. 20 rows per key take
+    // the narrow width W = 4 instead (the launchers instantiate the three table kernels for both): per 2^16 keys the secp256k1 fill
+    // costs ~1.3 / 2.5 / 5.0 ms at W = 4 / 5 / 6, and measured the widths cross at ~16 rows per key (abi.cu KT_WIDE_REUSE).
 #ifdef ECB_KT_W
     static constexpr int KT_W_DEFAULT = ECB_KT_W;
 #else

@@ -343,7 +343,7 @@ def test_keytab_path_matches_per_row_path_and_construction(eng, eng_rowpath, cna
 
 def test_keytab_policy_and_chunked_host_calls(eng, eng_rowpath):
     """(a) all keys distinct: the per-row path runs (no tables); (b) a host call that spans several pipeline chunks carries the
-    key groups from chunk to chunk (tables are built once per key per call); (c) below 8 rows per key the per-row path runs;
+    key groups from chunk to chunk (tables are built once per key per call); (c) below 4 rows per key the per-row path runs, from 4 on the (narrow) tables;
     (d) the device-pointer entry point takes the same path; (e) SEC1-encoded keys and SM2DSA go through it too."""
     import ecb200
     import torch
@@ -355,9 +355,13 @@ def test_keytab_policy_and_chunked_host_calls(eng, eng_rowpath):
     r0, t0 = eng.keytab_stats()
     assert eng.ecdsa_verify("k256", q, z, rs) == exp.tobytes()
     assert eng.keytab_stats() == (r0, t0)
-    q, z, rs, exp = wl.make_verify_batch(be_, "k256", n, 0xB2100101, n_keys=n // 4)     # (c) 4 rows per key
+    q, z, rs, exp = wl.make_verify_batch(be_, "k256", n, 0xB2100101, n_keys=n // 3)     # (c) 3 rows per key: below the policy's 4
     assert eng.ecdsa_verify("k256", q, z, rs) == exp.tobytes()
     assert eng.keytab_stats() == (r0, t0)
+    q, z, rs, exp = wl.make_verify_batch(be_, "k256", n, 0xB2100103, n_keys=n // 5)     # 5 rows per key: narrow tables
+    assert eng.ecdsa_verify("k256", q, z, rs) == exp.tobytes()
+    assert eng.keytab_stats() == (r0 + n, t0 + n // 5)
+    r0, t0 = eng.keytab_stats()
     n = 1500000                                                                            # (b) 227 328 + 1 136 640 + rest: three chunks
     nk = 3000
     q, z, rs, exp = wl.make_verify_batch(be_, "k256", n, 0xB2100102, n_keys=nk)
@@ -555,7 +559,7 @@ def test_keytab_both_table_widths(eng, eng_rowpath, eng_widths, golden, cname):
         Q = (int.from_bytes(bytes.fromhex(wx)[-fb:], "big"), int.from_bytes(bytes.fromhex(wy)[-fb:], "big"))
         rows.append((Q, ecb_bits2field(cname, hf(bytes.fromhex(msg)).digest()), rsv[0], rsv[1]))
     rows += [(Q, zb, r, s) for Q, zb, r, s in crafted.exceptional_rows(c) + crafted.reduced_x_rows(c)]
-    reps = 12
+    reps = 24                                   # enough rows for the table policy (4096) on every curve
     qb = b"".join(be(r[0], fb) for r in rows) * reps
     zb = b"".join(r[1] for r in rows) * reps
     rsb = b"".join(be((r[2], r[3]), fb) for r in rows) * reps
