@@ -69,17 +69,20 @@ def load_json(path, default=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is started BEFORE
+    the warm-up steps (nvidia-smi needs a few hundred ms before its first line) and polls every 50 ms; begin() / end() mark the
+    timed region and summary() keeps the samples that arrived inside it.  Should the region be shorter than one polling period,
+    the samples taken under the same load during the warm-up are reported instead and `window` says so."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.proc, self.t0, self.t1, self.w0, self.w1 = device, [], None, None, None, None, None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -88,11 +91,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_first(self, timeout):
+        t = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.01)
+
+    def warm_begin(self):
+        self.w0 = time.perf_counter()
+
+    def warm_end(self):
+        self.w1 = time.perf_counter()
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.15)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -100,14 +119,20 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        inside = [r for t, r in ok if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.05]
+        window = "timed region"
+        if not inside:      # region shorter than a polling period: the samples of the warm-up (same kernels, same load) right before it
+            inside = [r for t, r in ok if self.w0 is not None and self.w0 <= t <= (self.w1 or t) + 0.05]
+            window = "warm-up steps right before the timed region (the region is shorter than one 50 ms polling period)"
+        sm = [float(r[0]) for r in inside]
+        mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         reasons = []
         for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(len(r) >= 7 and r[col].lower().startswith("active") for r in self.rows):
+            if any(r[col].lower().startswith("active") for r in inside):
                 reasons.append(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def imad_peaks(sm_mhz):
@@ -485,23 +510,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- kernel-resident timing
-    for _ in range(warmup):
-        w.dev()
-    barrier()
-    chk = w.check()
-    assert chk["ok"], "output check failed: " + chk["check"]
-    l0 = eng.launch_count
-    kt0 = eng.keytab_stats()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.kernel_timing(True)
+    # ---- kernel-resident timing (the clock sampler is already polling when the warm-up starts)
     with ClockSampler(local) as clk:
+        clk.wait_first(3.0)
+        clk.warm_begin()
+        for _ in range(warmup):
+            w.dev()
         barrier()
+        clk.warm_end()
+        chk = w.check()
+        assert chk["ok"], "output check failed: " + chk["check"]
+        l0 = eng.launch_count
+        kt0 = eng.keytab_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.kernel_timing(True)
+        barrier()
+        clk.begin()
         e0.record(ts)
         for _ in range(steps):
             w.dev()
         e1.record(ts)
         barrier()
+        clk.end()
     eng.kernel_timing(False)
     k_ms, k_cnt = eng.kernel_timing_read()
     kernel_ms = max_over_ranks(k_ms / max(k_cnt, 1))
