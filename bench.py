@@ -177,7 +177,10 @@ def roofline(op, curve, n_rows, step_ms, sm_mhz, kernel_ms=None, ct=False, io=No
                     "macs_per_row_dominant_kernel": round(macs_dom, 1), "macs_per_row_step": prof["wide_macs_per_row"],
                     "step_executed": round(step, 1), "step_executed_frac": round(step / peak, 4),
                     "fmaheavy_pipe_pct": dom.get("fmaheavy_pct"), "issue_active_pct": dom.get("issue_active_pct"),
-                    "registers": dom.get("registers"), "traffic": prof.get("dram_bytes_per_launch"), "traffic_rows": prof["n_rows"],
+                    "registers": dom.get("registers"),
+                    # DRAM bytes (read + written) of the dominant kernel's launch in the ncu --set full capture; the whole call beside it
+                    "traffic": dom.get("dram_bytes") if dom.get("dram_bytes") is not None else prof.get("dram_bytes_per_launch"),
+                    "traffic_whole_call": prof.get("dram_bytes_per_launch"), "traffic_rows": prof["n_rows"],
                     "executed_source": prof.get("source")})
     elif prof.get("wide_macs_per_row"):      # round-1 style entry: one kernel only
         ach = n_rows * prof["wide_macs_per_row"] / (dur * 1e-3) / 1e9

@@ -219,6 +219,10 @@ template <class C, int W = 0> __global__ void __launch_bounds__(BLK, ktf_min_cta
 #ifndef ECB_KT_MIN_CTAS
 #define ECB_KT_MIN_CTAS 0
 #endif
+// Measured at 2^22 rows / 2^16 keys (P-384: 2^20 rows), M verifies/s at the per-row kernels' occupancy / 7 / 8 resident CTAs
+// (profiles/r02_ab_occupancy_table_kernels.txt): secp256k1 (7) 123.5 / 123.5 / 121.7, P-256 (6) 111.0 / 111.8 / 112.3, P-384 (4) 21.17 /
+// 21.82 / 21.23.  The +1 .. 3 % of the higher settings come with spills (P-256 at 64 registers: 76 / 60 B instead of 12 / 12;
+// P-384 at 72: 160 / 136 B instead of none) and were not taken.
 template <class C> constexpr int kt_min_ctas() { return ECB_KT_MIN_CTAS ? ECB_KT_MIN_CTAS : fast_min_ctas<C>(); }
 template <class C, int MODE, int W = 0> __global__ void __launch_bounds__(BLK, kt_min_ctas<C>()) k_verify_keytab(int n, const u8* rs, const u8* z, const u32* scratch, const int* gid, const u8* kvalid,
                                                                                                                      const u32* tab, const u32* gbig, int gw, u8* ok) {
