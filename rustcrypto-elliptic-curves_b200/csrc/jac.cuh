@@ -90,12 +90,43 @@ template <class C> struct Jac {
         dbl(r, t);
     }
 
+#ifndef ECB_MADD_EARLY_STORE
+#define ECB_MADD_EARLY_STORE 1
+#endif
     // ---- mixed addition r = p + q, q affine and not the identity.  zr (optional) receives Z3 / Z1 (= H)
     // (valid only on the generic branch; callers that need it guarantee no exceptional case).
     ECB_POINT_FN static void madd(J& r, const J& p, const A& q, E* zr) {
         if (is_inf(p)) { from_affine(r, q); return; }
         // madd-2004-hmv (8M + 3S, 7 add-type ops): Z1Z1 = Z1^2, U2 = x2*Z1Z1, S2 = y2*Z1*Z1Z1, H = U2 - X1, R = S2 - Y1,
         // Z3 = Z1*H, HH = H^2, HHH = H*HH, V = X1*HH, X3 = R^2 - HHH - 2V, Y3 = R(V - X3) - Y1*HHH
+#if ECB_MADD_EARLY_STORE
+        // Same formulas, ordered for register pressure: every value dies as early as the data flow allows and each output
+        // coordinate is stored as soon as its input counterpart has been read for the last time (r may alias p), so at most
+        // four field elements are live across a multiplier call instead of five
+        E z1z1, u2, s2, h, rr, hh, hhh, v, t;
+        F::sqr(z1z1, p.Z);
+        F::mul(u2, q.x, z1z1);
+        F::sub(h, u2, p.X);
+        F::mul(s2, q.y, p.Z); F::mul(s2, s2, z1z1);
+        F::sub(rr, s2, p.Y);
+        if (F::is_zero(h)) {
+            if (F::is_zero(rr)) dbl_affine(r, q);   // p == q
+            else set_inf(r);                         // p == -q
+            return;
+        }
+        if (zr) *zr = h;
+        F::mul(t, p.Z, h);
+        r.Z = t;                                     // Z1 is not read again
+        F::sqr(hh, h);
+        F::mul(hhh, hh, h);
+        F::mul(v, p.X, hh);
+        F::sqr(t, rr); F::sub(t, t, hhh); F::sub(t, t, v); F::sub(t, t, v);   // two subtractions are cheaper than dbl + sub
+        r.X = t;                                     // X1 is not read again
+        F::sub(v, v, t); F::mul(v, rr, v);
+        F::mul(t, p.Y, hhh);
+        F::sub(v, v, t);
+        r.Y = v;
+#else
         E z1z1, u2, s2, h, rr, hh, hhh, v, t;
         F::sqr(z1z1, p.Z);
         F::mul(u2, q.x, z1z1);
@@ -118,6 +149,7 @@ template <class C> struct Jac {
         F::mul(t, p.Y, hhh);
         F::sub(y3, y3, t);
         r.X = x3; r.Y = y3; r.Z = z3;
+#endif
     }
 
     // ---- branch-free mixed addition for the secret-scalar FIXED-BASE path (kernels.cuh body_gen_half): p += q in place.
@@ -128,6 +160,31 @@ template <class C> struct Jac {
     // than every entry of the window being added (see body_gen_half), so the exceptional cases of the Jacobian formulas
     // cannot occur and no complete formula is needed until the halves are combined.  Returns the new `inf`.
     ECB_POINT_FN static u32 madd_ct(J& p, u32 inf, const A& q, u32 take) {
+#if ECB_MADD_EARLY_STORE
+        // ordered like madd above: each coordinate is committed (by mask) as soon as its old value has been read for the last time
+        E z1z1, u2, s2, h, rr, hh, hhh, v, t;
+        F::sqr(z1z1, p.Z);
+        F::mul(u2, q.x, z1z1);
+        F::sub(h, u2, p.X);
+        F::mul(s2, q.y, p.Z); F::mul(s2, s2, z1z1);
+        F::sub(rr, s2, p.Y);
+        F::mul(t, p.Z, h);
+        F::set_one(u2);
+        F::cmov(t, u2, inf);
+        F::cmov(p.Z, t, take);
+        F::sqr(hh, h);
+        F::mul(hhh, hh, h);
+        F::mul(v, p.X, hh);
+        F::sqr(t, rr); F::sub(t, t, hhh); F::sub(t, t, v); F::sub(t, t, v);
+        F::sub(v, v, t); F::mul(v, rr, v);                 // rr (V - X3), with the true X3
+        F::cmov(t, q.x, inf);
+        F::cmov(p.X, t, take);
+        F::mul(t, p.Y, hhh);
+        F::sub(v, v, t);
+        F::cmov(v, q.y, inf);
+        F::cmov(p.Y, v, take);
+        return inf & ~take;
+#else
         E z1z1, u2, s2, h, rr, hh, hhh, v, t, x3, y3, z3, one;
         F::sqr(z1z1, p.Z);
         F::mul(u2, q.x, z1z1);
@@ -146,6 +203,7 @@ template <class C> struct Jac {
         F::cmov(x3, q.x, inf); F::cmov(y3, q.y, inf); F::cmov(z3, one, inf);
         F::cmov(p.X, x3, take); F::cmov(p.Y, y3, take); F::cmov(p.Z, z3, take);
         return inf & ~take;
+#endif
     }
 
     // ---- full Jacobian addition r = p + q
