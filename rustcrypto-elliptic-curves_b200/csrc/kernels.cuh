@@ -1003,6 +1003,26 @@ template <class C, int KTW = 0> struct Bodies {
         if ((dst & 1) == 0) { a = dst >> 1; b = a; }
         else { a = 1 << r; b = dst - a; }
     }
+    // L2 prefetch of the part of an item round r touches (entries 1 .. 2^(r+1)), requested while the previous item is being
+    // computed: a thread's items lie nthreads KB apart in a table far larger than L2, so every first touch is a DRAM round trip
+    // (ncu: long_scoreboard 3.1 per issue at four resident CTAs).  MEASURED SLOWER on the B200 and off by default: k_kt_fill 4.35 ->
+    // 4.94 ms per 2^16 secp256k1 keys (profiles/r02_ab_prefetch.txt) - the prefetched lines evict each other before they are used
+    // (1 MB in flight per SM).  ECB_KT_PREFETCH_MAIN (next window's entries in k_verify_keytab): secp256k1 -0.5 %, P-256 -0.7 %,
+    // P-384 +0.8 %; off as well.
+#ifndef ECB_KT_PREFETCH
+#define ECB_KT_PREFETCH 0
+#endif
+#ifndef ECB_KT_PREFETCH_MAIN
+#define ECB_KT_PREFETCH_MAIN 0
+#endif
+    ECB_DEV static void kt_prefetch_item(const u32* ent, int r) {
+#if defined(__CUDA_ARCH__) && !defined(ECB_EMU) && ECB_KT_PREFETCH
+        const int bytes = (2 << r) * 2 * L * 4;
+        for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(ent) + o));
+#else
+        (void)ent; (void)r;
+#endif
+    }
     template <class INV = OwnInv>
     ECB_DEV static void body_kt_fill(int tid, int nthreads, int items, u32* tab) {
 #if defined(__CUDA_ARCH__)
@@ -1020,6 +1040,7 @@ template <class C, int KTW = 0> struct Bodies {
                 const int i = tid + j * nthreads;
                 if (i >= items) break;
                 u32* ent = tab + (size_t)i * KT_E * 2 * L;
+                if (j + 1 < KT_EPT && i + nthreads < items) kt_prefetch_item(ent + (size_t)nthreads * KT_E * 2 * L, r);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -1042,6 +1063,7 @@ template <class C, int KTW = 0> struct Bodies {
             for (int j = cnt - 1; j >= 0; j--) {
                 const int i = tid + j * nthreads;
                 u32* ent = tab + (size_t)i * KT_E * 2 * L;
+                if (j > 0) kt_prefetch_item(ent - (size_t)nthreads * KT_E * 2 * L, r);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -1137,6 +1159,14 @@ template <class C, int KTW = 0> struct Bodies {
 #endif
             for (int w = 0; w < KT_WINDOWS; w++) {
                 u32 mag, neg;
+#if defined(__CUDA_ARCH__) && ECB_KT_PREFETCH_MAIN
+                if (w + 1 < KT_WINDOWS) {                  // request the two entries of the next window while this one is added
+                    kt_digit(k1, w + 1, mag, neg);
+                    if (mag) asm volatile("prefetch.global.L2 [%0];" ::"l"(tk + ((size_t)(w + 1) * KT_E + mag - 1) * 2 * L));
+                    kt_digit(k2, w + 1, mag, neg);
+                    if (mag) asm volatile("prefetch.global.L2 [%0];" ::"l"(tk + ((size_t)(w + 1) * KT_E + mag - 1) * 2 * L));
+                }
+#endif
                 kt_digit(k1, w, mag, neg);
                 if (mag) {
                     typename JJ::A e;
@@ -1176,6 +1206,12 @@ template <class C, int KTW = 0> struct Bodies {
 #endif
             for (int w = 0; w < KT_WINDOWS; w++) {
                 u32 mag, neg;
+#if defined(__CUDA_ARCH__) && ECB_KT_PREFETCH_MAIN
+                if (w + 1 < KT_WINDOWS) {
+                    kt_digit(kb, w + 1, mag, neg);
+                    if (mag) asm volatile("prefetch.global.L2 [%0];" ::"l"(tk + ((size_t)(w + 1) * KT_E + mag - 1) * 2 * L));
+                }
+#endif
                 kt_digit(kb, w, mag, neg);
                 if (mag) {
                     typename JJ::A e;
