@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
 LIMIT=${1:-170}
-( timeout 100 python __graft_entry__.py smoke 2>&1 | tail -2 ) | tee $O/s20_smoke.txt; echo "smoke at ${SECONDS}s"
+( timeout 100 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ) | tee $O/s20_smoke.txt; echo "smoke at ${SECONDS}s"
 run() { # name args...
   local name=$1; shift
   local left=$((LIMIT - SECONDS))
