@@ -80,3 +80,41 @@ def reduced_x_recover_rows(c):
         rows.append((z, r, s, 2 | (R[1] & 1)))
         rows.append((z, r, s, R[1] & 1))      # same r without the bit: decompress(r) — a different point or none
     return rows
+
+
+def fixed_base_digits(c, u1, gw):
+    """Signed digits of u1 as jac.cuh add_fixed_base recodes it: gw-bit windows biased by 2^(gw-1) below the top one
+    (digit in [-2^(gw-1), 2^(gw-1) - 1]), unsigned top window that absorbs the carry.  sum(d_w 2^(gw w)) == u1."""
+    bits = 8 * c.fb
+    nwin = (bits + gw - 1) // gw
+    half = 1 << (gw - 1)
+    kb = u1 + sum(half << (gw * w) for w in range(nwin - 1))
+    digs = [((kb >> (gw * w)) & ((1 << gw) - 1)) - half for w in range(nwin - 1)] + [kb >> (gw * (nwin - 1))]
+    assert sum(d << (gw * w) for w, d in enumerate(digs)) == u1
+    return digs
+
+
+def fixed_base_collision_rows(c, gw, windows=None, seed=77):
+    """Rows whose accumulator MEETS the fixed-base table entry it is about to receive: the public-input kernels add the
+    windows of u1*G (low to high) onto acc = u2*Q, so with Q = d*G and u2 = (+-d_j 2^(gw j) - sum_{w<j} d_w 2^(gw w)) / d the
+    j-th gathered addition is P + P (sign +) or P + (-P) (sign -, leaving the identity for the windows above).  One pair of
+    rows per window j of the gw-bit recoding; verdicts come from the oracle (valid signatures unless a rule bites)."""
+    import random
+    rng = random.Random(seed + c.cid + 1000 * gw)
+    n = c.n
+    rows = []
+    nwin = (8 * c.fb + gw - 1) // gw
+    for j in (windows if windows is not None else range(nwin)):
+        for sign in (1, -1):
+            for _ in range(50):
+                u1, d = rng.randrange(1, n), rng.randrange(2, n)
+                digs = fixed_base_digits(c, u1, gw)
+                if digs[j] == 0:
+                    continue
+                partial = sum(dw << (gw * w) for w, dw in enumerate(digs[:j]))
+                u2 = (sign * (digs[j] << (gw * j)) - partial) * pow(d, -1, n) % n
+                row = craft(c, u1, u2, d) if u2 else None
+                if row is not None and not (c.low_s and row[3] > n >> 1):      # a high s would be refused before any point arithmetic
+                    rows.append(row)
+                    break
+    return rows

@@ -327,6 +327,26 @@ def test_verify_fixed_base_window_widths(cname, gw, monkeypatch):
     assert sum(got) >= len(rows) // 2 - 1
 
 
+@pytest.mark.parametrize("cname", CUR)
+@pytest.mark.parametrize("gw", [5, 8])
+def test_verify_fixed_base_window_collisions(cname, gw, monkeypatch):
+    """Rows built so that the accumulator u2*Q + (windows of u1*G below j) equals, or is the negative of, the table entry of
+    window j (tests/crafted.py fixed_base_collision_rows): the P + P and P + (-P) branches of the gathered mixed addition at
+    EVERY window position of the recoding incl. the unsigned top window, on the per-row and the per-key-table kernels."""
+    from tests import crafted
+    monkeypatch.setenv("ECB_EMU_GW", str(gw))
+    c = o.curve(cname)
+    nwin = (8 * c.fb + gw - 1) // gw
+    windows = list(range(nwin)) if c.fb <= 32 and gw == 8 else sorted(set(list(range(0, nwin, 5 if c.fb <= 32 else 9)) + [1, nwin - 2, nwin - 1]))
+    rows = crafted.fixed_base_collision_rows(c, gw, windows)
+    assert len(rows) >= 2 * len(windows) - 2
+    # twins with a different r must be rejected on the same exceptional path
+    rows += [(Q, z, r % (c.n - 1) + 1, s) for Q, z, r, s in rows[::3]]
+    got, exp = run_verify(c, rows)
+    assert got == list(exp)
+    assert sum(got) >= 2 * len(windows) - 4 and sum(got) < len(got)
+
+
 @pytest.mark.parametrize("cname", ["k256", "p256", "sm2", "p224"])
 def test_verify_keytab_reused_keys_and_overflow(cname):
     """Few keys, many rows (the shape the per-key tables exist for), incl. an off-curve key shared by several rows, corrupted

@@ -430,6 +430,34 @@ def test_keytab_wycheproof_and_crafted_rows_tiled(eng, golden):
         assert got == exp and 0 < sum(got) < len(got)
 
 
+@pytest.mark.parametrize("cname", ["k256", "p256", "p384", "p224"])
+def test_fixed_base_window_collisions_at_device_widths(eng, cname):
+    """Rows whose accumulator u2*Q + (windows of u1*G below j) equals the table entry of window j or its negative
+    (tests/crafted.py fixed_base_collision_rows), for the window width the device tables really have (20 bits on the 256-bit and
+    smaller curves, 16 on P-384): the P + P and P + (-P) branches of the gathered mixed addition at every window position incl.
+    the unsigned top window - on the per-row kernels (a small call) and on the per-key tables (the same rows tiled)."""
+    from tests import crafted
+    c = o.curve(cname)
+    fb = c.fb
+    gw = 16 if fb > 32 else 20
+    rows = crafted.fixed_base_collision_rows(c, gw)
+    nwin = (8 * fb + gw - 1) // gw
+    assert len(rows) >= 2 * nwin - 2
+    rows += [(Q, z, r % (c.n - 1) + 1, s) for Q, z, r, s in rows[::3]]           # same path, wrong r: must be rejected
+    q = b"".join(be(r[0], fb) for r in rows)
+    z = b"".join(r[1] for r in rows)
+    rs = b"".join(be((r[2], r[3]), fb) for r in rows)
+    exp = o.batch_verify(c, q, z, rs)
+    assert sum(exp) >= 2 * nwin - 4 and sum(exp) < len(exp)
+    r0, _ = eng.keytab_stats()
+    assert eng.ecdsa_verify(cname, q, z, rs) == exp                             # < 4096 rows: per-row path
+    assert eng.keytab_stats()[0] == r0
+    reps = 4096 // len(rows) + 1
+    got = eng.ecdsa_verify(cname, q * reps, z * reps, rs * reps)
+    assert eng.keytab_stats()[0] - r0 == len(rows) * reps, "the per-key table path did not run"
+    assert got == exp * reps
+
+
 def ecb_bits2field(cname, digest):
     import ecb200
     return ecb200.bits2field(cname, digest)
