@@ -25,7 +25,7 @@
 // (Scalar::invert_vartime, k256 scalar.rs:467-516, p256 scalar.rs:365-409); to_affine uses the Fermat
 // chain as the reference does.
 //
-//   g++ -O3 -march=native -fopenmp -shared -fPIC -o oracle/libecport.so oracle/ecport.cpp
+//   g++ -O3 -march=x86-64-v3 -fopenmp -shared -fPIC -o oracle/libecport.so oracle/ecport.cpp      (oracle/Makefile)
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
