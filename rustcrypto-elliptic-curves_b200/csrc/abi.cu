@@ -618,8 +618,8 @@ void staged_copy(void* dst, const void* src, size_t bytes) {
 // memory and sent H2D on the copy-in stream while piece i-1 computes and piece i-2 drains D2H.
 // in[k]/out[k]: host arrays with per-element byte sizes in_sz[k]/out_sz[k] (0 = unused, NULL allowed).
 template <class Fn>
-int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, const size_t* in_sz, int n_out, uint8_t* const* out,
-                 const size_t* out_sz, Fn&& enqueue) {
+int run_pipeline_pieces(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, const size_t* in_sz, int n_out, uint8_t* const* out,
+                        const size_t* out_sz, Fn&& enqueue) {
     if (n == 0) return 0;
     const size_t FIRST = (size_t)ECB200_FIRST_CHUNK;   // the first piece is short, so the (unoverlapped) first H2D is short
     auto piece = [&](size_t ch, size_t& off, size_t& cnt) {
@@ -695,6 +695,20 @@ int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, co
     return 0;
 }
 
+// The caller owns its buffers again the moment an entry point returns - also when it returns an error: a failure in the middle
+// of the pipeline (allocation, launch, copy) must not leave DMA transfers from / into caller memory in flight.
+template <class Fn>
+int run_pipeline(ecb200_ctx* c, size_t n, int n_in, const uint8_t* const* in, const size_t* in_sz, int n_out, uint8_t* const* out,
+                 const size_t* out_sz, Fn&& enqueue) {
+    const int r = run_pipeline_pieces(c, n, n_in, in, in_sz, n_out, out, out_sz, enqueue);
+    if (r) {
+        cudaStreamSynchronize(c->copy_in);
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->copy_out);
+        cudaGetLastError();      // the error that ended the pipeline is already in c->err
+    }
+    return r;
+}
 
 // Secret scalars (signing keys, nonces, FLAG_CT scalars) pass through the context's staging buffers, which live until
 // ecb200_destroy and are reused by later calls.  The reference zeroizes such values (Zeroizing / ZeroizeOnDrop on
